@@ -1,0 +1,396 @@
+// K1b — AdaRound fake-quant: floor + rectified-sigmoid soft / hard rounding, with the rounding
+// regulariser sum(1-|2h-1|^b) and its gradient folded into the same pass over (w, alpha).
+//   reference arithmetic: quant/adaptive_rounding.py:49-74, quant/block_recon.py:167-174,
+//   quant/channelQuant.py:66-78 (sym-aware bounds via qmin/qmax)
+// Single-tensor entry points serve the nn.Module surface; the *_mt entry points run every
+// QuantModule of a reconstruction unit in one launch from a device-resident descriptor table.
+#include "ssq_common.cuh"
+
+namespace ssq {
+
+__device__ __forceinline__ float clampf_(float v, float lo, float hi) {
+    return v < lo ? lo : (v > hi ? hi : v);
+}
+
+struct AdaOut { float y, q, reg; };
+
+template <bool SOFT, bool REG>
+__device__ __forceinline__ AdaOut ada_fwd_one(float w, float a, float d, float z, float qmin, float qmax, float b) {
+    AdaOut o;
+    float fl = floorf(__fdiv_rn(w, d));
+    float r;
+    o.reg = 0.f;
+    if (SOFT) {
+        r = rect_sigmoid(a);
+        if (REG) o.reg = reg_term(r, b);
+    } else {
+        r = (a >= 0.f) ? 1.f : 0.f;
+    }
+    o.q = clampf_(__fadd_rn(__fadd_rn(fl, r), z), qmin, qmax);
+    o.y = __fmul_rn(__fsub_rn(o.q, z), d);
+    return o;
+}
+
+// galpha for one element: reconstruction path + regulariser path
+template <bool REC, bool REG>
+__device__ __forceinline__ float ada_bwd_one(float g, float w, float a, float d, float z, float qmin, float qmax,
+                                             float b, float lam_g) {
+    float h;
+    float dh = rect_sigmoid_grad(a, h);
+    float out = 0.f;
+    if (REC) {
+        float xi = __fadd_rn(__fadd_rn(floorf(__fdiv_rn(w, d)), h), z);
+        bool inside = (xi >= qmin) && (xi <= qmax);
+        out = inside ? (g * d) * dh : 0.f;
+    }
+    if (REG) out += lam_g * reg_term_grad(h, b) * dh;
+    return out;
+}
+
+// ---- single tensor, forward -------------------------------------------------------------------
+// VEC: inner % 4 == 0 and 16B-aligned pointers. Each CTA walks tiles of SSQ_THREADS*4 elements.
+template <bool VEC, bool SOFT, bool REG>
+__global__ void __launch_bounds__(SSQ_THREADS)
+ada_fwd_kernel(const float* __restrict__ w, const float* __restrict__ alpha, const float* __restrict__ delta,
+               const float* __restrict__ zp, float* __restrict__ wq, float* __restrict__ codes,
+               int64_t n, int64_t inner, int64_t nchan, float qmin, float qmax,
+               const float* __restrict__ b_dev, float lambda, float* __restrict__ reg_out, WsView ws) {
+    __shared__ double smem[32];
+    float b = 0.f;
+    if (REG) b = __ldg(b_dev);
+    const bool reg_on = REG && (b > 0.f);
+    double acc[1] = {0.0};
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    if (VEC) {
+        const int64_t n4 = n >> 2, inner4 = inner >> 2;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+            int64_t c = (nchan == 1) ? 0 : ((i / inner4) % nchan);
+            float d = __ldg(delta + c), z = __ldg(zp + c);
+            float4 wv = ld_stream4(w + i * 4), av = ld_stream4(alpha + i * 4), y, q;
+            float rsum = 0.f;
+            AdaOut o;
+#define ONE(F) o = reg_on ? ada_fwd_one<SOFT, true>(wv.F, av.F, d, z, qmin, qmax, b) \
+                          : ada_fwd_one<SOFT, false>(wv.F, av.F, d, z, qmin, qmax, b); \
+               y.F = o.y; q.F = o.q; rsum += o.reg;
+            ONE(x) ONE(y) ONE(z) ONE(w)
+#undef ONE
+            st_stream4(wq + i * 4, y);
+            if (codes) st_stream4(codes + i * 4, q);
+            acc[0] += (double)rsum;
+        }
+    } else {
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+            int64_t c = (nchan == 1) ? 0 : ((i / inner) % nchan);
+            float d = __ldg(delta + c), z = __ldg(zp + c);
+            AdaOut o = reg_on ? ada_fwd_one<SOFT, true>(w[i], alpha[i], d, z, qmin, qmax, b)
+                              : ada_fwd_one<SOFT, false>(w[i], alpha[i], d, z, qmin, qmax, b);
+            wq[i] = o.y;
+            if (codes) codes[i] = o.q;
+            acc[0] += (double)o.reg;
+        }
+    }
+    if (!REG) return;
+    block_sum<1>(acc, smem);
+    if (grid_finish<1>(acc, ws, 0, blockIdx.x, gridDim.x, smem) && threadIdx.x == 0)
+        reg_out[0] = reg_on ? (float)((double)lambda * acc[0]) : 0.f;
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(SSQ_THREADS)
+ada_bwd_kernel(const float* __restrict__ gwq, const float* __restrict__ w, const float* __restrict__ alpha,
+               const float* __restrict__ delta, const float* __restrict__ zp, float* __restrict__ galpha,
+               int64_t n, int64_t inner, int64_t nchan, float qmin, float qmax,
+               const float* __restrict__ b_dev, float lambda, const float* __restrict__ greg, int accumulate) {
+    float b = b_dev ? __ldg(b_dev) : 0.f;
+    const bool reg_on = b_dev && (b > 0.f);
+    const float lam_g = reg_on ? lambda * (greg ? __ldg(greg) : 1.f) : 0.f;
+    const bool rec = gwq != nullptr;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    auto one = [&](float g, float wv, float av, float d, float z) -> float {
+        if (rec) return reg_on ? ada_bwd_one<true, true>(g, wv, av, d, z, qmin, qmax, b, lam_g)
+                               : ada_bwd_one<true, false>(g, wv, av, d, z, qmin, qmax, b, lam_g);
+        return reg_on ? ada_bwd_one<false, true>(g, wv, av, d, z, qmin, qmax, b, lam_g) : 0.f;
+    };
+    if (VEC) {
+        const int64_t n4 = n >> 2, inner4 = inner >> 2;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+            int64_t c = (nchan == 1) ? 0 : ((i / inner4) % nchan);
+            float d = __ldg(delta + c), z = __ldg(zp + c);
+            float4 wv = ld_stream4(w + i * 4), av = ld_stream4(alpha + i * 4);
+            float4 g = rec ? ld_stream4(gwq + i * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 o;
+            o.x = one(g.x, wv.x, av.x, d, z); o.y = one(g.y, wv.y, av.y, d, z);
+            o.z = one(g.z, wv.z, av.z, d, z); o.w = one(g.w, wv.w, av.w, d, z);
+            if (accumulate) {
+                float4 p = *reinterpret_cast<const float4*>(galpha + i * 4);
+                o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+            }
+            st_stream4(galpha + i * 4, o);
+        }
+    } else {
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+            int64_t c = (nchan == 1) ? 0 : ((i / inner) % nchan);
+            float o = one(rec ? gwq[i] : 0.f, w[i], alpha[i], __ldg(delta + c), __ldg(zp + c));
+            galpha[i] = accumulate ? galpha[i] + o : o;
+        }
+    }
+}
+
+// alpha init: rest = w/delta - floor(w/delta); alpha = -log((zeta-gamma)/(rest-gamma) - 1)
+__global__ void __launch_bounds__(SSQ_THREADS)
+ada_init_alpha_kernel(const float* __restrict__ w, const float* __restrict__ delta, float* __restrict__ alpha,
+                      int64_t n, int64_t inner, int64_t nchan) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int64_t c = (nchan == 1) ? 0 : ((i / inner) % nchan);
+        float u = __fdiv_rn(w[i], __ldg(delta + c));
+        float rest = __fsub_rn(u, floorf(u));
+        float t = __fsub_rn(__fdiv_rn(SSQ_STRETCH, __fsub_rn(rest, SSQ_GAMMA)), 1.0f);
+        alpha[i] = -logf(t);
+    }
+}
+
+// ---- stand-alone regulariser ---------------------------------------------------------------
+__global__ void __launch_bounds__(SSQ_THREADS)
+round_reg_fwd_kernel(const float* __restrict__ v, int64_t n, const float* __restrict__ b_dev, float lambda,
+                     float* __restrict__ reg_out, WsView ws) {
+    __shared__ double smem[32];
+    const float b = __ldg(b_dev);
+    double acc[1] = {0.0};
+    if (b > 0.f) {
+        const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+            acc[0] += (double)reg_term(rect_sigmoid(v[i]), b);
+    }
+    block_sum<1>(acc, smem);
+    if (grid_finish<1>(acc, ws, 0, blockIdx.x, gridDim.x, smem) && threadIdx.x == 0)
+        reg_out[0] = (b > 0.f) ? (float)((double)lambda * acc[0]) : 0.f;
+}
+
+__global__ void __launch_bounds__(SSQ_THREADS)
+round_reg_bwd_kernel(const float* __restrict__ v, int64_t n, const float* __restrict__ b_dev, float lambda,
+                     const float* __restrict__ greg, float* __restrict__ gv, int accumulate) {
+    const float b = __ldg(b_dev);
+    const float lam_g = (b > 0.f) ? lambda * (greg ? __ldg(greg) : 1.f) : 0.f;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float o = 0.f;
+        if (b > 0.f) {
+            float h;
+            float dh = rect_sigmoid_grad(v[i], h);
+            o = lam_g * reg_term_grad(h, b) * dh;
+        }
+        gv[i] = accumulate ? gv[i] + o : o;
+    }
+}
+
+// ---- multi-tensor ----------------------------------------------------------------------------
+struct MtTable { ssq_adaround_desc d[SSQ_MT_MAX]; };   // lives in kernel parameter space
+
+__device__ __forceinline__ int find_desc(const MtTable& table, int count, int64_t tile) {
+    int lo = 0;
+#pragma unroll 1
+    for (int i = 1; i < count; ++i) if (table.d[i].tile_begin <= tile) lo = i;
+    return lo;
+}
+
+template <bool SOFT>
+__global__ void __launch_bounds__(SSQ_THREADS)
+ada_fwd_mt_kernel(const __grid_constant__ MtTable table, int count, int64_t total_tiles,
+                  const float* __restrict__ b_dev, float lambda, float* __restrict__ reg_out, WsView ws) {
+    __shared__ double smem[32];
+    __shared__ ssq_adaround_desc D;
+    const float b = (SOFT && b_dev) ? __ldg(b_dev) : 0.f;
+    const bool reg_on = SOFT && reg_out && (b > 0.f);
+    double acc[1] = {0.0};
+    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x == 0) D = table.d[find_desc(table, count, tile)];
+        __syncthreads();
+        const int64_t e0 = (tile - D.tile_begin) * SSQ_MT_TILE;
+        const int64_t e1 = e0 + SSQ_MT_TILE < D.n ? e0 + SSQ_MT_TILE : D.n;
+        const bool vec = (D.inner % 4 == 0) && aligned16(D.w) && aligned16(D.alpha) && aligned16(D.wq);
+        if (vec) {
+            const int64_t inner4 = D.inner >> 2;
+            for (int64_t i = (e0 >> 2) + threadIdx.x; i < (e1 >> 2); i += blockDim.x) {
+                int64_t c = (D.nchan == 1) ? 0 : ((i / inner4) % D.nchan);
+                float d = __ldg(D.delta + c), z = __ldg(D.zero_point + c);
+                float4 wv = ld_stream4(D.w + i * 4), av = ld_stream4(D.alpha + i * 4), y;
+                float rsum = 0.f;
+                AdaOut o;
+#define ONE(F) o = reg_on ? ada_fwd_one<SOFT, true>(wv.F, av.F, d, z, D.qmin, D.qmax, b) \
+                          : ada_fwd_one<SOFT, false>(wv.F, av.F, d, z, D.qmin, D.qmax, b); \
+               y.F = o.y; rsum += o.reg;
+                ONE(x) ONE(y) ONE(z) ONE(w)
+#undef ONE
+                st_stream4(D.wq + i * 4, y);
+                acc[0] += (double)rsum;
+            }
+        } else {
+            for (int64_t i = e0 + threadIdx.x; i < e1; i += blockDim.x) {
+                int64_t c = (D.nchan == 1) ? 0 : ((i / D.inner) % D.nchan);
+                float d = __ldg(D.delta + c), z = __ldg(D.zero_point + c);
+                AdaOut o = reg_on ? ada_fwd_one<SOFT, true>(D.w[i], D.alpha[i], d, z, D.qmin, D.qmax, b)
+                                  : ada_fwd_one<SOFT, false>(D.w[i], D.alpha[i], d, z, D.qmin, D.qmax, b);
+                D.wq[i] = o.y;
+                acc[0] += (double)o.reg;
+            }
+        }
+    }
+    if (!reg_out) return;
+    block_sum<1>(acc, smem);
+    if (grid_finish<1>(acc, ws, 0, blockIdx.x, gridDim.x, smem) && threadIdx.x == 0)
+        reg_out[0] = reg_on ? (float)((double)lambda * acc[0]) : 0.f;
+}
+
+__global__ void __launch_bounds__(SSQ_THREADS)
+ada_bwd_mt_kernel(const __grid_constant__ MtTable table, int count, int64_t total_tiles,
+                  const float* __restrict__ b_dev, float lambda) {
+    __shared__ ssq_adaround_desc D;
+    const float b = b_dev ? __ldg(b_dev) : 0.f;
+    const bool reg_on = b_dev && (b > 0.f);
+    const float lam_g = reg_on ? lambda : 0.f;
+    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x == 0) D = table.d[find_desc(table, count, tile)];
+        __syncthreads();
+        const int64_t e0 = (tile - D.tile_begin) * SSQ_MT_TILE;
+        const int64_t e1 = e0 + SSQ_MT_TILE < D.n ? e0 + SSQ_MT_TILE : D.n;
+        const bool vec = (D.inner % 4 == 0) && aligned16(D.w) && aligned16(D.alpha) && aligned16(D.gwq) && aligned16(D.galpha);
+        auto one = [&](float g, float wv, float av, float d, float z) -> float {
+            return reg_on ? ada_bwd_one<true, true>(g, wv, av, d, z, D.qmin, D.qmax, b, lam_g)
+                          : ada_bwd_one<true, false>(g, wv, av, d, z, D.qmin, D.qmax, b, lam_g);
+        };
+        if (vec) {
+            const int64_t inner4 = D.inner >> 2;
+            for (int64_t i = (e0 >> 2) + threadIdx.x; i < (e1 >> 2); i += blockDim.x) {
+                int64_t c = (D.nchan == 1) ? 0 : ((i / inner4) % D.nchan);
+                float d = __ldg(D.delta + c), z = __ldg(D.zero_point + c);
+                float4 wv = ld_stream4(D.w + i * 4), av = ld_stream4(D.alpha + i * 4), g = ld_stream4(D.gwq + i * 4), o;
+                o.x = one(g.x, wv.x, av.x, d, z); o.y = one(g.y, wv.y, av.y, d, z);
+                o.z = one(g.z, wv.z, av.z, d, z); o.w = one(g.w, wv.w, av.w, d, z);
+                st_stream4(D.galpha + i * 4, o);
+            }
+        } else {
+            for (int64_t i = e0 + threadIdx.x; i < e1; i += blockDim.x) {
+                int64_t c = (D.nchan == 1) ? 0 : ((i / D.inner) % D.nchan);
+                D.galpha[i] = one(D.gwq[i], D.w[i], D.alpha[i], __ldg(D.delta + c), __ldg(D.zero_point + c));
+            }
+        }
+    }
+}
+
+static inline int check_layout(int64_t n, int64_t inner, int64_t nchan) {
+    if (n < 0 || inner <= 0 || nchan <= 0 || n % inner != 0 || (n / inner) % nchan != 0) return SSQ_ERR_SIZE;
+    return SSQ_OK;
+}
+
+}  // namespace ssq
+
+using namespace ssq;
+
+extern "C" int ssq_fq_adaround_fwd(const float* w, const float* alpha, const float* delta, const float* zero_point,
+                                   float* wq, float* codes, int64_t n, int64_t inner, int64_t nchan,
+                                   float qmin, float qmax, int soft,
+                                   const float* b_dev, float lambda, float* reg_out,
+                                   void* ws, size_t ws_bytes, void* stream) {
+    if (n == 0) return SSQ_OK;
+    if (!w || !alpha || !delta || !zero_point || !wq) return SSQ_ERR_NULL;
+    if (int e = check_layout(n, inner, nchan)) return e;
+    const bool reg = reg_out != nullptr;
+    if (reg && (!b_dev || !soft)) return SSQ_ERR_MODE;
+    if (reg && (!ws || ws_bytes < ssq_ws_bytes(1))) return SSQ_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    bool vec = aligned16(w) && aligned16(alpha) && aligned16(wq) && (!codes || aligned16(codes)) && (inner % 4 == 0);
+    int64_t per_cta = (int64_t)SSQ_THREADS * (vec ? 4 : 1);
+    int grid = grid_for((n + per_cta - 1) / per_cta);
+    WsView v = ws_view(ws, 1);
+#define LAUNCH(V, S, R) ada_fwd_kernel<V, S, R><<<grid, SSQ_THREADS, 0, st>>>( \
+        w, alpha, delta, zero_point, wq, codes, n, inner, nchan, qmin, qmax, b_dev, lambda, reg_out, v)
+    if (vec) {
+        if (soft) { if (reg) LAUNCH(true, true, true); else LAUNCH(true, true, false); }
+        else LAUNCH(true, false, false);
+    } else {
+        if (soft) { if (reg) LAUNCH(false, true, true); else LAUNCH(false, true, false); }
+        else LAUNCH(false, false, false);
+    }
+#undef LAUNCH
+    return launch_status();
+}
+
+extern "C" int ssq_fq_adaround_bwd(const float* gwq, const float* w, const float* alpha, const float* delta,
+                                   const float* zero_point, float* galpha,
+                                   int64_t n, int64_t inner, int64_t nchan, float qmin, float qmax,
+                                   const float* b_dev, float lambda, const float* greg,
+                                   int accumulate, void* stream) {
+    if (n == 0) return SSQ_OK;
+    if (!w || !alpha || !delta || !zero_point || !galpha) return SSQ_ERR_NULL;
+    if (int e = check_layout(n, inner, nchan)) return e;
+    bool vec = (!gwq || aligned16(gwq)) && aligned16(w) && aligned16(alpha) && aligned16(galpha) && (inner % 4 == 0);
+    int64_t per_cta = (int64_t)SSQ_THREADS * (vec ? 4 : 1);
+    int grid = grid_for((n + per_cta - 1) / per_cta);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (vec) ada_bwd_kernel<true><<<grid, SSQ_THREADS, 0, st>>>(gwq, w, alpha, delta, zero_point, galpha, n, inner, nchan, qmin, qmax, b_dev, lambda, greg, accumulate);
+    else ada_bwd_kernel<false><<<grid, SSQ_THREADS, 0, st>>>(gwq, w, alpha, delta, zero_point, galpha, n, inner, nchan, qmin, qmax, b_dev, lambda, greg, accumulate);
+    return launch_status();
+}
+
+extern "C" int ssq_adaround_init_alpha(const float* w, const float* delta, float* alpha,
+                                       int64_t n, int64_t inner, int64_t nchan, void* stream) {
+    if (n == 0) return SSQ_OK;
+    if (!w || !delta || !alpha) return SSQ_ERR_NULL;
+    if (int e = check_layout(n, inner, nchan)) return e;
+    int grid = grid_for((n + SSQ_THREADS - 1) / SSQ_THREADS);
+    ada_init_alpha_kernel<<<grid, SSQ_THREADS, 0, (cudaStream_t)stream>>>(w, delta, alpha, n, inner, nchan);
+    return launch_status();
+}
+
+extern "C" int ssq_round_reg_fwd(const float* v, int64_t n, const float* b_dev, float lambda,
+                                 float* reg_out, void* ws, size_t ws_bytes, void* stream) {
+    if (!v || !b_dev || !reg_out) return SSQ_ERR_NULL;
+    if (n < 0) return SSQ_ERR_SIZE;
+    if (!ws || ws_bytes < ssq_ws_bytes(1)) return SSQ_ERR_WORKSPACE;
+    int grid = grid_for((n + SSQ_THREADS * 4 - 1) / (SSQ_THREADS * 4));
+    round_reg_fwd_kernel<<<grid, SSQ_THREADS, 0, (cudaStream_t)stream>>>(v, n, b_dev, lambda, reg_out, ws_view(ws, 1));
+    return launch_status();
+}
+
+extern "C" int ssq_round_reg_bwd(const float* v, int64_t n, const float* b_dev, float lambda,
+                                 const float* greg, float* gv, int accumulate, void* stream) {
+    if (n == 0) return SSQ_OK;
+    if (!v || !b_dev || !gv) return SSQ_ERR_NULL;
+    if (n < 0) return SSQ_ERR_SIZE;
+    int grid = grid_for((n + SSQ_THREADS * 4 - 1) / (SSQ_THREADS * 4));
+    round_reg_bwd_kernel<<<grid, SSQ_THREADS, 0, (cudaStream_t)stream>>>(v, n, b_dev, lambda, greg, gv, accumulate);
+    return launch_status();
+}
+
+extern "C" int ssq_fq_adaround_fwd_mt(const ssq_adaround_desc* table, int count, int64_t total_tiles,
+                                      int soft, const float* b_dev, float lambda, float* reg_out,
+                                      void* ws, size_t ws_bytes, void* stream) {
+    if (count == 0 || total_tiles == 0) return SSQ_OK;
+    if (!table) return SSQ_ERR_NULL;
+    if (count < 0 || count > SSQ_MT_MAX || total_tiles < 0) return SSQ_ERR_SIZE;
+    if (reg_out && (!ws || ws_bytes < ssq_ws_bytes(1))) return SSQ_ERR_WORKSPACE;
+    if (reg_out && !b_dev) return SSQ_ERR_MODE;
+    int grid = grid_for(total_tiles);
+    WsView v = ws_view(ws, 1);
+    cudaStream_t st = (cudaStream_t)stream;
+    MtTable t;
+    for (int i = 0; i < count; ++i) t.d[i] = table[i];
+    if (soft) ada_fwd_mt_kernel<true><<<grid, SSQ_THREADS, 0, st>>>(t, count, total_tiles, b_dev, lambda, reg_out, v);
+    else ada_fwd_mt_kernel<false><<<grid, SSQ_THREADS, 0, st>>>(t, count, total_tiles, b_dev, lambda, nullptr, v);
+    return launch_status();
+}
+
+extern "C" int ssq_fq_adaround_bwd_mt(const ssq_adaround_desc* table, int count, int64_t total_tiles,
+                                      const float* b_dev, float lambda, void* stream) {
+    if (count == 0 || total_tiles == 0) return SSQ_OK;
+    if (!table) return SSQ_ERR_NULL;
+    if (count < 0 || count > SSQ_MT_MAX || total_tiles < 0) return SSQ_ERR_SIZE;
+    int grid = grid_for(total_tiles);
+    MtTable t;
+    for (int i = 0; i < count; ++i) t.d[i] = table[i];
+    ada_bwd_mt_kernel<<<grid, SSQ_THREADS, 0, (cudaStream_t)stream>>>(t, count, total_tiles, b_dev, lambda);
+    return launch_status();
+}

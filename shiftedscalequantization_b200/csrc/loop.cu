@@ -1,0 +1,100 @@
+// Calibration-loop plumbing that lets one reconstruction iteration live inside a CUDA graph:
+//  - ssq_adam_step: torch.optim.Adam semantics (quant/block_recon.py:60,103) on one flat buffer per
+//    reconstruction unit, step count and learning rate read from device memory;
+//  - ssq_loop_advance: device-side iteration state (mini-batch indices = the reference's
+//    torch.randperm(N)[:B] stream, precomputed on the host: quant/block_recon.py:90;
+//    temperature b: quant/block_recon.py:185-202; lr: CosineAnnealingLR of :73).
+#include "ssq_common.cuh"
+
+namespace ssq {
+
+__global__ void __launch_bounds__(SSQ_THREADS)
+adam_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,
+            int64_t n, const float* __restrict__ lr_dev, double beta1d, double beta2d, double epsd,
+            const int64_t* __restrict__ step_dev) {
+    // host-side doubles of torch/optim/adam.py (_single_tensor_adam), evaluated per thread
+    const double t = (double)(*step_dev);
+    const double bc1 = 1.0 - pow(beta1d, t);
+    const double bc2 = 1.0 - pow(beta2d, t);
+    const float step_size = (float)((double)__ldg(lr_dev) / bc1);
+    const float bc2_sqrt = (float)sqrt(bc2);
+    // Python-double scalars, cast to fp32 by ATen when they meet an fp32 tensor
+    const float w1 = (float)(1.0 - beta1d);   // lerp weight (< 0.5 => m + w*(g-m))
+    const float w2 = (float)(1.0 - beta2d);
+    const float beta2 = (float)beta2d, eps = (float)epsd;
+    const bool vec = aligned16(param) && aligned16(grad) && aligned16(m) && aligned16(v);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    auto one = [&](float& p, float g, float& mm, float& vv) {
+        mm = mm + w1 * (g - mm);
+        vv = vv * beta2 + w2 * g * g;
+        float denom = sqrtf(vv) / bc2_sqrt + eps;
+        p = p - step_size * (mm / denom);
+    };
+    const int64_t n4 = vec ? (n >> 2) : 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 p4 = *reinterpret_cast<float4*>(param + i * 4);
+        float4 g4 = ld_stream4(grad + i * 4);
+        float4 m4 = *reinterpret_cast<float4*>(m + i * 4);
+        float4 v4 = *reinterpret_cast<float4*>(v + i * 4);
+        one(p4.x, g4.x, m4.x, v4.x); one(p4.y, g4.y, m4.y, v4.y);
+        one(p4.z, g4.z, m4.z, v4.z); one(p4.w, g4.w, m4.w, v4.w);
+        *reinterpret_cast<float4*>(param + i * 4) = p4;
+        *reinterpret_cast<float4*>(m + i * 4) = m4;
+        *reinterpret_cast<float4*>(v + i * 4) = v4;
+    }
+    for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        one(param[i], grad[i], m[i], v[i]);
+}
+
+__global__ void loop_advance_kernel(int64_t* step_dev, const int64_t* __restrict__ idx_table, int64_t* idx_live, int batch,
+                                    const float* __restrict__ b_table, float* b_live,
+                                    const float* __restrict__ lr_table, float* lr_live, int64_t n_steps) {
+    int64_t s = *step_dev;
+    if (s >= n_steps) s = n_steps - 1;   // replays past the schedule keep the last row
+    if (idx_table && idx_live)
+        for (int j = threadIdx.x; j < batch; j += blockDim.x) idx_live[j] = idx_table[s * batch + j];
+    if (threadIdx.x == 0) {
+        if (b_table && b_live) *b_live = b_table[s];
+        if (lr_table && lr_live) *lr_live = lr_table[s];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *step_dev = *step_dev + 1;
+}
+
+}  // namespace ssq
+
+using namespace ssq;
+
+extern "C" int ssq_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                             const float* lr_dev, double beta1, double beta2, double eps,
+                             const int64_t* step_dev, void* stream) {
+    if (n == 0) return SSQ_OK;
+    if (!param || !grad || !exp_avg || !exp_avg_sq || !lr_dev || !step_dev) return SSQ_ERR_NULL;
+    if (n < 0) return SSQ_ERR_SIZE;
+    int grid = grid_for((n + SSQ_THREADS * 4 - 1) / (SSQ_THREADS * 4));
+    adam_kernel<<<grid, SSQ_THREADS, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr_dev, beta1, beta2, eps, step_dev);
+    return launch_status();
+}
+
+extern "C" int ssq_loop_advance(int64_t* step_dev, const int64_t* idx_table, int64_t* idx_live, int batch,
+                                const float* b_table, float* b_live, const float* lr_table, float* lr_live,
+                                int64_t n_steps, void* stream) {
+    if (!step_dev) return SSQ_ERR_NULL;
+    if (n_steps <= 0 || batch < 0) return SSQ_ERR_SIZE;
+    loop_advance_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(step_dev, idx_table, idx_live, batch, b_table, b_live, lr_table, lr_live, n_steps);
+    return launch_status();
+}
+
+extern "C" int ssq_abi_version(void) { return SSQ_ABI_VERSION; }
+
+extern "C" const char* ssq_status_string(int status) {
+    switch (status) {
+        case SSQ_OK: return "ok";
+        case SSQ_ERR_NULL: return "required pointer is NULL";
+        case SSQ_ERR_SIZE: return "inconsistent or out-of-range size";
+        case SSQ_ERR_WORKSPACE: return "workspace missing or too small";
+        case SSQ_ERR_MODE: return "unknown mode / unsupported combination";
+        case SSQ_ERR_ALIGN: return "pointer not 4-byte aligned";
+        default: return status > 0 ? cudaGetErrorString((cudaError_t)status) : "unknown ssq status";
+    }
+}

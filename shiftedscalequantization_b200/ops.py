@@ -1,0 +1,532 @@
+"""Tensor-level entry points over the C-ABI, and the autograd Functions the quantiser modules use.
+
+PyTorch is plumbing here: it owns device memory and the stream; every arithmetic result comes from
+libssq_b200.so. All tensors must be CUDA fp32; anything else raises (there is no CPU path).
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import AdaRoundDesc, MT_MAX, MT_TILE, SHIFT_ADASHIFT, SHIFT_DEQUANT
+
+# --------------------------------------------------------------------------------------- plumbing
+_launch_count = 0          # kernels launched through this module (bench.py reports it)
+_ws_cache: dict = {}
+
+
+def launch_count() -> int:
+    return _launch_count
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _req(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a tensor, got {type(t)}")
+    if not t.is_cuda:
+        raise _lib.SsqError(f"{name}: tensor is on {t.device}; the ssq kernels are CUDA-only (no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise _lib.SsqError(f"{name}: dtype {t.dtype} not supported (fp32 only, as the reference)")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def workspace(device: torch.device, nbytes: int, tag: str = "default") -> torch.Tensor:
+    """Zero-initialised scratch for the deterministic reductions (tickets reset themselves).
+    One buffer per (device, tag); callers on the same stream may share it."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.zeros(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def _ws(t: torch.Tensor, nchan: int = 1, tag: str = "default") -> torch.Tensor:
+    return workspace(t.device, _lib.load().ssq_ws_bytes(int(nchan)), tag)
+
+
+def _call(name: str, *args) -> None:
+    global _launch_count
+    _lib.check(getattr(_lib.load(), name)(*args), name)
+    _launch_count += 1
+
+
+def channel_layout(x: torch.Tensor, delta: torch.Tensor) -> Tuple[int, int]:
+    """(inner, nchan) of the header's channel layout for a quantiser whose delta is a scalar
+    (per-tensor) or [C,1,...] along dim 0 (the reference's shapes, quant_layer.py:67-77)."""
+    n = x.numel()
+    c = delta.numel()
+    if c == 1:
+        return max(n, 1), 1
+    if x.dim() == 0 or x.shape[0] != c:
+        raise _lib.SsqError(f"delta has {c} channels but tensor shape is {tuple(x.shape)}")
+    return max(n // c, 1), c
+
+
+def scalar_dev(value: float, device) -> torch.Tensor:
+    return torch.tensor([float(value)], dtype=torch.float32, device=device)
+
+
+# --------------------------------------------------------------------------------------- K1a
+def fq_affine_fwd(x, delta, zero_point, qmin: float, qmax: float, in_scale=None, want_codes=False):
+    x = _req(x, "x"); delta = _req(delta, "delta"); zero_point = _req(zero_point, "zero_point")
+    inner, nchan = channel_layout(x, delta)
+    if in_scale is not None:
+        in_scale = _req(in_scale, "in_scale")
+        if in_scale.numel() != inner:
+            raise _lib.SsqError("in_scale must have IC*kh*kw elements")
+    y = torch.empty_like(x)
+    codes = torch.empty_like(x) if want_codes else None
+    _call("ssq_fq_affine_fwd", x.data_ptr(), delta.data_ptr(), zero_point.data_ptr(), _ptr(in_scale),
+          y.data_ptr(), _ptr(codes), x.numel(), inner, nchan, qmin, qmax, _stream(x))
+    return (y, codes) if want_codes else y
+
+
+def fq_affine_bwd(gy, x, delta, zero_point, qmin, qmax, need_gx=True, need_gparams=True):
+    gy = _req(gy, "gy"); x = _req(x, "x"); delta = _req(delta, "delta"); zero_point = _req(zero_point, "zero_point")
+    inner, nchan = channel_layout(x, delta)
+    gx = torch.empty_like(x) if need_gx else None
+    gd = torch.empty_like(delta) if need_gparams else None
+    gz = torch.empty_like(zero_point) if need_gparams else None
+    ws = _ws(x, nchan)
+    _call("ssq_fq_affine_bwd", gy.data_ptr(), x.data_ptr(), delta.data_ptr(), zero_point.data_ptr(),
+          _ptr(gx), _ptr(gd), _ptr(gz), x.numel(), inner, nchan, qmin, qmax, ws.data_ptr(), ws.numel(), _stream(x))
+    return gx, gd, gz
+
+
+class FakeQuantAffine(torch.autograd.Function):
+    """UniformAffineQuantizer.forward (quant/quant_layer.py:92-97) with its autograd."""
+
+    @staticmethod
+    def forward(ctx, x, delta, zero_point, qmin, qmax):
+        ctx.save_for_backward(x, delta, zero_point)
+        ctx.bounds = (qmin, qmax)
+        return fq_affine_fwd(x, delta, zero_point, qmin, qmax)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, delta, zero_point = ctx.saved_tensors
+        qmin, qmax = ctx.bounds
+        need_x, need_d, need_z = ctx.needs_input_grad[:3]
+        gx, gd, gz = fq_affine_bwd(gy, x, delta, zero_point, qmin, qmax, need_gx=need_x, need_gparams=need_d or need_z)
+        if gx is not None and gx.shape != x.shape:
+            gx = gx.view_as(x)
+        return gx, (gd if need_d else None), (gz if need_z else None), None, None
+
+
+# --------------------------------------------------------------------------------------- K1b
+def adaround_fwd(w, alpha, delta, zero_point, qmin, qmax, soft: bool, b_dev=None, lam: float = 0.0,
+                 want_codes=False, want_reg=False):
+    w = _req(w, "w"); alpha = _req(alpha, "alpha"); delta = _req(delta, "delta"); zero_point = _req(zero_point, "zero_point")
+    if alpha.shape != w.shape:
+        raise _lib.SsqError("alpha must have the weight's shape")
+    inner, nchan = channel_layout(w, delta)
+    wq = torch.empty_like(w)
+    codes = torch.empty_like(w) if want_codes else None
+    reg = torch.empty(1, dtype=torch.float32, device=w.device) if want_reg else None
+    ws = _ws(w, 1) if want_reg else None
+    _call("ssq_fq_adaround_fwd", w.data_ptr(), alpha.data_ptr(), delta.data_ptr(), zero_point.data_ptr(),
+          wq.data_ptr(), _ptr(codes), w.numel(), inner, nchan, qmin, qmax, int(bool(soft)),
+          _ptr(b_dev), float(lam), _ptr(reg), _ptr(ws), 0 if ws is None else ws.numel(), _stream(w))
+    out = [wq]
+    if want_codes:
+        out.append(codes)
+    if want_reg:
+        out.append(reg)
+    return out[0] if len(out) == 1 else tuple(out)
+
+
+def adaround_bwd(gwq, w, alpha, delta, zero_point, qmin, qmax, b_dev=None, lam: float = 0.0, greg=None,
+                 out=None, accumulate=False):
+    w = _req(w, "w"); alpha = _req(alpha, "alpha"); delta = _req(delta, "delta"); zero_point = _req(zero_point, "zero_point")
+    if gwq is not None:
+        gwq = _req(gwq, "gwq")
+    inner, nchan = channel_layout(w, delta)
+    galpha = out if out is not None else torch.empty_like(alpha)
+    _call("ssq_fq_adaround_bwd", _ptr(gwq), w.data_ptr(), alpha.data_ptr(), delta.data_ptr(), zero_point.data_ptr(),
+          galpha.data_ptr(), w.numel(), inner, nchan, qmin, qmax, _ptr(b_dev), float(lam), _ptr(greg),
+          int(bool(accumulate)), _stream(w))
+    return galpha
+
+
+def adaround_init_alpha(w, delta):
+    w = _req(w, "w"); delta = _req(delta, "delta")
+    inner, nchan = channel_layout(w, delta)
+    alpha = torch.empty_like(w)
+    _call("ssq_adaround_init_alpha", w.data_ptr(), delta.data_ptr(), alpha.data_ptr(), w.numel(), inner, nchan, _stream(w))
+    return alpha
+
+
+class AdaRoundSoft(torch.autograd.Function):
+    """AdaRoundQuantizer soft forward (quant/adaptive_rounding.py:49-59); gradient flows to alpha only
+    (weight sees floor() => zero gradient in the reference; delta/zero_point are never optimised here)."""
+
+    @staticmethod
+    def forward(ctx, w, alpha, delta, zero_point, qmin, qmax):
+        ctx.save_for_backward(w, alpha, delta, zero_point)
+        ctx.bounds = (qmin, qmax)
+        return adaround_fwd(w, alpha, delta, zero_point, qmin, qmax, soft=True)
+
+    @staticmethod
+    def backward(ctx, gwq):
+        w, alpha, delta, zero_point = ctx.saved_tensors
+        qmin, qmax = ctx.bounds
+        galpha = adaround_bwd(gwq, w, alpha, delta, zero_point, qmin, qmax) if ctx.needs_input_grad[1] else None
+        return None, galpha, None, None, None, None
+
+
+def round_reg_fwd(v, b_dev, lam):
+    v = _req(v, "v")
+    reg = torch.empty(1, dtype=torch.float32, device=v.device)
+    ws = _ws(v, 1)
+    _call("ssq_round_reg_fwd", v.data_ptr(), v.numel(), b_dev.data_ptr(), float(lam), reg.data_ptr(),
+          ws.data_ptr(), ws.numel(), _stream(v))
+    return reg
+
+
+def round_reg_bwd(v, b_dev, lam, greg=None, out=None, accumulate=False):
+    v = _req(v, "v")
+    gv = out if out is not None else torch.empty_like(v)
+    _call("ssq_round_reg_bwd", v.data_ptr(), v.numel(), b_dev.data_ptr(), float(lam), _ptr(greg), gv.data_ptr(),
+          int(bool(accumulate)), _stream(v))
+    return gv
+
+
+class RoundReg(torch.autograd.Function):
+    """lambda * sum(1 - |2h(v)-1|^b)  (quant/block_recon.py:173-174); returns a 0-dim tensor."""
+
+    @staticmethod
+    def forward(ctx, v, b_dev, lam):
+        ctx.save_for_backward(v, b_dev)
+        ctx.lam = lam
+        return round_reg_fwd(v, b_dev, lam).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        v, b_dev = ctx.saved_tensors
+        greg = g.reshape(1).contiguous()
+        return round_reg_bwd(v, b_dev, ctx.lam, greg=greg), None, None
+
+
+# multi-tensor AdaRound -------------------------------------------------------------------------
+class AdaRoundTable:
+    """Host-side descriptor table for the *_mt launches (one reconstruction unit)."""
+
+    def __init__(self, entries: Sequence[dict]):
+        if not 0 < len(entries) <= MT_MAX:
+            raise _lib.SsqError(f"a unit may hold 1..{MT_MAX} quantised layers, got {len(entries)}")
+        self.count = len(entries)
+        self.table = (AdaRoundDesc * self.count)()
+        self.keep = entries          # keeps the tensors alive
+        tile = 0
+        for i, e in enumerate(entries):
+            w = _req(e["w"], "w"); alpha = _req(e["alpha"], "alpha")
+            inner, nchan = channel_layout(w, e["delta"])
+            d = self.table[i]
+            d.w, d.alpha = w.data_ptr(), alpha.data_ptr()
+            d.delta, d.zero_point = _req(e["delta"], "delta").data_ptr(), _req(e["zero_point"], "zp").data_ptr()
+            d.wq = e["wq"].data_ptr()
+            d.gwq = 0
+            d.galpha = e["galpha"].data_ptr() if e.get("galpha") is not None else 0
+            d.n, d.inner, d.nchan = w.numel(), inner, nchan
+            d.tile_begin = tile
+            d.qmin, d.qmax = e["qmin"], e["qmax"]
+            tile += (w.numel() + MT_TILE - 1) // MT_TILE
+        self.total_tiles = tile
+        self.device = entries[0]["w"].device
+
+    def forward(self, soft: bool, b_dev=None, lam: float = 0.0, reg_out=None):
+        ws = workspace(self.device, _lib.load().ssq_ws_bytes(1), "mt") if reg_out is not None else None
+        _call("ssq_fq_adaround_fwd_mt", self.table, self.count, self.total_tiles, int(bool(soft)), _ptr(b_dev),
+              float(lam), _ptr(reg_out), _ptr(ws), 0 if ws is None else ws.numel(),
+              torch.cuda.current_stream(self.device).cuda_stream)
+
+    def backward(self, gwqs: Sequence[torch.Tensor], b_dev=None, lam: float = 0.0):
+        for i, g in enumerate(gwqs):
+            self.table[i].gwq = _req(g, "gwq").data_ptr()
+        _call("ssq_fq_adaround_bwd_mt", self.table, self.count, self.total_tiles, _ptr(b_dev), float(lam),
+              torch.cuda.current_stream(self.device).cuda_stream)
+
+
+# --------------------------------------------------------------------------------------- K1c
+def shift_probs_fwd(alpha, reg_mode: int = -1, b_dev=None, lam: float = 0.0, want_reg=False):
+    alpha = _req(alpha, "alpha")
+    S = alpha.shape[-1]
+    groups = alpha.numel() // S
+    p = torch.empty_like(alpha)
+    reg = torch.empty(1, dtype=torch.float32, device=alpha.device) if want_reg else None
+    ws = _ws(alpha, 1) if want_reg else None
+    _call("ssq_shift_probs_fwd", alpha.data_ptr(), p.data_ptr(), groups, S, int(reg_mode), _ptr(b_dev), float(lam),
+          _ptr(reg), _ptr(ws), 0 if ws is None else ws.numel(), _stream(alpha))
+    return (p, reg) if want_reg else p
+
+
+def shift_probs_bwd(alpha, gp, reg_mode: int = -1, b_dev=None, lam: float = 0.0, greg=None):
+    alpha = _req(alpha, "alpha")
+    S = alpha.shape[-1]
+    groups = alpha.numel() // S
+    if gp is not None:
+        gp = _req(gp, "gp")
+    galpha = torch.empty_like(alpha)
+    _call("ssq_shift_probs_bwd", alpha.data_ptr(), _ptr(gp), galpha.data_ptr(), groups, S, int(reg_mode), _ptr(b_dev),
+          float(lam), _ptr(greg), _stream(alpha))
+    return galpha
+
+
+class ShiftProbs(torch.autograd.Function):
+    """p = clamp(softmax(alpha,-1)*1.2-0.1, 0, 1)  (quant/channelQuant.py:120-121)."""
+
+    @staticmethod
+    def forward(ctx, alpha):
+        ctx.save_for_backward(alpha)
+        return shift_probs_fwd(alpha)
+
+    @staticmethod
+    def backward(ctx, gp):
+        (alpha,) = ctx.saved_tensors
+        return shift_probs_bwd(alpha, gp)
+
+
+class ShiftProbsReg(torch.autograd.Function):
+    """regulariser on the group probabilities: mode 0 entropy, mode 1 pow (see include/ssq_b200.h)."""
+
+    @staticmethod
+    def forward(ctx, alpha, reg_mode, b_dev, lam):
+        ctx.save_for_backward(alpha, b_dev) if b_dev is not None else ctx.save_for_backward(alpha)
+        ctx.cfg = (reg_mode, lam, b_dev is not None)
+        _, reg = shift_probs_fwd(alpha, reg_mode, b_dev, lam, want_reg=True)
+        return reg.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        reg_mode, lam, has_b = ctx.cfg
+        alpha = ctx.saved_tensors[0]
+        b_dev = ctx.saved_tensors[1] if has_b else None
+        return shift_probs_bwd(alpha, None, reg_mode, b_dev, lam, greg=g.reshape(1).contiguous()), None, None, None
+
+
+def _shift_dims(w: torch.Tensor, per_element: bool):
+    oc = w.shape[0]
+    ic = w.shape[1] if w.dim() > 1 else 1
+    kk = w.numel() // (oc * ic)
+    if per_element:
+        return oc, ic * kk, 1
+    return oc, ic, kk
+
+
+def fq_shift_fwd(w, shift_delta, delta, zero_point, p, beta, mode, hard_targets, hard_round, qmin, qmax, per_element):
+    w = _req(w, "w"); shift_delta = _req(shift_delta, "shift_delta"); p = _req(p, "p")
+    delta = _req(delta, "delta"); zero_point = _req(zero_point, "zero_point")
+    if beta is not None:
+        beta = _req(beta, "beta")
+    oc, ic, kk = _shift_dims(w, per_element)
+    S = p.shape[-1]
+    y = torch.empty_like(w)
+    _call("ssq_fq_shift_fwd", w.data_ptr(), shift_delta.data_ptr(), delta.data_ptr(), zero_point.data_ptr(), p.data_ptr(),
+          _ptr(beta), y.data_ptr(), oc, ic, kk, S, int(per_element), int(mode), int(bool(hard_targets)),
+          int(bool(hard_round)), qmin, qmax, _stream(w))
+    return y
+
+
+def fq_shift_bwd(gy, w, shift_delta, delta, zero_point, p, beta, mode, hard_round, qmin, qmax, per_element, need_gbeta):
+    gy = _req(gy, "gy"); w = _req(w, "w"); p = _req(p, "p")
+    oc, ic, kk = _shift_dims(w, per_element)
+    S = p.shape[-1]
+    gp = torch.empty_like(p)
+    gbeta = torch.empty_like(w) if (need_gbeta and beta is not None) else None
+    nbytes = _lib.load().ssq_shift_bwd_ws_bytes(oc, ic, kk, S, int(per_element))
+    ws = workspace(w.device, nbytes, "shift")
+    _call("ssq_fq_shift_bwd", gy.data_ptr(), w.data_ptr(), shift_delta.data_ptr(), delta.data_ptr(), zero_point.data_ptr(),
+          p.data_ptr(), _ptr(beta), gp.data_ptr(), _ptr(gbeta), oc, ic, kk, S, int(per_element), int(mode),
+          int(bool(hard_round)), qmin, qmax, ws.data_ptr(), ws.numel(), _stream(w))
+    return gp, gbeta
+
+
+class ShiftMix(torch.autograd.Function):
+    """ChannelQuant 'learned_hard_sigmoid' / 'adaShift' soft forward (quant/channelQuant.py:49-64,96-118)."""
+
+    @staticmethod
+    def forward(ctx, p, beta, w, shift_delta, delta, zero_point, mode, hard_round, qmin, qmax, per_element):
+        ctx.save_for_backward(p, beta if beta is not None else p.new_empty(0), w, shift_delta, delta, zero_point)
+        ctx.cfg = (mode, hard_round, qmin, qmax, per_element, beta is not None)
+        return fq_shift_fwd(w, shift_delta, delta, zero_point, p, beta, mode, False, hard_round, qmin, qmax, per_element)
+
+    @staticmethod
+    def backward(ctx, gy):
+        p, beta, w, shift_delta, delta, zero_point = ctx.saved_tensors
+        mode, hard_round, qmin, qmax, per_element, has_beta = ctx.cfg
+        beta = beta if has_beta else None
+        need_gbeta = has_beta and ctx.needs_input_grad[1] and not hard_round
+        gp, gbeta = fq_shift_bwd(gy, w, shift_delta, delta, zero_point, p, beta, mode, hard_round, qmin, qmax,
+                                 per_element, need_gbeta)
+        return gp, (gbeta if need_gbeta else None), None, None, None, None, None, None, None, None, None
+
+
+# --------------------------------------------------------------------------------------- K2
+def mse_scale_search(x2d, n_levels: int, symmetric: bool, p_norm: float = 2.4):
+    """x2d: [rows, k]. Returns delta, zero_point, raw_zero_point, best_score (fp32 [rows]) and index (int32)."""
+    x2d = _req(x2d, "x")
+    rows, k = x2d.shape
+    dev = x2d.device
+    delta = torch.empty(rows, dtype=torch.float32, device=dev)
+    zp = torch.empty_like(delta); raw = torch.empty_like(delta); score = torch.empty_like(delta)
+    idx = torch.empty(rows, dtype=torch.int32, device=dev)
+    ws = workspace(dev, _lib.load().ssq_mse_scale_search_ws_bytes(rows, k), "search")
+    _call("ssq_mse_scale_search", x2d.data_ptr(), rows, k, int(n_levels), int(bool(symmetric)), float(p_norm),
+          delta.data_ptr(), zp.data_ptr(), raw.data_ptr(), score.data_ptr(), idx.data_ptr(),
+          ws.data_ptr(), ws.numel(), _stream(x2d))
+    return delta, zp, raw, score, idx
+
+
+def row_minmax(x2d):
+    x2d = _req(x2d, "x")
+    rows, k = x2d.shape
+    mn = torch.empty(rows, dtype=torch.float32, device=x2d.device)
+    mx = torch.empty_like(mn)
+    done = 0
+    while done < rows:   # gridDim.y limit
+        r = min(rows - done, 65535)
+        ws = _ws(x2d, r, "search")
+        _call("ssq_row_minmax", x2d[done:].data_ptr(), r, k, mn[done:].data_ptr(), mx[done:].data_ptr(),
+              ws.data_ptr(), ws.numel(), _stream(x2d))
+        done += r
+    return mn, mx
+
+
+def inp_scale_search(w2d, delta, raw_zero_point, cand, x_range: float, lo: float, hi: float, inp_scale):
+    """w2d [oc,k]; updates inp_scale ([k]) in place and returns it."""
+    w2d = _req(w2d, "w"); delta = _req(delta, "delta"); raw_zero_point = _req(raw_zero_point, "raw_zero_point")
+    cand = _req(cand, "cand"); inp_scale = _req(inp_scale, "inp_scale")
+    oc, k = w2d.shape
+    ws = workspace(w2d.device, _lib.load().ssq_inp_scale_search_ws_bytes(k), "inpscale")
+    _call("ssq_inp_scale_search", w2d.data_ptr(), delta.data_ptr(), raw_zero_point.data_ptr(), cand.data_ptr(),
+          cand.numel(), float(x_range), float(lo), float(hi), inp_scale.data_ptr(), oc, k,
+          ws.data_ptr(), ws.numel(), _stream(w2d))
+    return inp_scale
+
+
+# --------------------------------------------------------------------------------------- K3
+LOSS_MODES = {"mse": 0, "fisher_diag": 1, "fisher_full": 2}
+
+
+def _loss_dims(pred: torch.Tensor):
+    batch = pred.shape[0]
+    per_sample = pred.numel() // max(batch, 1)
+    chan = pred.shape[1] if pred.dim() > 1 else 1
+    denom = pred.numel() / chan          # mean over everything but dim 1 (quant_layer.py:30)
+    return batch, per_sample, float(denom)
+
+
+def recon_loss(pred, tgt, p: float = 2.0, mode: str = "mse", fisher=None, tgt_index=None, want_grad=True,
+               gscale=None):
+    """Returns (loss[1], dpred or None). With tgt_index, tgt/fisher are the full cached tensors."""
+    pred = _req(pred, "pred"); tgt = _req(tgt, "tgt")
+    if fisher is not None:
+        fisher = _req(fisher, "fisher")
+    batch, per_sample, denom = _loss_dims(pred)
+    if tgt_index is None and tgt.shape != pred.shape:
+        raise _lib.SsqError("pred/tgt shape mismatch")
+    loss = torch.empty(1, dtype=torch.float32, device=pred.device)
+    dpred = torch.empty_like(pred) if want_grad else None
+    ws = _ws(pred, batch if mode == "fisher_full" else 1, "loss")
+    _call("ssq_recon_loss", pred.data_ptr(), tgt.data_ptr(), _ptr(fisher), _ptr(tgt_index), loss.data_ptr(),
+          _ptr(dpred), batch, per_sample, denom, LOSS_MODES[mode], float(p), _ptr(gscale),
+          ws.data_ptr(), ws.numel(), _stream(pred))
+    return loss, dpred
+
+
+def recon_loss_bwd(pred, tgt, gloss, p: float = 2.0, mode: str = "mse", fisher=None, tgt_index=None):
+    pred = _req(pred, "pred"); tgt = _req(tgt, "tgt")
+    batch, per_sample, denom = _loss_dims(pred)
+    dpred = torch.empty_like(pred)
+    ws = _ws(pred, batch if mode == "fisher_full" else 1, "loss")
+    _call("ssq_recon_loss_bwd", pred.data_ptr(), tgt.data_ptr(), _ptr(fisher), _ptr(tgt_index), gloss.data_ptr(),
+          dpred.data_ptr(), batch, per_sample, denom, LOSS_MODES[mode], float(p), ws.data_ptr(), ws.numel(),
+          _stream(pred))
+    return dpred
+
+
+class ReconLoss(torch.autograd.Function):
+    """lp_loss(pred, tgt, p) / Fisher losses as one reduction (quant/quant_layer.py:25-32,
+    quant/block_recon.py:154-162). Gradient flows to pred only."""
+
+    @staticmethod
+    def forward(ctx, pred, tgt, p, mode, fisher):
+        loss, _ = recon_loss(pred, tgt, p, mode, fisher, want_grad=False)
+        ctx.save_for_backward(pred, tgt, fisher if fisher is not None else pred.new_empty(0))
+        ctx.cfg = (p, mode, fisher is not None)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, tgt, fisher = ctx.saved_tensors
+        p, mode, has_f = ctx.cfg
+        dpred = recon_loss_bwd(pred, tgt, g.reshape(1).contiguous(), p, mode, fisher if has_f else None)
+        return dpred.view_as(pred), None, None, None, None
+
+
+# --------------------------------------------------------------------------------------- affine / adam / loop
+def chan_affine_fwd(x, a, b):
+    x = _req(x, "x"); a = _req(a, "a"); b = _req(b, "b")
+    nchan = a.numel()
+    inner = x.numel() // (x.shape[0] * nchan) if x.numel() else 1
+    y = torch.empty_like(x)
+    _call("ssq_chan_affine_fwd", x.data_ptr(), a.data_ptr(), b.data_ptr(), y.data_ptr(), x.numel(), max(inner, 1), nchan, _stream(x))
+    return y
+
+
+def chan_affine_bwd(gy, x, a, need_gx=True):
+    gy = _req(gy, "gy"); x = _req(x, "x"); a = _req(a, "a")
+    nchan = a.numel()
+    inner = x.numel() // (x.shape[0] * nchan) if x.numel() else 1
+    gx = torch.empty_like(x) if need_gx else None
+    ga = torch.empty_like(a); gb = torch.empty_like(a)
+    ws = _ws(x, nchan)
+    _call("ssq_chan_affine_bwd", gy.data_ptr(), x.data_ptr(), a.data_ptr(), _ptr(gx), ga.data_ptr(), gb.data_ptr(),
+          x.numel(), max(inner, 1), nchan, ws.data_ptr(), ws.numel(), _stream(x))
+    return gx, ga, gb
+
+
+class ChanAffine(torch.autograd.Function):
+    """out*alpha_out + beta_out (quant/quant_layer.py:258-259)."""
+
+    @staticmethod
+    def forward(ctx, x, a, b):
+        ctx.save_for_backward(x, a)
+        return chan_affine_fwd(x, a, b)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, a = ctx.saved_tensors
+        gx, ga, gb = chan_affine_bwd(gy, x, a, need_gx=ctx.needs_input_grad[0])
+        return gx, ga.view_as(a), gb.view_as(a)
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr_dev, step_dev, betas=(0.9, 0.999), eps=1e-8):
+    _call("ssq_adam_step", param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel(),
+          lr_dev.data_ptr(), float(betas[0]), float(betas[1]), float(eps), step_dev.data_ptr(), _stream(param))
+
+
+def gather_rows(src, index, out=None):
+    src = _req(src, "src")
+    batch = index.numel()
+    per_sample = src.numel() // src.shape[0]
+    if out is None:
+        out = torch.empty((batch,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    _call("ssq_gather_rows", src.data_ptr(), index.data_ptr(), out.data_ptr(), batch, per_sample, _stream(src))
+    return out
+
+
+def loop_advance(step_dev, idx_table, idx_live, b_table, b_live, lr_table, lr_live, n_steps: int):
+    batch = 0 if idx_live is None else idx_live.numel()
+    _call("ssq_loop_advance", step_dev.data_ptr(), _ptr(idx_table), _ptr(idx_live), batch, _ptr(b_table), _ptr(b_live),
+          _ptr(lr_table), _ptr(lr_live), int(n_steps), _stream(step_dev))
