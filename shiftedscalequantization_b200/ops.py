@@ -61,15 +61,26 @@ def _call(name: str, *args) -> None:
 
 
 def channel_layout(x: torch.Tensor, delta: torch.Tensor) -> Tuple[int, int]:
-    """(inner, nchan) of the header's channel layout for a quantiser whose delta is a scalar
-    (per-tensor) or [C,1,...] along dim 0 (the reference's shapes, quant_layer.py:67-77)."""
+    """(inner, nchan) of the header's channel layout. delta is a scalar (per-tensor), [C,1,...] along
+    dim 0 (quant_layer.py:67-77), or — after ChannelQuant.update_delta (channelQuant.py:221-237,296-298) —
+    [OC,IC,1,1] / [OC,IC]: any shape whose non-unit dims are a prefix of x's."""
     n = x.numel()
     c = delta.numel()
     if c == 1:
         return max(n, 1), 1
-    if x.dim() == 0 or x.shape[0] != c:
-        raise _lib.SsqError(f"delta has {c} channels but tensor shape is {tuple(x.shape)}")
+    lead = list(delta.shape)
+    while lead and lead[-1] == 1:
+        lead.pop()
+    if tuple(lead) != tuple(x.shape[:len(lead)]):
+        raise _lib.SsqError(f"delta shape {tuple(delta.shape)} does not prefix tensor shape {tuple(x.shape)}")
     return max(n // c, 1), c
+
+
+def match_param(param: torch.Tensor, delta: torch.Tensor) -> torch.Tensor:
+    """zero_point broadcast to delta's shape (they differ after update_delta)"""
+    if param.numel() == delta.numel():
+        return param
+    return param.expand_as(delta).contiguous()
 
 
 def scalar_dev(value: float, device) -> torch.Tensor:
@@ -78,7 +89,7 @@ def scalar_dev(value: float, device) -> torch.Tensor:
 
 # --------------------------------------------------------------------------------------- K1a
 def fq_affine_fwd(x, delta, zero_point, qmin: float, qmax: float, in_scale=None, want_codes=False):
-    x = _req(x, "x"); delta = _req(delta, "delta"); zero_point = _req(zero_point, "zero_point")
+    x = _req(x, "x"); delta = _req(delta, "delta"); zero_point = _req(match_param(zero_point, delta), "zero_point")
     inner, nchan = channel_layout(x, delta)
     if in_scale is not None:
         in_scale = _req(in_scale, "in_scale")
@@ -126,7 +137,8 @@ class FakeQuantAffine(torch.autograd.Function):
 # --------------------------------------------------------------------------------------- K1b
 def adaround_fwd(w, alpha, delta, zero_point, qmin, qmax, soft: bool, b_dev=None, lam: float = 0.0,
                  want_codes=False, want_reg=False):
-    w = _req(w, "w"); alpha = _req(alpha, "alpha"); delta = _req(delta, "delta"); zero_point = _req(zero_point, "zero_point")
+    w = _req(w, "w"); alpha = _req(alpha, "alpha"); delta = _req(delta, "delta")
+    zero_point = _req(match_param(zero_point, delta), "zero_point")
     if alpha.shape != w.shape:
         raise _lib.SsqError("alpha must have the weight's shape")
     inner, nchan = channel_layout(w, delta)
@@ -147,7 +159,8 @@ def adaround_fwd(w, alpha, delta, zero_point, qmin, qmax, soft: bool, b_dev=None
 
 def adaround_bwd(gwq, w, alpha, delta, zero_point, qmin, qmax, b_dev=None, lam: float = 0.0, greg=None,
                  out=None, accumulate=False):
-    w = _req(w, "w"); alpha = _req(alpha, "alpha"); delta = _req(delta, "delta"); zero_point = _req(zero_point, "zero_point")
+    w = _req(w, "w"); alpha = _req(alpha, "alpha"); delta = _req(delta, "delta")
+    zero_point = _req(match_param(zero_point, delta), "zero_point")
     if gwq is not None:
         gwq = _req(gwq, "gwq")
     inner, nchan = channel_layout(w, delta)
@@ -415,14 +428,14 @@ def inp_scale_search(w2d, delta, raw_zero_point, cand, x_range: float, lo: float
 
 
 # --------------------------------------------------------------------------------------- K3
-LOSS_MODES = {"mse": 0, "fisher_diag": 1, "fisher_full": 2}
+LOSS_MODES = {"mse": 0, "mse_all": 0, "fisher_diag": 1, "fisher_full": 2}   # mse_all: lp_loss(reduction != 'none')
 
 
-def _loss_dims(pred: torch.Tensor):
-    batch = pred.shape[0]
+def _loss_dims(pred: torch.Tensor, mode: str = "mse"):
+    batch = pred.shape[0] if pred.dim() > 0 else 1
     per_sample = pred.numel() // max(batch, 1)
-    chan = pred.shape[1] if pred.dim() > 1 else 1
-    denom = pred.numel() / chan          # mean over everything but dim 1 (quant_layer.py:30)
+    chan = pred.shape[1] if (pred.dim() > 1 and mode != "mse_all") else 1
+    denom = pred.numel() / chan          # mean over everything but dim 1 (quant_layer.py:30); global mean for :32
     return batch, per_sample, float(denom)
 
 
@@ -432,7 +445,7 @@ def recon_loss(pred, tgt, p: float = 2.0, mode: str = "mse", fisher=None, tgt_in
     pred = _req(pred, "pred"); tgt = _req(tgt, "tgt")
     if fisher is not None:
         fisher = _req(fisher, "fisher")
-    batch, per_sample, denom = _loss_dims(pred)
+    batch, per_sample, denom = _loss_dims(pred, mode)
     if tgt_index is None and tgt.shape != pred.shape:
         raise _lib.SsqError("pred/tgt shape mismatch")
     loss = torch.empty(1, dtype=torch.float32, device=pred.device)
@@ -446,7 +459,7 @@ def recon_loss(pred, tgt, p: float = 2.0, mode: str = "mse", fisher=None, tgt_in
 
 def recon_loss_bwd(pred, tgt, gloss, p: float = 2.0, mode: str = "mse", fisher=None, tgt_index=None):
     pred = _req(pred, "pred"); tgt = _req(tgt, "tgt")
-    batch, per_sample, denom = _loss_dims(pred)
+    batch, per_sample, denom = _loss_dims(pred, mode)
     dpred = torch.empty_like(pred)
     ws = _ws(pred, batch if mode == "fisher_full" else 1, "loss")
     _call("ssq_recon_loss_bwd", pred.data_ptr(), tgt.data_ptr(), _ptr(fisher), _ptr(tgt_index), gloss.data_ptr(),

@@ -1,0 +1,412 @@
+"""GPU parity suite: every kernel, called through the C-ABI (ctypes -> libssq_b200.so), against
+ (a) the committed golden vectors produced by the real reference, and
+ (b) the numpy oracle on seeded inputs incl. ragged / misaligned / empty / large cases.
+Integer codes must be bit-exact; floats <= 1e-5 relative (north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_close, assert_exact, golden
+from oracle import ssq_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    a = np.asarray(a, dtype=np.float32)
+    return torch.from_numpy(np.ascontiguousarray(a)).reshape(a.shape).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from shiftedscalequantization_b200 import ops
+    return ops
+
+
+def rng(seed):
+    return np.random.default_rng(seed)
+
+
+# ------------------------------------------------------------------------------------------- K1a
+@pytest.mark.parametrize("case", golden("uaq").cases())
+def test_fq_affine_golden(ops, case):
+    g = golden("uaq").case(case)
+    bits, sym, cw, _ = (int(v) for v in g["meta"])
+    qmin, qmax = (float(v) for v in O.bounds(2 ** bits, bool(sym)))
+    x, d, z = dev(g["x"]), dev(g["delta"]), dev(g["zp"])
+    y, codes = ops.fq_affine_fwd(x, d, z, qmin, qmax, want_codes=True)
+    assert_exact(host(codes), g["codes"], "codes vs reference")
+    assert_close(host(y), g["y"], what="dequant vs reference")
+    gx, gd, gz = ops.fq_affine_bwd(dev(g["gy"]), x, d, z, qmin, qmax)
+    assert_close(host(gx), g["gx"], what="gx")
+    assert_close(host(gd), g["gdelta"], rtol=2e-5, what="gdelta")
+    assert_close(host(gz), g["gzp"], rtol=2e-5, what="gzp")
+
+
+@pytest.mark.parametrize("shape,cw,bits,sym", [
+    ((64, 64, 3, 3), True, 2, False), ((32, 1, 3, 3), True, 4, False), ((64, 3, 7, 7), True, 8, False),
+    ((1000, 512), True, 8, False), ((16, 24, 1, 1), True, 3, True), ((8, 64, 28, 28), False, 4, False),
+    ((5, 7, 3, 3), False, 4, False), ((3, 5), False, 2, False)])
+def test_fq_affine_oracle(ops, shape, cw, bits, sym):
+    r = rng(hash((shape, bits)) % 2 ** 31)
+    x = (r.standard_normal(shape) * (0.05 if cw else 1.0)).astype(np.float32)
+    if cw:
+        d = (np.abs(x.reshape(shape[0], -1)).max(1) / (2 ** bits - 1) * 1.7).astype(np.float32)
+        z = np.round(r.uniform(0, 2 ** bits - 1, shape[0])).astype(np.float32)
+        dshape = (shape[0],) + (1,) * (len(shape) - 1)
+        d, z = d.reshape(dshape), z.reshape(dshape)
+    else:
+        d = np.float32(np.abs(x).max() / (2 ** bits - 1) * 1.3).reshape(())
+        z = np.float32(3.0).reshape(())
+    qmin, qmax = (float(v) for v in O.bounds(2 ** bits, sym))
+    y_ref, c_ref = O.uaq_forward(x, d, z, qmin, qmax)
+    y, codes = ops.fq_affine_fwd(dev(x), dev(d), dev(z), qmin, qmax, want_codes=True)
+    assert_exact(host(codes), c_ref, "codes"); assert_exact(host(y), y_ref, "dequant")
+    gy = r.standard_normal(shape).astype(np.float32)
+    gx_ref, gd_ref, gz_ref = O.uaq_backward(gy, x, d, z, qmin, qmax)
+    gx, gd, gz = ops.fq_affine_bwd(dev(gy), dev(x), dev(d), dev(z), qmin, qmax)
+    assert_exact(host(gx), gx_ref, "gx")
+    assert_close(host(gd), gd_ref, what="gdelta"); assert_close(host(gz), gz_ref, what="gzp")
+
+
+def test_fq_affine_misaligned_and_empty(ops):
+    r = rng(7)
+    base = torch.as_tensor(r.standard_normal(4 * 1024 + 1).astype(np.float32)).cuda()
+    x = base[1:]                                     # 4-byte aligned only -> scalar path
+    d = dev(np.float32(0.11).reshape(())); z = dev(np.float32(5).reshape(()))
+    y, c = ops.fq_affine_fwd(x, d, z, 0.0, 15.0, want_codes=True)
+    y_ref, c_ref = O.uaq_forward(host(x), 0.11, 5, 0, 15)
+    assert_exact(host(c), c_ref); assert_exact(host(y), y_ref)
+    e = torch.empty(0, device="cuda")
+    assert ops.fq_affine_fwd(e, d, z, 0.0, 15.0).numel() == 0
+
+
+def test_fq_affine_large_property(ops):
+    """BASELINE-size activation [256,256,56,56] is too big for the numpy oracle in seconds: check
+    idempotence (fq(fq(x)) == fq(x)), code range, and a checksum against torch-free arithmetic on a slice."""
+    torch.manual_seed(0)
+    x = torch.relu(torch.randn(64, 256, 56, 56, device="cuda"))
+    d = dev(np.float32(0.2).reshape(())); z = dev(np.float32(0).reshape(()))
+    y, c = ops.fq_affine_fwd(x, d, z, 0.0, 15.0, want_codes=True)
+    assert float(c.min()) >= 0 and float(c.max()) <= 15
+    assert torch.equal(c, c.round())
+    y2 = ops.fq_affine_fwd(y, d, z, 0.0, 15.0)
+    assert torch.equal(y2, y)
+    sl = slice(12345, 12345 + 100000)
+    y_ref, c_ref = O.uaq_forward(host(x.flatten()[sl]), 0.2, 0, 0, 15)
+    assert_exact(host(c.flatten()[sl]), c_ref); assert_exact(host(y.flatten()[sl]), y_ref)
+
+
+@pytest.mark.parametrize("case", golden("channelquantmse").cases())
+def test_fq_affine_in_scale_golden(ops, case):
+    g = golden("channelquantmse").case(case)
+    L = 2 ** int(g["bits"])
+    w, d = dev(g["w"]), dev(g["delta"])
+    zero = torch.round(dev(g["raw"]) / d)
+    for level in (1, 4, 16, 64):
+        s = dev(g[f"inp_scale_l{level}"])
+        y, c = ops.fq_affine_fwd(w, d, zero, 0.0, float(L - 1), in_scale=s.flatten(), want_codes=True)
+        assert_exact(host(c), g[f"codes_l{level}"], "codes vs reference")
+        assert_close(host(y), g[f"y_l{level}"], what="dequant vs reference")
+
+
+# ------------------------------------------------------------------------------------------- K1b
+@pytest.mark.parametrize("case", golden("adaround").cases())
+def test_adaround_golden(ops, case):
+    g = golden("adaround").case(case)
+    L = 2 ** int(g["bits"])
+    w, d, z, a = dev(g["w"]), dev(g["delta"]), dev(g["zp"]), dev(g["alpha"])
+    assert_close(host(ops.adaround_init_alpha(w, d)), g["alpha0"], rtol=2e-5, what="alpha init")
+    wq = ops.adaround_fwd(w, a, d, z, 0.0, float(L - 1), soft=True)
+    assert_close(host(wq), g["wq_soft"], what="soft")
+    wqh, codes = ops.adaround_fwd(w, a, d, z, 0.0, float(L - 1), soft=False, want_codes=True)
+    assert_exact(host(codes), g["codes_hard"], "hard codes vs reference")
+    assert_exact(host(wqh), g["wq_hard"], "hard dequant vs reference")
+    ga = ops.adaround_bwd(dev(g["gw"]), w, a, d, z, 0.0, float(L - 1))
+    assert_close(host(ga), g["galpha"], what="galpha")
+    for b in (20, 11.3, 2.0):
+        bd = ops.scalar_dev(b, "cuda")
+        assert_close(host(ops.round_reg_fwd(a, bd, 0.01))[0], g[f"reg_b{b}"], rtol=2e-5, what=f"reg {b}")
+        assert_close(host(ops.round_reg_bwd(a, bd, 0.01)), g[f"greg_b{b}"], rtol=2e-5, what=f"greg {b}")
+        # fused: forward + regulariser in one launch, backward with both paths in one launch
+        wq2, reg = ops.adaround_fwd(w, a, d, z, 0.0, float(L - 1), soft=True, b_dev=bd, lam=0.01, want_reg=True)
+        assert torch.equal(wq2, wq)
+        assert_close(host(reg)[0], g[f"reg_b{b}"], rtol=2e-5, what="fused reg")
+        gboth = ops.adaround_bwd(dev(g["gw"]), w, a, d, z, 0.0, float(L - 1), b_dev=bd, lam=0.01)
+        assert_close(host(gboth), g["galpha"] + g[f"greg_b{b}"], rtol=2e-5, what="fused galpha")
+
+
+@pytest.mark.parametrize("shape,bits", [((128, 64, 3, 3), 2), ((96, 1, 3, 3), 3), ((1000, 512), 8), ((64, 3, 7, 7), 8)])
+def test_adaround_oracle_and_mt(ops, shape, bits):
+    r = rng(sum(shape) + bits)
+    L = 2 ** bits
+    w = (r.standard_normal(shape) * 0.05).astype(np.float32)
+    dshape = (shape[0],) + (1,) * (len(shape) - 1)
+    d = (np.abs(w.reshape(shape[0], -1)).max(1) / (L - 1) * 1.5).astype(np.float32).reshape(dshape)
+    z = np.round(r.uniform(0, L - 1, shape[0])).astype(np.float32).reshape(dshape)
+    a = (r.standard_normal(shape) * 3).astype(np.float32)
+    wq_ref, _ = O.adaround_forward(w, a, d, z, 0, L - 1, soft=True)
+    _, ch_ref = O.adaround_forward(w, a, d, z, 0, L - 1, soft=False)
+    W, A, D, Z = dev(w), dev(a), dev(d), dev(z)
+    assert_close(host(ops.adaround_fwd(W, A, D, Z, 0.0, float(L - 1), soft=True)), wq_ref, what="soft")
+    _, ch = ops.adaround_fwd(W, A, D, Z, 0.0, float(L - 1), soft=False, want_codes=True)
+    assert_exact(host(ch), ch_ref, "hard codes")
+    # multi-tensor launch == single-tensor launches, and its regulariser == sum of oracle regs
+    w2 = (r.standard_normal((32, 16, 3, 3)) * 0.05).astype(np.float32)
+    d2 = np.full((32, 1, 1, 1), 0.02, np.float32); z2 = np.full((32, 1, 1, 1), 1.0, np.float32)
+    a2 = (r.standard_normal(w2.shape) * 3).astype(np.float32)
+    W2, A2, D2, Z2 = dev(w2), dev(a2), dev(d2), dev(z2)
+    out1, out2 = torch.empty_like(W), torch.empty_like(W2)
+    g1, g2 = torch.empty_like(W), torch.empty_like(W2)
+    tab = ops.AdaRoundTable([
+        dict(w=W, alpha=A, delta=D, zero_point=Z, wq=out1, galpha=g1, qmin=0.0, qmax=float(L - 1)),
+        dict(w=W2, alpha=A2, delta=D2, zero_point=Z2, wq=out2, galpha=g2, qmin=0.0, qmax=3.0)])
+    bd = ops.scalar_dev(7.5, "cuda"); reg = torch.zeros(1, device="cuda")
+    tab.forward(True, bd, 0.01, reg)
+    assert torch.equal(out1, ops.adaround_fwd(W, A, D, Z, 0.0, float(L - 1), soft=True))
+    assert torch.equal(out2, ops.adaround_fwd(W2, A2, D2, Z2, 0.0, 3.0, soft=True))
+    assert_close(host(reg)[0], np.float32(O.round_reg(a, 7.5, 0.01) + O.round_reg(a2, 7.5, 0.01)), rtol=2e-5, what="mt reg")
+    gw1, gw2 = dev(r.standard_normal(shape)), dev(r.standard_normal(w2.shape))
+    tab.backward([gw1, gw2], bd, 0.01)
+    assert torch.equal(g1, ops.adaround_bwd(gw1, W, A, D, Z, 0.0, float(L - 1), b_dev=bd, lam=0.01))
+    assert torch.equal(g2, ops.adaround_bwd(gw2, W2, A2, D2, Z2, 0.0, 3.0, b_dev=bd, lam=0.01))
+    ref = O.adaround_backward(host(gw1), w, a, d, z, 0, L - 1) + O.round_reg_grad(a, 7.5, 0.01)
+    assert_close(host(g1), ref, rtol=2e-5, what="mt galpha")
+    # warm-up: b <= 0 switches the regulariser off (block_recon.py:167)
+    b0 = ops.scalar_dev(0.0, "cuda")
+    tab.forward(True, b0, 0.01, reg)
+    assert float(reg) == 0.0
+
+
+# ------------------------------------------------------------------------------------------- K3
+@pytest.mark.parametrize("case", ["conv", "fc"])
+def test_recon_loss_golden(ops, case):
+    g = golden("loss").case(case)
+    pred, tgt = dev(g["pred"]), dev(g["tgt"])
+    for p in (2.0, 2.4):
+        loss, dp = ops.recon_loss(pred, tgt, p)
+        assert_close(host(loss)[0], g[f"lp{p}"], what=f"lp{p}")
+        assert_close(host(dp), g[f"dlp{p}"], what=f"dlp{p}")
+        dp2 = ops.recon_loss_bwd(pred, tgt, ops.scalar_dev(1.0, "cuda"), p)
+        assert torch.equal(dp, dp2)
+    if case == "conv":
+        f = dev(g["fisher"])
+        loss, dp = ops.recon_loss(pred, tgt, mode="fisher_diag", fisher=f)
+        assert_close(host(loss)[0], g["fdiag"], what="fdiag"); assert_close(host(dp), g["dfdiag"], what="dfdiag")
+        loss, dp = ops.recon_loss(pred, tgt, mode="fisher_full", fisher=f)
+        assert_close(host(loss)[0], g["ffull"], what="ffull"); assert_close(host(dp), g["dffull"], rtol=2e-5, what="dffull")
+
+
+def test_recon_loss_gather_and_autograd(ops):
+    r = rng(11)
+    cache = dev(r.standard_normal((40, 8, 6, 6)))
+    idx = torch.as_tensor(r.permutation(40)[:16]).cuda()
+    pred = dev(r.standard_normal((16, 8, 6, 6)))
+    l1, d1 = ops.recon_loss(pred, cache, 2.0, tgt_index=idx)
+    l2, d2 = ops.recon_loss(pred, cache[idx].contiguous(), 2.0)
+    assert torch.equal(l1, l2) and torch.equal(d1, d2)
+    assert torch.equal(ops.gather_rows(cache, idx), cache[idx])
+    l_ref, d_ref = O.lp_loss(host(pred), host(cache[idx]), 2.0)
+    assert_close(host(l1)[0], l_ref); assert_close(host(d1), d_ref)
+    pr = pred.clone().requires_grad_(True)
+    out = ops.ReconLoss.apply(pr, cache[idx].contiguous(), 2.4, "mse", None)
+    (out * 3.0).backward()
+    _, d_ref = O.lp_loss(host(pred), host(cache[idx]), 2.4)
+    assert_close(host(pr.grad), 3.0 * d_ref)
+
+
+def test_recon_loss_large_property(ops):
+    """ResNet-50 layer1-sized batch (25.7 M elements): linearity + determinism."""
+    torch.manual_seed(1)
+    pred = torch.randn(32, 256, 56, 56, device="cuda"); tgt = torch.randn_like(pred)
+    l1, d1 = ops.recon_loss(pred, tgt, 2.0)
+    l2, d2 = ops.recon_loss(pred, tgt, 2.0)
+    assert torch.equal(l1, l2) and torch.equal(d1, d2)          # fixed-order reduction
+    ref = ((pred.double() - tgt.double()) ** 2).sum() / (32 * 56 * 56)
+    assert abs(float(l1) - float(ref)) / float(ref) < 1e-6
+    assert torch.allclose(d1, 2 * (pred - tgt) / (32 * 56 * 56), rtol=1e-6, atol=0)
+
+
+# ------------------------------------------------------------------------------------------- K2a
+@pytest.mark.parametrize("case", [c for c in golden("uaq").cases() if "max" not in c])
+def test_mse_search_golden(ops, case):
+    g = golden("uaq").case(case)
+    bits, sym, cw, _ = (int(v) for v in g["meta"])
+    x = dev(g["x"])
+    x2 = x.reshape(x.shape[0], -1) if cw else x.reshape(1, -1)
+    d, z, raw, score, idx = ops.mse_scale_search(x2, 2 ** bits, bool(sym))
+    assert (host(idx) >= 0).all()
+    assert_exact(host(d).reshape(g["delta"].shape), g["delta"], "delta vs reference")
+    assert_exact(host(z).reshape(g["zp"].shape), g["zp"], "zero_point vs reference")
+    assert_exact(host(raw).reshape(g["raw"].shape), g["raw"], "raw_zero_point vs reference")
+
+
+@pytest.mark.parametrize("rows,k,bits", [(64, 576, 2), (48, 9, 4), (16, 147, 8), (10, 512, 8), (128, 4608, 2), (1, 70000, 4)])
+def test_mse_search_oracle(ops, rows, k, bits):
+    r = rng(rows * 131 + k)
+    x = (r.standard_normal((rows, k)) * 0.05).astype(np.float32)
+    if rows == 1:
+        x = np.maximum(x * 20, 0).astype(np.float32)         # activation-like, goes down the grid-wide path
+    d, z, raw, score, idx = ops.mse_scale_search(dev(x), 2 ** bits, False)
+    flips = 0
+    for i in range(rows):
+        (dr, zr, rr, ir), scores = O.mse_search_row(x[i], bits, return_scores=True)
+        if int(host(idx)[i]) != ir:
+            # a flip is only legitimate at an fp32 tie of the reference's own scores
+            rel = abs(float(scores[int(host(idx)[i])]) - float(scores[ir])) / float(scores[ir])
+            assert rel < 2e-6, f"row {i}: picked {int(host(idx)[i])} vs {ir}, score gap {rel:.2e}"
+            flips += 1
+        else:
+            assert host(d)[i] == dr and host(z)[i] == zr and host(raw)[i] == rr
+    assert flips <= max(1, rows // 50)
+
+
+def test_mse_search_degenerate_row(ops):
+    x = torch.zeros(3, 36, device="cuda"); x[1] = torch.randn(36, device="cuda")
+    d, z, raw, score, idx = ops.mse_scale_search(x, 4, False)
+    assert int(idx[0]) == -1 and int(idx[2]) == -1 and int(idx[1]) >= 0   # all-zero channel: delta stays None upstream
+    mn, mx = ops.row_minmax(x)
+    assert torch.equal(mn, x.min(1)[0]) and torch.equal(mx, x.max(1)[0])
+
+
+# ------------------------------------------------------------------------------------------- K2b
+@pytest.mark.parametrize("case", golden("channelquantmse").cases())
+def test_inp_scale_search_golden(ops, case):
+    g = golden("channelquantmse").case(case)
+    L = 2 ** int(g["bits"])
+    w = dev(g["w"]); oc = w.shape[0]
+    for level in (1, 4, 16, 64):
+        thr = float(g[f"thr_l{level}"])
+        cand = torch.tensor([i / level for i in range(level, 0, -1)], dtype=torch.float32).cuda()
+        lo = float(np.float32(0.0 - 0.5 / (L - 1) * thr)); hi = float(np.float32(1.0 + 0.5 / (L - 1) * thr))
+        s = torch.ones(w.numel() // oc, device="cuda")
+        ops.inp_scale_search(w.reshape(oc, -1), dev(g["delta"]).flatten(), dev(g["raw"]).flatten(), cand, L - 1, lo, hi, s)
+        assert_exact(host(s).reshape(g[f"inp_scale_l{level}"].shape), g[f"inp_scale_l{level}"], f"inp_scale l{level}")
+
+
+def test_inp_scale_search_oracle_large(ops):
+    r = rng(5)
+    w = (r.standard_normal((512, 256, 3, 3)) * 0.02).astype(np.float32)       # the notebook's layer shape
+    d, z, raw = zip(*[O.max_init(row, 2) for row in w.reshape(512, -1)])
+    d = np.array(d, np.float32); raw = np.array(raw, np.float32)
+    for level, thr in [(8, 1.5), (1024, 1.5)]:
+        ref = O.inp_scale_search(w, d.reshape(-1, 1, 1, 1), raw.reshape(-1, 1, 1, 1), 4, level, thr) if level <= 8 else None
+        cand = torch.tensor([i / level for i in range(level, 0, -1)], dtype=torch.float32).cuda()
+        lo = float(np.float32(0.0 - 0.5 / 3 * thr)); hi = float(np.float32(1.0 + 0.5 / 3 * thr))
+        s = torch.ones(256 * 9, device="cuda")
+        ops.inp_scale_search(dev(w).reshape(512, -1), dev(d), dev(raw), cand, 3, lo, hi, s)
+        if ref is not None:
+            assert_exact(host(s), ref.reshape(-1), "inp_scale")
+        else:
+            # monotone property: every chosen scale is a candidate and the column fits at it
+            assert set(np.unique(host(s))).issubset(set(host(cand).tolist()))
+
+
+# ------------------------------------------------------------------------------------------- K1c
+@pytest.mark.parametrize("case", golden("channelquant").cases())
+def test_shift_golden(ops, case):
+    g = golden("channelquant").case(case)
+    L = 2 ** int(g["bits"]); shifts = [float(s) for s in g["shifts"]]
+    w, d, z = dev(g["w"]), dev(g["delta"]), dev(g["zp"])
+    per_el = w.dim() == 2
+    sd = torch.stack([d.flatten() * s for s in shifts])          # delta * python float, fp32 like ATen
+    alpha = dev(g["alpha"])
+    p = ops.shift_probs_fwd(alpha)
+    assert_close(host(p), g["p"], what="p")
+    y = ops.fq_shift_fwd(w, sd, d, z, p, None, ops.SHIFT_DEQUANT, False, False, 0.0, float(L - 1), per_el)
+    assert_close(host(y), g["y_soft"], what="soft mixture vs reference")
+    yh = ops.fq_shift_fwd(w, sd, d, z, dev(g["p"]), None, ops.SHIFT_DEQUANT, True, False, 0.0, float(L - 1), per_el)
+    assert_exact(host(yh), g["y_hard"], "hard select vs reference")
+    gp, _ = ops.fq_shift_bwd(dev(g["gy"]), w, sd, d, z, p, None, ops.SHIFT_DEQUANT, False, 0.0, float(L - 1), per_el, False)
+    assert_close(host(ops.shift_probs_bwd(alpha, gp)), g["galpha_soft"], rtol=3e-5, what="galpha vs reference")
+    _, ent = ops.shift_probs_fwd(alpha, 0, None, 0.7, want_reg=True)
+    assert_close(host(ent)[0], g["ent"], what="entropy")
+    assert_close(host(ops.shift_probs_bwd(alpha, None, 0, None, 0.7)), g["gent"], rtol=3e-5, what="d entropy")
+    # adaShift
+    a2, b2 = dev(g["as_alpha"]), dev(g["as_beta"])
+    p2 = ops.shift_probs_fwd(a2)
+    y = ops.fq_shift_fwd(w, sd, d, z, p2, b2, ops.SHIFT_ADASHIFT, False, False, 0.0, float(L - 1), per_el)
+    assert_close(host(y), g["as_y"], what="adaShift soft vs reference")
+    yh = ops.fq_shift_fwd(w, sd, d, z, p2, b2, ops.SHIFT_ADASHIFT, True, True, 0.0, float(L - 1), per_el)
+    assert_exact(host(yh), g["as_y_hard"], "adaShift hard vs reference")
+    gp, gb = ops.fq_shift_bwd(dev(g["gy"]), w, sd, d, z, p2, b2, ops.SHIFT_ADASHIFT, False, 0.0, float(L - 1), per_el, True)
+    assert_close(host(ops.shift_probs_bwd(a2, gp)), g["as_galpha"], rtol=3e-5, what="adaShift galpha")
+    assert_close(host(gb), g["as_gbeta"], what="adaShift gbeta")
+    for bb in (20, 7.7):
+        bd = ops.scalar_dev(bb, "cuda")
+        _, rs = ops.shift_probs_fwd(a2, 1, bd, 0.3, want_reg=True)
+        assert_close(host(rs)[0], g[f"as_regS_b{bb}"], rtol=2e-5, what="regS")
+        assert_close(host(ops.shift_probs_bwd(a2, None, 1, bd, 0.3)), g[f"as_gregS_b{bb}"], rtol=3e-5, what="d regS")
+    # adaround mode on the per-(oc,ic) delta selected by update_delta
+    y = ops.adaround_fwd(w, dev(g["ar_beta"]), dev(g["ar_delta"]), z, 0.0, float(L - 1), soft=True)
+    assert_close(host(y), g["ar_y"], what="adaround-after-shift")
+    yh = ops.adaround_fwd(w, dev(g["ar_beta"]), dev(g["ar_delta"]), z, 0.0, float(L - 1), soft=False)
+    assert_exact(host(yh), g["ar_y_hard"], "adaround-after-shift hard")
+    gb = ops.adaround_bwd(dev(g["gy"]), w, dev(g["ar_beta"]), dev(g["ar_delta"]), z, 0.0, float(L - 1))
+    assert_close(host(gb), g["ar_gbeta"], what="adaround-after-shift gbeta")
+
+
+def test_shift_oracle_resnet_shape(ops):
+    r = rng(23)
+    shape = (128, 64, 3, 3); L = 4; shifts = [0.96875, 1.03125, 1.0]
+    w = (r.standard_normal(shape) * 0.05).astype(np.float32)
+    d = (np.abs(w.reshape(128, -1)).max(1) / 3 * 1.4).astype(np.float32).reshape(128, 1, 1, 1)
+    z = np.full((128, 1, 1, 1), 2.0, np.float32)
+    alpha = (r.standard_normal((64, 3)) * 1.5).astype(np.float32)
+    beta = (r.standard_normal(shape) * 2).astype(np.float32)
+    gy = r.standard_normal(shape).astype(np.float32)
+    p_ref = O.shift_probs(alpha)
+    W, D, Z, A, B, GY = dev(w), dev(d), dev(z), dev(alpha), dev(beta), dev(gy)
+    sd = torch.stack([D.flatten() * s for s in shifts])
+    P = ops.shift_probs_fwd(A)
+    for mode, name in ((ops.SHIFT_DEQUANT, "dequant"), (ops.SHIFT_ADASHIFT, "adashift")):
+        y = ops.fq_shift_fwd(W, sd, D, Z, P, B, mode, False, False, 0.0, 3.0, False)
+        assert_close(host(y), O.shift_forward(w, d, z, shifts, p_ref, 0, 3, name, beta=beta), what=name)
+        gp, gb = ops.fq_shift_bwd(GY, W, sd, D, Z, P, B, mode, False, 0.0, 3.0, False, mode == ops.SHIFT_ADASHIFT)
+        gp_ref, gb_ref = O.shift_backward(gy, w, d, z, shifts, p_ref, 0, 3, name, beta=beta)
+        assert_close(host(gp), gp_ref, rtol=3e-5, what=name + " gp")
+        if gb_ref is not None:
+            assert_close(host(gb), gb_ref, what=name + " gbeta")
+
+
+# ------------------------------------------------------------------------------------------- Adam / loop / affine
+def test_adam_and_loop_advance(ops):
+    g = golden("adam")
+    p = dev(g["p0"]); m = torch.zeros_like(p); v = torch.zeros_like(p)
+    step = torch.zeros(1, dtype=torch.int64, device="cuda")
+    lr = ops.scalar_dev(1e-3, "cuda")
+    idx_table = torch.arange(5 * 4, dtype=torch.int64, device="cuda").reshape(5, 4)
+    idx_live = torch.zeros(4, dtype=torch.int64, device="cuda")
+    b_table = torch.arange(5, dtype=torch.float32, device="cuda") + 0.5
+    b_live = torch.zeros(1, device="cuda")
+    for s in range(1, 6):
+        ops.loop_advance(step, idx_table, idx_live, b_table, b_live, None, None, 5)
+        assert int(step) == s and torch.equal(idx_live, idx_table[s - 1]) and float(b_live) == s - 0.5
+        ops.adam_step(p, dev(g[f"g{s}"]), m, v, lr, step)
+        assert_close(host(p), g[f"p{s}"], rtol=2e-6, what=f"adam step {s} vs torch.optim.Adam")
+
+
+def test_chan_affine(ops):
+    r = rng(3)
+    x = r.standard_normal((4, 6, 5, 5)).astype(np.float32)
+    a = r.standard_normal(6).astype(np.float32); b = r.standard_normal(6).astype(np.float32)
+    y = ops.chan_affine_fwd(dev(x), dev(a), dev(b))
+    assert_exact(host(y), x * a.reshape(1, 6, 1, 1) + b.reshape(1, 6, 1, 1))
+    gy = r.standard_normal(x.shape).astype(np.float32)
+    gx, ga, gb = ops.chan_affine_bwd(dev(gy), dev(x), dev(a))
+    assert_close(host(gx), gy * a.reshape(1, 6, 1, 1))
+    assert_close(host(ga), (gy.astype(np.float64) * x).sum((0, 2, 3)))
+    assert_close(host(gb), gy.astype(np.float64).sum((0, 2, 3)))
+
+
+def test_bad_arguments_raise(ops):
+    from shiftedscalequantization_b200._lib import SsqError
+    with pytest.raises(SsqError):
+        ops.fq_affine_fwd(torch.zeros(4), torch.ones(1), torch.zeros(1), 0.0, 3.0)          # CPU tensor: no fallback
+    with pytest.raises(SsqError):
+        ops.fq_affine_fwd(torch.zeros(4, device="cuda").double(), torch.ones(1, device="cuda"),
+                          torch.zeros(1, device="cuda"), 0.0, 3.0)
