@@ -1,0 +1,85 @@
+"""Multi-GPU plumbing for the calibration path: one process per GPU, torch.distributed (NCCL over
+NVLink 5 / NVSwitch; gloo in the CPU tests). The path has exactly one exchange step per reconstruction
+iteration — a SUM all-reduce of the unit's flat gradient buffer (reference intent: link.allreduce at
+quant/block_recon.py:100-102) — plus an all-average of the activation step sizes after their init
+(quant/quant_model.py:78-83) and an all-gather when the scale search is sharded by output channel.
+"""
+from __future__ import annotations
+
+import os
+from typing import Tuple
+
+import torch
+import torch.distributed as td
+
+
+def is_initialized() -> bool:
+    return td.is_available() and td.is_initialized()
+
+
+def world_size() -> int:
+    return td.get_world_size() if is_initialized() else 1
+
+
+def rank() -> int:
+    return td.get_rank() if is_initialized() else 0
+
+
+def init_from_env(backend: str = None) -> Tuple[int, int, int]:
+    """(rank, local_rank, world). Reads RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* as torchrun sets them."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rk = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            td.init_process_group(backend, rank=rk, world_size=world, device_id=torch.device("cuda", local))
+        else:
+            td.init_process_group(backend, rank=rk, world_size=world)
+    return rk, local, world
+
+
+def all_reduce_sum_(flat: torch.Tensor) -> torch.Tensor:
+    if world_size() > 1:
+        td.all_reduce(flat, op=td.ReduceOp.SUM)
+    return flat
+
+
+def all_average_(t: torch.Tensor) -> torch.Tensor:
+    if world_size() > 1:
+        td.all_reduce(t, op=td.ReduceOp.SUM)
+        t.div_(world_size())
+    return t
+
+
+def shard_range(n: int, r: int = None, w: int = None) -> Tuple[int, int]:
+    """contiguous shard [lo, hi) of n items for rank r of w (remainder spread over the first ranks)"""
+    r = rank() if r is None else r
+    w = world_size() if w is None else w
+    base, rem = divmod(n, w)
+    lo = r * base + min(r, rem)
+    return lo, lo + base + (1 if r < rem else 0)
+
+
+def shard_calibration(cali_data: torch.Tensor) -> torch.Tensor:
+    """this rank's images (reference intent: num_samples/ngpus per rank, Brecq/main_imagenet_dist.py:165)"""
+    lo, hi = shard_range(cali_data.shape[0])
+    return cali_data[lo:hi]
+
+
+def all_gather_rows(local: torch.Tensor, n_total: int) -> torch.Tensor:
+    """concatenate per-rank row shards produced with shard_range (output-channel-sharded scale search)"""
+    if world_size() == 1:
+        return local
+    w = world_size()
+    sizes = [shard_range(n_total, r, w) for r in range(w)]
+    width = max(hi - lo for lo, hi in sizes)
+    pad = torch.zeros((width,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    out = [torch.empty_like(pad) for _ in range(w)]
+    td.all_gather(out, pad)
+    return torch.cat([o[:hi - lo] for o, (lo, hi) in zip(out, sizes)])

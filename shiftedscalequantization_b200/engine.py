@@ -1,0 +1,248 @@
+"""ReconEngine — the reconstruction hot loop (reference: quant/block_recon.py:89-105, quant/layer_recon.py:79-96)
+re-designed for B200:
+
+  * all trainable state of a unit lives in ONE flat device buffer (every AdaRound alpha of the block, or every
+    activation step size), with the nn.Parameters the API exposes as views into it — one multi-tensor
+    fake-quant launch, one fused Adam launch, one all-reduce bucket per iteration;
+  * the mini-batch indices (the reference's CPU `torch.randperm(N)[:B]` stream), the temperature b and the
+    learning rate are precomputed tables read through a device-side step counter, so the whole iteration —
+    gather, fake-quant, cuDNN convs, loss, backward, Adam — is captured once in a CUDA graph and replayed;
+  * the reconstruction loss reads the cached FP outputs in place through the index (no gathered copy), writes
+    d(loss)/d(pred) in the same pass, and the regulariser and its gradient ride inside the fake-quant kernels.
+
+Per-iteration launches of ours (weight phase): loop_advance, gather_rows, adaround_fwd_mt, recon_loss,
+adaround_bwd_mt, adam_step = 6, against ~530 ATen dispatches upstream.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import dist as ssq_dist
+from . import ops
+
+
+def temperature(t: int, t_max: int, rel_start_decay: float, start_b, end_b):
+    """LinearTempDecay.__call__ (quant/block_recon.py:193-202), host doubles"""
+    start_decay = rel_start_decay * t_max
+    if t < start_decay:
+        return start_b
+    rel_t = (t - start_decay) / (t_max - start_decay)
+    return end_b + (start_b - end_b) * max(0.0, (1 - rel_t))
+
+
+def brecq_b_table(iters: int, warmup: float, b_range, round_loss: bool) -> torch.Tensor:
+    """b used at iteration i (0-based) by LossFunction: count = i+1 is incremented BEFORE use
+    (block_recon.py:153); b = 0 (regulariser off) while count < iters*warmup (:167)."""
+    out = torch.zeros(max(iters, 1), dtype=torch.float32)
+    if not round_loss:
+        return out
+    loss_start = iters * warmup
+    for i in range(iters):
+        count = i + 1
+        if count >= loss_start:
+            out[i] = float(temperature(count, iters, warmup, b_range[0], b_range[1]))
+    return out
+
+
+def index_table(n_samples: int, batch: int, iters: int) -> torch.Tensor:
+    """the exact CPU RNG call sequence of the reference loop (block_recon.py:90), consumed up front"""
+    tab = torch.empty((max(iters, 1), batch), dtype=torch.int64)
+    for i in range(iters):
+        tab[i] = torch.randperm(n_samples)[:batch]
+    return tab
+
+
+def cosine_lr_table(lr: float, iters: int) -> torch.Tensor:
+    """learning rates Adam sees under CosineAnnealingLR(T_max=iters, eta_min=0) (block_recon.py:72-73),
+    produced by the real scheduler so the recursive form's rounding is reproduced"""
+    p = nn.Parameter(torch.zeros(1))
+    opt = torch.optim.Adam([p], lr=lr)
+    sch = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=max(iters, 1), eta_min=0.)
+    out = torch.empty(max(iters, 1), dtype=torch.float32)
+    for i in range(iters):
+        out[i] = opt.param_groups[0]['lr']
+        opt.step()
+        sch.step()
+    return out
+
+
+def _pad4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
+class ReconEngine:
+    """Runs `iters` reconstruction iterations of one unit (QuantModule or BaseQuantBlock).
+
+    weight phase (act_quant=False): optimises the AdaRound alpha of every QuantModule in the unit.
+    activation phase (act_quant=True): optimises the activation step sizes (LSQ) with frozen hard-rounded weights.
+    """
+
+    def __init__(self, unit: nn.Module, modules: Sequence[nn.Module], cached_inps: torch.Tensor,
+                 cached_outs: torch.Tensor, cached_grads: Optional[torch.Tensor] = None, *,
+                 act_quant: bool, iters: int, weight: float, b_range=(20, 2), warmup: float = 0.0, p: float = 2.0,
+                 lr: float = 4e-5, opt_mode: str = 'mse', batch_size: int = 32, multi_gpu: bool = False,
+                 act_quantizers: Sequence[nn.Module] = (), use_graph: Optional[bool] = None,
+                 idx_table: Optional[torch.Tensor] = None, verbose: bool = True):
+        self.unit, self.modules = unit, list(modules)
+        self.dev = cached_inps.device
+        if self.dev.type != 'cuda':
+            raise ops._lib.SsqError('reconstruction runs on CUDA only (no CPU fallback)')
+        self.cached_inps = cached_inps.contiguous()
+        self.cached_outs = cached_outs.contiguous()
+        self.cached_grads = None if cached_grads is None else cached_grads.contiguous()
+        self.act_quant, self.iters, self.weight, self.p, self.opt_mode = act_quant, int(iters), float(weight), float(p), opt_mode
+        self.batch = min(int(batch_size), self.cached_inps.shape[0])
+        self.multi_gpu = bool(multi_gpu) and ssq_dist.world_size() > 1
+        self.use_graph = (self.iters >= 8) if use_graph is None else bool(use_graph)
+        self.verbose = verbose
+        self.launches_per_iter = 0
+        self.graph = None
+        n = self.cached_inps.shape[0]
+        # ---- device-side schedules -------------------------------------------------------------------
+        tab = idx_table if idx_table is not None else index_table(n, self.batch, self.iters)
+        self.idx_table = tab.to(self.dev)
+        self.b_table = brecq_b_table(self.iters, warmup, b_range, round_loss=not act_quant).to(self.dev)
+        lr_tab = cosine_lr_table(lr, self.iters) if act_quant else torch.full((max(self.iters, 1),), 1e-3)
+        self.lr_table = lr_tab.to(self.dev)
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self.idx_live = torch.zeros(self.batch, dtype=torch.int64, device=self.dev)
+        self.b_live = torch.zeros(1, device=self.dev)
+        self.lr_live = torch.zeros(1, device=self.dev)
+        self.cur_inp = torch.empty((self.batch,) + tuple(self.cached_inps.shape[1:]), device=self.dev)
+        self.loss_dev = torch.zeros(1, device=self.dev)
+        self.reg_dev = torch.zeros(1, device=self.dev)
+        # ---- freeze everything that is not optimised (no wasted wgrad / bias-grad kernels) ---------------
+        self._frozen = [(q, q.requires_grad) for q in unit.parameters()]
+        for q, _ in self._frozen:
+            q.requires_grad_(False)
+        if act_quant:
+            self._setup_act_phase(list(act_quantizers))
+        else:
+            self._setup_weight_phase()
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+
+    # ------------------------------------------------------------------------------------------ setup
+    def _setup_weight_phase(self):
+        qs = [m.weight_quantizer for m in self.modules]
+        sizes = [_pad4(q.alpha.numel()) for q in qs]
+        self.flat = torch.zeros(sum(sizes), device=self.dev)
+        self.gflat = torch.zeros_like(self.flat)
+        entries, self.wq_leaves, off = [], [], 0
+        for m, q, sz in zip(self.modules, qs, sizes):
+            n = q.alpha.numel()
+            view = self.flat[off:off + n].view(q.alpha.shape)
+            view.copy_(q.alpha.detach())
+            q.alpha = nn.Parameter(view, requires_grad=False)      # API-visible parameter = view of the flat buffer
+            wq = torch.empty_like(m.weight, memory_format=torch.contiguous_format).requires_grad_(True)
+            self.wq_leaves.append(wq)
+            m._engine_weight = wq
+            entries.append(dict(w=m.weight.detach(), alpha=view, delta=q.delta.detach(),
+                                zero_point=ops.match_param(q.zero_point.detach(), q.delta.detach()), wq=wq.detach(),
+                                galpha=self.gflat[off:off + n].view(q.alpha.shape),
+                                qmin=0.0, qmax=float(q.n_levels - 1)))
+            off += sz
+        self.table = ops.AdaRoundTable(entries)
+
+    def _setup_act_phase(self, act_quantizers: List[nn.Module]):
+        self.act_quantizers = [q for q in act_quantizers if q.delta is not None]
+        k = max(len(self.act_quantizers), 1)
+        self.flat = torch.zeros(_pad4(k), device=self.dev)
+        self.gflat = torch.zeros_like(self.flat)
+        self.delta_params = []
+        for i, q in enumerate(self.act_quantizers):
+            view = self.flat[i:i + 1].view(q.delta.shape)
+            view.copy_(q.delta.detach())
+            q.delta = nn.Parameter(view, requires_grad=True)
+            self.delta_params.append(q.delta)
+        with torch.no_grad():                                        # weights are constants in this phase
+            for m in self.modules:
+                m._engine_weight = m.weight_quantizer(m.weight).detach()
+
+    # ------------------------------------------------------------------------------------------ one iteration
+    def _iteration(self):
+        ops.loop_advance(self.step_dev, self.idx_table, self.idx_live, self.b_table, self.b_live,
+                         self.lr_table, self.lr_live, max(self.iters, 1))
+        ops.gather_rows(self.cached_inps, self.idx_live, out=self.cur_inp)
+        if not self.act_quant:
+            self.table.forward(True, self.b_live, self.weight, self.reg_dev)
+        with torch.enable_grad():
+            out = self.unit(self.cur_inp)
+        loss, dpred = ops.recon_loss(out.detach(), self.cached_outs, self.p, self.opt_mode, fisher=self.cached_grads,
+                                     tgt_index=self.idx_live)
+        self.loss_dev = loss
+        if self.act_quant:
+            grads = torch.autograd.grad([out], self.delta_params, [dpred.view_as(out)], allow_unused=True)
+            if self.delta_params:
+                packed = torch.stack([torch.zeros((), device=self.dev) if g is None else g.reshape(()) for g in grads])
+                self.gflat[:packed.numel()].copy_(packed)
+        else:
+            gwqs = torch.autograd.grad([out], self.wq_leaves, [dpred.view_as(out)])
+            self.table.backward(gwqs, self.b_live, self.weight)
+        if self.multi_gpu:
+            ssq_dist.all_reduce_sum_(self.gflat)                     # SUM, as link.allreduce at block_recon.py:100-102
+        ops.adam_step(self.flat, self.gflat, self.exp_avg, self.exp_avg_sq, self.lr_live, self.step_dev)
+
+    # ------------------------------------------------------------------------------------------ graph capture
+    def _snapshot(self):
+        return (self.flat.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(), self.step_dev.clone())
+
+    def _restore(self, snap):
+        self.flat.copy_(snap[0]); self.exp_avg.copy_(snap[1]); self.exp_avg_sq.copy_(snap[2]); self.step_dev.copy_(snap[3])
+
+    def capture(self, warm: int = 3):
+        """warm up eagerly on a side stream (allocations, cuDNN plans, workspaces), roll the state back,
+        then capture one iteration"""
+        snap = self._snapshot()
+        side = torch.cuda.Stream(self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            for _ in range(warm):
+                self._iteration()
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        self._restore(snap)
+        before = ops.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._iteration()
+        self.launches_per_iter = ops.launch_count() - before
+        self._restore(snap)
+
+    # ------------------------------------------------------------------------------------------ driver
+    def step(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            before = ops.launch_count()
+            self._iteration()
+            self.launches_per_iter = ops.launch_count() - before
+
+    def run(self):
+        if self.iters <= 0:
+            return
+        if self.use_graph and self.graph is None:
+            self.capture()
+        for i in range(self.iters):
+            self.step()
+            count = i + 1
+            if self.verbose and count % 500 == 0:
+                rec, rnd = float(self.loss_dev), float(self.reg_dev)
+                print('Total loss:\t{:.3f} (rec:{:.3f}, round:{:.3f})\tb={:.2f}\tcount={}'.format(
+                    rec + rnd, rec, rnd, float(self.b_live), count))
+
+    def close(self):
+        for m in self.modules:
+            m._engine_weight = None
+        for q, flag in self._frozen:
+            q.requires_grad_(flag)
+        if self.act_quant:
+            for q in self.act_quantizers:
+                q.delta.requires_grad_(True)
+        else:
+            for m in self.modules:
+                m.weight_quantizer.alpha.requires_grad_(True)
+        self.graph = None

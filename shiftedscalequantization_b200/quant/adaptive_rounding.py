@@ -26,12 +26,9 @@ class AdaRoundQuantizer(nn.Module):
         self.soft_targets = False
         self.gamma, self.zeta = -0.1, 1.1
         self.beta = 2 / 3
-        self._precomputed = None      # set by the reconstruction engine: weight already produced by a multi-tensor launch
         self.init_alpha(x=weight_tensor.clone())
 
     def forward(self, x):
-        if self._precomputed is not None:
-            return self._precomputed
         hi = float(self.n_levels - 1)       # upstream always clamps unsigned here, even if sym (adaptive_rounding.py:58)
         if self.round_mode == 'learned_hard_sigmoid':
             if self.soft_targets:

@@ -1,0 +1,132 @@
+"""block_reconstruction / LossFunction / LinearTempDecay — mirror of the reference's quant/block_recon.py.
+
+The public function keeps the upstream signature and side effects (quantiser swap, quant-state toggles,
+hard rounding at the end); the 20 000-iteration loop itself runs in ..engine.ReconEngine.
+LossFunction stays usable on its own (callers such as notebooks build it directly); it evaluates the same
+three fused kernels — reconstruction loss, rounding regulariser — under autograd.
+"""
+import torch
+
+from .. import ops
+from ..engine import ReconEngine, temperature
+from .adaptive_rounding import AdaRoundQuantizer
+from .data_utils import save_grad_data, save_inp_oup_data
+from .quant_block import BaseQuantBlock
+from .quant_layer import QuantModule, StraightThrough, lp_loss
+from .quant_model import QuantModel
+
+
+def _quant_modules(unit):
+    return [m for _n, m in unit.named_modules() if isinstance(m, QuantModule)]
+
+
+def reconstruct_unit(model, unit, cali_data, *, is_block, batch_size, iters, weight, opt_mode, asym, include_act_func,
+                     b_range, warmup, act_quant, lr, p, multi_gpu, eval):
+    """shared body of block_reconstruction (block_recon.py:10-116) and layer_reconstruction (layer_recon.py:10-104)"""
+    if eval:
+        iters = 0          # structure-only call: swap the quantisers, learn nothing (block_recon.py:36-37)
+    model.set_quant_state(False, False)
+    unit.set_quant_state(True, act_quant)
+    round_mode = 'learned_hard_sigmoid'
+    if not include_act_func:
+        org_act_func = unit.activation_function
+        unit.activation_function = StraightThrough()
+    modules = _quant_modules(unit)
+    act_quantizers = []
+    if not act_quant:
+        for m in modules:
+            m.weight_quantizer = AdaRoundQuantizer(uaq=m.weight_quantizer, round_mode=round_mode,
+                                                   weight_tensor=m.org_weight.data)
+            m.weight_quantizer.soft_targets = True
+    else:
+        if is_block and hasattr(unit.act_quantizer, 'delta'):
+            act_quantizers.append(unit.act_quantizer)
+        act_quantizers += [m.act_quantizer for m in modules if m.act_quantizer.delta is not None]
+
+    if iters > 0:
+        cached_inps, cached_outs = save_inp_oup_data(model, unit, cali_data, asym, act_quant, batch_size)
+        cached_grads = save_grad_data(model, unit, cali_data, act_quant, batch_size=batch_size) if opt_mode != 'mse' else None
+        engine = ReconEngine(unit, modules, cached_inps, cached_outs, cached_grads, act_quant=act_quant, iters=iters,
+                             weight=weight, b_range=b_range, warmup=warmup, p=p, lr=lr, opt_mode=opt_mode,
+                             batch_size=batch_size, multi_gpu=multi_gpu, act_quantizers=act_quantizers)
+        try:
+            engine.run()
+        finally:
+            engine.close()
+        del cached_inps, cached_outs, cached_grads
+        torch.cuda.empty_cache()
+
+    for m in modules:                       # finish: hard rounding (block_recon.py:110-112, layer_recon.py:100)
+        m.weight_quantizer.soft_targets = False
+    if not include_act_func:
+        unit.activation_function = org_act_func
+
+
+def block_reconstruction(model: QuantModel, block: BaseQuantBlock, cali_data: torch.Tensor,
+                         batch_size: int = 32, iters: int = 20000, weight: float = 0.01, opt_mode: str = 'mse',
+                         asym: bool = False, include_act_func: bool = True, b_range: tuple = (20, 2),
+                         warmup: float = 0.0, act_quant: bool = False, lr: float = 4e-5, p: float = 2.0,
+                         multi_gpu: bool = False, eval: bool = False):
+    """Optimise the rounding (or, with act_quant, the activation step sizes) of every layer in `block` so the
+    block output matches the FP block output on the calibration data. Arguments as upstream."""
+    reconstruct_unit(model, block, cali_data, is_block=True, batch_size=batch_size, iters=iters, weight=weight,
+                     opt_mode=opt_mode, asym=asym, include_act_func=include_act_func, b_range=b_range, warmup=warmup,
+                     act_quant=act_quant, lr=lr, p=p, multi_gpu=multi_gpu, eval=eval)
+
+
+class LossFunction:
+    """rec_loss + rounding regulariser (block_recon.py:119-182). `count` is incremented before use."""
+
+    def __init__(self, block, round_loss: str = 'relaxation', weight: float = 1., rec_loss: str = 'mse',
+                 max_count: int = 2000, b_range: tuple = (10, 2), decay_start: float = 0.0, warmup: float = 0.0,
+                 p: float = 2.):
+        self.block = block
+        self.layer = block
+        self.round_loss = round_loss
+        self.weight = weight
+        self.rec_loss = rec_loss
+        self.loss_start = max_count * warmup
+        self.p = p
+        self.temp_decay = LinearTempDecay(max_count, rel_start_decay=warmup + (1 - warmup) * decay_start,
+                                          start_b=b_range[0], end_b=b_range[1])
+        self.count = 0
+
+    def __call__(self, pred, tgt, grad=None):
+        self.count += 1
+        if self.rec_loss == 'mse':
+            rec_loss = lp_loss(pred, tgt, p=self.p)
+        elif self.rec_loss in ('fisher_diag', 'fisher_full'):
+            rec_loss = ops.ReconLoss.apply(pred, tgt, 2.0, self.rec_loss, grad)
+        else:
+            raise ValueError('Not supported reconstruction loss function: {}'.format(self.rec_loss))
+        b = self.temp_decay(self.count)
+        if self.count < self.loss_start or self.round_loss == 'none':
+            b = round_loss = 0
+        elif self.round_loss == 'relaxation':
+            round_loss = 0
+            b_dev = ops.scalar_dev(b, pred.device)
+            for m in _quant_modules(self.block):
+                round_loss = round_loss + ops.RoundReg.apply(m.weight_quantizer.alpha, b_dev, self.weight)
+        else:
+            raise NotImplementedError
+        total_loss = rec_loss + round_loss
+        if self.count % 500 == 0:
+            print('Total loss:\t{:.3f} (rec:{:.3f}, round:{:.3f})\tb={:.2f}\tcount={}'.format(
+                float(total_loss), float(rec_loss), float(round_loss), b, self.count))
+        return total_loss
+
+
+class LinearTempDecay:
+    """temperature b(t): start_b until rel_start_decay*t_max, then linear to end_b (block_recon.py:185-202)"""
+
+    def __init__(self, t_max: int, rel_start_decay: float = 0.2, start_b: int = 10, end_b: int = 2):
+        self.t_max = t_max
+        self.start_decay = rel_start_decay * t_max
+        self.start_b = start_b
+        self.end_b = end_b
+
+    def __call__(self, t):
+        if t < self.start_decay:
+            return self.start_b
+        rel_t = (t - self.start_decay) / (self.t_max - self.start_decay)
+        return self.end_b + (self.start_b - self.end_b) * max(0.0, (1 - rel_t))

@@ -197,6 +197,7 @@ class QuantModule(nn.Module):
         self.beta_out = nn.Parameter(torch.zeros(affine_shape))     # README's varphi^z
         self._affine_key = None
         self._affine_identity = True
+        self._engine_weight = None      # set by ReconEngine: weight already produced by a multi-tensor launch
         self.selection = None
         self.selectionInited = False
         self.pathName = ''
@@ -218,7 +219,8 @@ class QuantModule(nn.Module):
             self.cached_inp_features += [input.cpu().clone().detach()]
         quantized = self.use_weight_quant and self.cache_features == 'none'
         if quantized:
-            weight, bias = self.weight_quantizer(self.weight), self.bias
+            weight = self._engine_weight if self._engine_weight is not None else self.weight_quantizer(self.weight)
+            bias = self.bias
         else:
             weight, bias = self.org_weight, self.org_bias
         out = self.fwd_func(input, weight, bias, **self.fwd_kwargs)
