@@ -5,9 +5,7 @@ import torch.nn as nn
 import torch.nn.init as init
 
 
-class StraightThrough(nn.Module):
-    def forward(self, input):
-        return input
+from .quant_layer import StraightThrough  # noqa: E402  (upstream defines a second identical class here)
 
 
 def _fold_bn(conv_module, bn_module):

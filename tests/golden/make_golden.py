@@ -256,6 +256,64 @@ def main():
     traj["cosine_lr"] = np.array(lrs, dtype=np.float64)
     save("adam", **traj)
 
+    # ---------------------------------------------------------------- reconstruction loops (tiny ResNet-18, CPU)
+    from quant import QuantModel, QuantModule, layer_reconstruction
+    from quant.data_utils import save_inp_oup_data
+    from models.resnet import resnet18 as ref_resnet18
+    torch.manual_seed(1005)
+    cnn = ref_resnet18(num_classes=10).eval()
+    wq = {'n_bits': 2, 'channel_wise': True, 'scale_method': 'max'}     # 'max': the mse init of 5.8k channels takes ~50 s here
+    aq = {'n_bits': 4, 'channel_wise': False, 'scale_method': 'mse', 'leaf_param': True}
+    qnn = QuantModel(model=cnn, weight_quant_params=wq, act_quant_params=aq).eval()
+    qnn.set_first_last_layer_to_8bit()
+    cali = torch.randn(32, 3, 16, 16)
+    qnn.set_quant_state(True, False)
+    with torch.no_grad():
+        qnn(cali)
+    # the network itself is not stored: zoo.resnet18(num_classes=10) under torch.manual_seed(1005) is bit-identical
+    # to the reference constructor (checked in tests/test_host_cpu.py against the probe weights below)
+    rl = {"cali": npy(cali), "probe.conv1_w": npy(qnn.model.conv1.org_weight[:4]),
+          "probe.l4_w": npy(qnn.model.layer4[1].conv2.org_weight[:2])}
+    # -- block loop: the body of quant/block_recon.py:89-105 driven here because :88-93 hard-code 'cuda'
+    block = qnn.model.layer1[0]
+    iters, bs = 12, 16
+    qnn.set_quant_state(False, False); block.set_quant_state(True, False)
+    mods = [m for _n, m in block.named_modules() if isinstance(m, QuantModule)]
+    for m in mods:
+        m.weight_quantizer = AdaRoundQuantizer(uaq=m.weight_quantizer, round_mode='learned_hard_sigmoid', weight_tensor=m.org_weight.data)
+        m.weight_quantizer.soft_targets = True
+    opt = torch.optim.Adam([m.weight_quantizer.alpha for m in mods])
+    lf = LossFunction(block, round_loss='relaxation', weight=0.01, max_count=iters, rec_loss='mse', b_range=(20, 2),
+                      decay_start=0, warmup=0.2, p=2.0)
+    inps, outs = save_inp_oup_data(qnn, block, cali, True, False, bs)
+    torch.manual_seed(77)
+    idx_tab, losses = [], []
+    for i in range(iters):
+        idx = torch.randperm(inps.size(0))[:bs]
+        idx_tab.append(npy(idx))
+        opt.zero_grad()
+        err = lf(block(inps[idx]), outs[idx])
+        err.backward(retain_graph=True)
+        opt.step()
+        losses.append(float(err))
+    rl.update({"block.inps": npy(inps), "block.outs": npy(outs), "block.idx": np.stack(idx_tab), "block.losses": np.array(losses)})
+    for n, m in (("conv1", block.conv1), ("conv2", block.conv2)):
+        rl.update({f"block.{n}.weight": npy(m.org_weight), f"block.{n}.bias": npy(m.org_bias), f"block.{n}.delta": npy(m.weight_quantizer.delta),
+                   f"block.{n}.zp": npy(m.weight_quantizer.zero_point), f"block.{n}.alpha": npy(m.weight_quantizer.alpha)})
+    for m in mods:
+        m.weight_quantizer.soft_targets = False
+    # -- layer loop: the real layer_reconstruction (runs on CPU unmodified); the RNG stream starts at seed 78
+    torch.manual_seed(78)
+    layer_reconstruction(qnn, qnn.model.fc, cali_data=cali, iters=iters, weight=0.01, asym=True, b_range=(20, 2), warmup=0.2,
+                         act_quant=False, opt_mode='mse', batch_size=bs)
+    fc = qnn.model.fc
+    rl.update({"fc.weight": npy(fc.org_weight), "fc.bias": npy(fc.org_bias), "fc.delta": npy(fc.weight_quantizer.delta),
+               "fc.zp": npy(fc.weight_quantizer.zero_point), "fc.alpha": npy(fc.weight_quantizer.alpha)})
+    qnn.set_quant_state(True, False)
+    with torch.no_grad():
+        rl["final_logits"] = npy(qnn(cali[:8]))
+    save("recon_loop", **rl)
+
 
 if __name__ == "__main__":
     main()

@@ -1,0 +1,223 @@
+"""CPU suite for the host logic: C-ABI surface, model refactoring, schedules, RNG stream, loud failure
+without CUDA, the oracle's loop restatement against the real reference's loops, 2-rank gloo plumbing."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, assert_close, assert_exact, golden
+
+WQ = {'n_bits': 2, 'channel_wise': True, 'scale_method': 'mse'}
+AQ = {'n_bits': 4, 'channel_wise': False, 'scale_method': 'mse', 'leaf_param': True}
+
+
+# ------------------------------------------------------------------------------------------- C-ABI
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "ssq_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(ssq_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    from shiftedscalequantization_b200 import _lib, build
+    build.build()
+    lib = ctypes.CDLL(str(_lib.LIB_PATH))
+    names = _declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/ssq_b200.h but not exported"
+        assert n in _lib.PROTOTYPES, f"{n} has no ctypes prototype"
+    assert set(_lib.PROTOTYPES) == set(names)
+    assert _lib.load().ssq_abi_version() == 1
+    assert _lib.load().ssq_ws_bytes(64) > 0
+    assert b"NULL" in _lib.load().ssq_status_string(-1)
+
+
+def test_argument_errors_are_reported_without_a_gpu():
+    """argument validation happens before any CUDA call, so it can be exercised here"""
+    from shiftedscalequantization_b200 import _lib
+    lib = _lib.load()
+    assert lib.ssq_fq_affine_fwd(None, None, None, None, None, None, 16, 4, 4, 0.0, 3.0, None) == -1      # NULL
+    assert lib.ssq_fq_affine_fwd(None, None, None, None, None, None, 0, 4, 4, 0.0, 3.0, None) == 0        # empty is a no-op
+    buf = (ctypes.c_float * 16)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert lib.ssq_fq_affine_fwd(p, p, p, None, p, None, 15, 4, 4, 0.0, 3.0, None) == -2                  # n % inner
+    assert lib.ssq_mse_scale_search(p, 1, 16, 1000, 0, 2.4, p, p, p, None, None, None, 0, None) == -2     # n_levels
+    assert lib.ssq_recon_loss(p, p, None, None, p, None, 2, 8, 4.0, 7, 2.0, None, None, 0, None) == -4     # mode
+
+
+def test_quantiser_refuses_cpu_tensors():
+    from shiftedscalequantization_b200 import ops
+    from shiftedscalequantization_b200._lib import SsqError
+    from shiftedscalequantization_b200.quant.quant_layer import UniformAffineQuantizer
+    q = UniformAffineQuantizer(n_bits=4, channel_wise=True, scale_method='mse')
+    with pytest.raises(SsqError, match="no CPU fallback"):
+        q(torch.randn(4, 3, 3, 3))
+    with pytest.raises(SsqError):
+        ops.recon_loss(torch.randn(2, 3), torch.randn(2, 3))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "shiftedscalequantization_b200")
+    for dirpath, _d, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in re.sub(r"#.*", "", src).replace("ssq_oracle", "oracle") or "import" not in \
+                    "".join(l for l in src.splitlines() if "oracle" in l), f"{f} references oracle/"
+
+
+# ------------------------------------------------------------------------------------------- model graph
+def _qnn(arch="resnet18", **kw):
+    from shiftedscalequantization_b200 import quant as Q, zoo
+    torch.manual_seed(1005)
+    cnn = zoo.build(arch, **kw).eval()
+    return Q, Q.QuantModel(cnn, dict(WQ), dict(AQ))
+
+
+def test_resnet18_refactor_matches_survey_counts():
+    Q, qnn = _qnn()
+    from shiftedscalequantization_b200.quant.quant_block import QuantBasicBlock
+    from shiftedscalequantization_b200.quant.quant_layer import StraightThrough
+    mods = [m for m in qnn.modules() if isinstance(m, Q.QuantModule)]
+    blocks = [m for m in qnn.modules() if isinstance(m, Q.BaseQuantBlock)]
+    assert len(mods) == 21 and len(blocks) == 8 and all(isinstance(b, QuantBasicBlock) for b in blocks)
+    assert sum(m.weight.numel() for m in mods) == 11_678_912 and sum(m.weight.shape[0] for m in mods) == 5800
+    assert isinstance(qnn.model.bn1, StraightThrough) and isinstance(qnn.model.relu, StraightThrough)
+    assert isinstance(qnn.model.conv1.activation_function, torch.nn.ReLU)
+    assert qnn.model.layer1[0].conv1.pathName == '.layer1.0.conv1' and qnn.model.fc.pathName == '.fc'
+    qnn.set_first_last_layer_to_8bit()
+    assert mods[0].ignore_reconstruction and mods[0].weight_quantizer.n_bits == 8 and mods[-1].weight_quantizer.n_levels == 256
+    assert mods[-2].act_quantizer.n_bits == 8
+    qnn.disable_network_output_quantization()
+    assert mods[-1].disable_act_quant
+    # FP forward works on CPU (no quantiser kernel involved) and BN folding kept the function
+    torch.manual_seed(1005)
+    from shiftedscalequantization_b200 import zoo
+    ref = zoo.resnet18().eval()
+    x = torch.randn(2, 3, 64, 64)
+    with torch.no_grad():
+        assert torch.allclose(qnn(x), ref(x), atol=1e-4)
+    qnn.set_quant_state(True, True)
+    assert all(m.use_weight_quant and m.use_act_quant for m in mods)
+    qnn.store_quantization_state(); qnn.set_quant_state(False, False); qnn.restore_quantization_state()
+    assert all(m.use_weight_quant for m in mods) and not any(m.use_act_quant for m in mods)
+
+
+@pytest.mark.parametrize("arch,n_units,n_qm", [("resnet50", 18, 54), ("mobilenetv2", 20, 53), ("regnetx_600m", 18, 54), ("regnetx_3200m", 27, 81)])
+def test_other_families_build(arch, n_units, n_qm):
+    Q, qnn = _qnn(arch)
+    mods = [m for m in qnn.modules() if isinstance(m, Q.QuantModule)]
+    blocks = [m for m in qnn.modules() if isinstance(m, Q.BaseQuantBlock)]
+    in_blocks = {id(m) for b in blocks for m in b.modules() if isinstance(m, Q.QuantModule)}
+    units = len(blocks) + sum(1 for m in mods if id(m) not in in_blocks)
+    assert (units, len(mods)) == (n_units, n_qm)
+    assert all(b.pathName for b in blocks)
+
+
+def test_zoo_seeded_init_equals_reference_probe():
+    from shiftedscalequantization_b200 import quant as Q, zoo
+    g = golden("recon_loop")
+    torch.manual_seed(1005)
+    qnn = Q.QuantModel(zoo.resnet18(num_classes=10).eval(), dict(WQ, scale_method='max'), dict(AQ))
+    assert_exact(qnn.model.conv1.org_weight[:4].numpy(), g["probe.conv1_w"], "stem weights")
+    assert_exact(qnn.model.layer4[1].conv2.org_weight[:2].numpy(), g["probe.l4_w"], "layer4 weights")
+    assert_exact(torch.randn(32, 3, 16, 16).numpy(), g["cali"], "calibration tensor")
+
+
+# ------------------------------------------------------------------------------------------- schedules / RNG
+def test_schedules_follow_the_reference():
+    from shiftedscalequantization_b200.engine import brecq_b_table, cosine_lr_table, index_table, temperature
+    g = golden("loss")
+    assert [float(temperature(int(t), 200, 0.2, 20, 2)) for t in g["temp.t"]] == [float(v) for v in g["temp.b"]]
+    tab = brecq_b_table(200, 0.2, (20, 2), True)
+    assert float(tab[38]) == 0.0 and float(tab[39]) == 20.0                 # count = i+1 reaches loss_start = 40 at i = 39
+    assert float(tab[199]) == 2.0 and brecq_b_table(10, 0.2, (20, 2), False).abs().sum() == 0
+    assert_close(cosine_lr_table(4e-4, 50).numpy(), golden("adam")["cosine_lr"], rtol=1e-6, what="cosine lr")
+    torch.manual_seed(5); a = index_table(100, 32, 6)
+    torch.manual_seed(5); b = torch.stack([torch.randperm(100)[:32] for _ in range(6)])
+    assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------- oracle loop vs reference loop
+def _golden_block_unit(g):
+    L = {}
+    for n, act in (("conv1", "relu"), ("conv2", None)):
+        L[n] = dict(weight=torch.from_numpy(g[f"block.{n}.weight"]), bias=torch.from_numpy(g[f"block.{n}.bias"]),
+                    conv=dict(stride=1, padding=1, dilation=1, groups=1), act=act, delta=torch.from_numpy(g[f"block.{n}.delta"]),
+                    zero_point=torch.from_numpy(g[f"block.{n}.zp"]), n_levels=4)
+    return {"kind": "basic", "layers": L, "tail_act": "relu"}
+
+
+def test_oracle_loop_reproduces_reference_block_loop():
+    from oracle import ref_loop_torch as R
+    g = golden("recon_loop")
+    unit = _golden_block_unit(g)
+    alphas, losses = R.recon_weight_loop(unit, torch.from_numpy(g["block.inps"]), torch.from_numpy(g["block.outs"]),
+                                         torch.from_numpy(g["block.idx"]), 12, weight=0.01, b_range=(20, 2), warmup=0.2)
+    assert_close(np.array(losses), g["block.losses"], rtol=1e-6, what="loss trace")
+    for n in ("conv1", "conv2"):
+        assert_close(alphas[n].detach().numpy(), g[f"block.{n}.alpha"], rtol=1e-6, what=f"alpha {n}")
+
+
+def test_oracle_loop_reproduces_reference_layer_reconstruction():
+    """also proves the index stream: the table is regenerated from the seed, not stored"""
+    from oracle import ref_loop_torch as R
+    from shiftedscalequantization_b200.engine import index_table
+    g = golden("recon_loop")
+    unit = {"kind": "layer", "layers": {"fc": dict(weight=torch.from_numpy(g["fc.weight"]), bias=torch.from_numpy(g["fc.bias"]),
+            conv=None, act=None, delta=torch.from_numpy(g["fc.delta"]), zero_point=torch.from_numpy(g["fc.zp"]), n_levels=256)}}
+    # inputs of fc = pooled features; outputs = FP logits: regenerate them with the FP weights of the golden run
+    from shiftedscalequantization_b200 import quant as Q, zoo
+    torch.manual_seed(1005)
+    cnn = zoo.resnet18(num_classes=10).eval()
+    feats = []
+    h = cnn.avgpool.register_forward_hook(lambda m, i, o: feats.append(torch.flatten(o, 1)))
+    # the golden run's fc input comes from the quantised prefix (asym=True), which needs the GPU path; here we only
+    # check the loop mechanics on the FP features (GPU test test_full_api_matches_reference_loops covers the rest)
+    with torch.no_grad():
+        logits = cnn(torch.from_numpy(g["cali"]))
+    h.remove()
+    torch.manual_seed(78)
+    tab = index_table(32, 16, 12)
+    alphas, losses = R.recon_weight_loop(unit, feats[0], logits, tab, 12, weight=0.01, b_range=(20, 2), warmup=0.2)
+    assert np.isfinite(losses).all() and alphas["fc"].shape == (10, 512)
+
+
+# ------------------------------------------------------------------------------------------- 2-rank gloo
+_WORKER = r'''
+import os, sys, torch
+sys.path.insert(0, os.environ["SSQ_ROOT"])
+from shiftedscalequantization_b200 import dist as D
+rk, local, world = D.init_from_env("gloo")
+assert (world, D.world_size(), D.rank()) == (2, 2, rk)
+lo, hi = D.shard_range(1024)
+assert (lo, hi) == ((0, 512) if rk == 0 else (512, 1024))
+cali = torch.arange(10.).reshape(10, 1)
+assert D.shard_calibration(cali).shape[0] == 5
+# gradient bucket: SUM all-reduce keeps replicas identical (block_recon.py:100-102 semantics)
+g = torch.full((7,), float(rk + 1)); D.all_reduce_sum_(g); assert torch.equal(g, torch.full((7,), 3.0))
+d = torch.tensor([1.0 + rk]); D.all_average_(d); assert float(d) == 1.5
+# output-channel-sharded scale search: every rank contributes its rows, all ranks see all rows
+rows = torch.arange(9.).reshape(9, 1)
+lo, hi = D.shard_range(9)
+full = D.all_gather_rows(rows[lo:hi] * 2, 9)
+assert torch.equal(full, rows * 2)
+print("rank", rk, "ok")
+'''
+
+
+def test_two_rank_gloo_plumbing(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, SSQ_ROOT=ROOT)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29611", str(script)]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout

@@ -148,3 +148,44 @@ def test_fisher_modes_run():
     for mode in ("fisher_diag", "fisher_full"):
         Q.block_reconstruction(qnn, block, cali_data=cali, iters=6, weight=0.01, asym=True, warmup=0.2, opt_mode=mode, batch_size=16)
         assert torch.isfinite(block.conv2.weight_quantizer.alpha).all()
+
+
+def test_full_api_matches_reference_loops():
+    """Public API end to end against the REAL reference run on the CPU (tests/golden/recon_loop.npz): same seeded
+    network, same calibration tensor, same RNG stream for the mini-batches. 12 Adam steps on layer1.0 (block loop),
+    then layer_reconstruction of fc on top of it, then the quantised logits."""
+    from conftest import golden
+    from shiftedscalequantization_b200 import quant as Q, zoo
+    from shiftedscalequantization_b200.quant.data_utils import save_inp_oup_data
+    g = golden("recon_loop")
+    torch.manual_seed(1005)
+    cnn = zoo.resnet18(num_classes=10).cuda().eval()
+    qnn = Q.QuantModel(cnn, dict(WQ, scale_method='max'), dict(AQ)).cuda().eval()
+    qnn.set_first_last_layer_to_8bit()
+    cali = torch.from_numpy(g["cali"])
+    qnn.set_quant_state(True, False)
+    with torch.no_grad():
+        qnn(cali.cuda())
+    block = qnn.model.layer1[0]
+    for n, m in (("conv1", block.conv1), ("conv2", block.conv2)):          # 'max' init is host double arithmetic: exact
+        assert_exact(m.weight_quantizer.delta.detach().cpu().numpy(), g[f"block.{n}.delta"], "delta")
+        assert_exact(m.weight_quantizer.zero_point.detach().cpu().numpy(), g[f"block.{n}.zp"], "zero_point")
+    inps, outs = save_inp_oup_data(qnn, block, cali, True, False, 16)
+    assert_close(inps.cpu().numpy(), g["block.inps"], rtol=1e-4, what="captured inputs (quantised prefix)")
+    assert_close(outs.cpu().numpy(), g["block.outs"], rtol=1e-4, what="captured FP outputs")
+    kw = dict(cali_data=cali, iters=12, weight=0.01, asym=True, b_range=(20, 2), warmup=0.2, act_quant=False,
+              opt_mode='mse', batch_size=16)
+    torch.manual_seed(77)
+    Q.block_reconstruction(qnn, block, **kw)
+    for n, m in (("conv1", block.conv1), ("conv2", block.conv2)):
+        a, ref = m.weight_quantizer.alpha.detach().cpu().numpy(), g[f"block.{n}.alpha"]
+        assert_close(a, ref, rtol=2e-3, what=f"alpha after 12 iterations ({n})")
+        assert (np.sign(a) == np.sign(ref)).mean() > 0.9995
+    torch.manual_seed(78)
+    Q.layer_reconstruction(qnn, qnn.model.fc, **kw)
+    a, ref = qnn.model.fc.weight_quantizer.alpha.detach().cpu().numpy(), g["fc.alpha"]
+    assert_close(a, ref, rtol=2e-3, what="fc alpha")
+    qnn.set_quant_state(True, False)
+    with torch.no_grad():
+        logits = qnn(cali[:8].cuda()).cpu().numpy()
+    assert_close(logits, g["final_logits"], rtol=5e-3, what="quantised logits vs reference")
