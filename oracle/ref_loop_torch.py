@@ -105,13 +105,16 @@ def unit_forward(unit, x, wqs, act_state=None):
 
 
 def recon_weight_loop(unit, cached_inps, cached_outs, idx_table, iters, weight=0.01, b_range=(20, 2), warmup=0.2,
-                      p=2.0, alphas=None, start_count=0):
-    """the weight-rounding loop: returns (alphas, losses). `idx_table[i]` is the mini-batch of iteration i."""
+                      p=2.0, alphas=None, start_count=0, t_max=None):
+    """the weight-rounding loop: returns (alphas, losses). `idx_table[i]` is the mini-batch of iteration i.
+    t_max/start_count let a caller run a slice of a longer schedule (the CPU baseline times iterations from the
+    middle of the 20 000-iteration schedule, where the regulariser is live and b is non-integer)."""
     L = unit["layers"]
     if alphas is None:
-        alphas = {n: init_alpha(s["weight"], s["delta"]).requires_grad_(True) for n, s in L.items()}
+        alphas = {n: init_alpha(s["weight"].detach(), s["delta"].detach()).requires_grad_(True) for n, s in L.items()}
     opt = torch.optim.Adam(list(alphas.values()))
-    loss_start = iters * warmup
+    t_max = iters if t_max is None else t_max
+    loss_start = t_max * warmup
     losses, count = [], start_count
     for i in range(iters):
         idx = idx_table[i]
@@ -121,7 +124,7 @@ def recon_weight_loop(unit, cached_inps, cached_outs, idx_table, iters, weight=0
         out_quant = unit_forward(unit, cur_inp, wqs)
         count += 1
         rec = lp_loss(out_quant, cur_out, p=p)
-        b = temperature(count, iters, warmup, b_range[0], b_range[1])
+        b = temperature(count, t_max, warmup, b_range[0], b_range[1])
         if count < loss_start:
             b = rnd = 0
         else:

@@ -86,11 +86,20 @@ class ReconEngine:
                  act_quant: bool, iters: int, weight: float, b_range=(20, 2), warmup: float = 0.0, p: float = 2.0,
                  lr: float = 4e-5, opt_mode: str = 'mse', batch_size: int = 32, multi_gpu: bool = False,
                  act_quantizers: Sequence[nn.Module] = (), use_graph: Optional[bool] = None,
-                 idx_table: Optional[torch.Tensor] = None, verbose: bool = True):
+                 idx_table: Optional[torch.Tensor] = None, verbose: bool = True,
+                 host_resident: bool = False, device: Optional[torch.device] = None):
+        """host_resident=True keeps the cached features in (pinned) host memory, as the reference does with
+        keep_gpu=False (quant/data_utils.py:34-36, `cached_inps[idx].to(device)` at block_recon.py:91-92): every
+        step copies its mini-batch rows host->device before the captured iteration runs."""
         self.unit, self.modules = unit, list(modules)
-        self.dev = cached_inps.device
+        self.host_resident = bool(host_resident)
+        self.dev = torch.device(device) if device is not None else cached_inps.device
         if self.dev.type != 'cuda':
             raise ops._lib.SsqError('reconstruction runs on CUDA only (no CPU fallback)')
+        if self.host_resident:
+            pin = lambda t: t if (t is None or t.is_pinned()) else t.contiguous().pin_memory()
+            cached_inps, cached_outs, cached_grads = pin(cached_inps.cpu()), pin(cached_outs.cpu()), \
+                pin(None if cached_grads is None else cached_grads.cpu())
         self.cached_inps = cached_inps.contiguous()
         self.cached_outs = cached_outs.contiguous()
         self.cached_grads = None if cached_grads is None else cached_grads.contiguous()
@@ -105,6 +114,8 @@ class ReconEngine:
         # ---- device-side schedules -------------------------------------------------------------------
         tab = idx_table if idx_table is not None else index_table(n, self.batch, self.iters)
         self.idx_table = tab.to(self.dev)
+        self.idx_table_host = tab.cpu()
+        self.host_step = 0
         self.b_table = brecq_b_table(self.iters, warmup, b_range, round_loss=not act_quant).to(self.dev)
         lr_tab = cosine_lr_table(lr, self.iters) if act_quant else torch.full((max(self.iters, 1),), 1e-3)
         self.lr_table = lr_tab.to(self.dev)
@@ -113,6 +124,9 @@ class ReconEngine:
         self.b_live = torch.zeros(1, device=self.dev)
         self.lr_live = torch.zeros(1, device=self.dev)
         self.cur_inp = torch.empty((self.batch,) + tuple(self.cached_inps.shape[1:]), device=self.dev)
+        self.cur_out = torch.empty((self.batch,) + tuple(self.cached_outs.shape[1:]), device=self.dev) if self.host_resident else None
+        self.cur_grad = torch.empty((self.batch,) + tuple(self.cached_grads.shape[1:]), device=self.dev) \
+            if (self.host_resident and self.cached_grads is not None) else None
         self.loss_dev = torch.zeros(1, device=self.dev)
         self.reg_dev = torch.zeros(1, device=self.dev)
         # ---- freeze everything that is not optimised (no wasted wgrad / bias-grad kernels) ---------------
@@ -167,16 +181,23 @@ class ReconEngine:
     def _iteration(self):
         ops.loop_advance(self.step_dev, self.idx_table, self.idx_live, self.b_table, self.b_live,
                          self.lr_table, self.lr_live, max(self.iters, 1))
-        ops.gather_rows(self.cached_inps, self.idx_live, out=self.cur_inp)
+        if not self.host_resident:
+            ops.gather_rows(self.cached_inps, self.idx_live, out=self.cur_inp)
         if not self.act_quant:
             self.table.forward(True, self.b_live, self.weight, self.reg_dev)
         with torch.enable_grad():
             out = self.unit(self.cur_inp)
-        loss, dpred = ops.recon_loss(out.detach(), self.cached_outs, self.p, self.opt_mode, fisher=self.cached_grads,
-                                     tgt_index=self.idx_live)
+        if self.host_resident:
+            loss, dpred = ops.recon_loss(out.detach(), self.cur_out, self.p, self.opt_mode, fisher=self.cur_grad)
+        else:
+            loss, dpred = ops.recon_loss(out.detach(), self.cached_outs, self.p, self.opt_mode, fisher=self.cached_grads,
+                                         tgt_index=self.idx_live)
         self.loss_dev = loss
         if self.act_quant:
-            grads = torch.autograd.grad([out], self.delta_params, [dpred.view_as(out)], allow_unused=True)
+            # a unit whose output does not depend on any step size (e.g. the head after
+            # disable_network_output_quantization) yields zero gradients: Adam then leaves the deltas untouched
+            grads = torch.autograd.grad([out], self.delta_params, [dpred.view_as(out)], allow_unused=True) \
+                if out.requires_grad else [None] * len(self.delta_params)
             if self.delta_params:
                 packed = torch.stack([torch.zeros((), device=self.dev) if g is None else g.reshape(()) for g in grads])
                 self.gflat[:packed.numel()].copy_(packed)
@@ -198,6 +219,8 @@ class ReconEngine:
         """warm up eagerly on a side stream (allocations, cuDNN plans, workspaces), roll the state back,
         then capture one iteration"""
         snap = self._snapshot()
+        if self.host_resident:
+            self._stage_batch_from_host(); self.host_step = 0
         side = torch.cuda.Stream(self.dev)
         side.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(side):
@@ -213,7 +236,26 @@ class ReconEngine:
         self._restore(snap)
 
     # ------------------------------------------------------------------------------------------ driver
+    def _stage_batch_from_host(self):
+        """H2D copy of this step's mini-batch rows straight from the pinned cache (one async copy per row:
+        no host-side gather; the batch-memcpy driver entry points are deliberately not used)"""
+        rows = self.idx_table_host[min(self.host_step, self.idx_table_host.shape[0] - 1)].tolist()
+        for j, r in enumerate(rows):
+            self.cur_inp[j].copy_(self.cached_inps[r], non_blocking=True)
+            self.cur_out[j].copy_(self.cached_outs[r], non_blocking=True)
+            if self.cur_grad is not None:
+                self.cur_grad[j].copy_(self.cached_grads[r], non_blocking=True)
+        self.host_step += 1
+
+    def h2d_bytes_per_step(self) -> int:
+        if not self.host_resident:
+            return 0
+        n = self.cur_inp.numel() + self.cur_out.numel() + (0 if self.cur_grad is None else self.cur_grad.numel())
+        return 4 * n
+
     def step(self):
+        if self.host_resident:
+            self._stage_batch_from_host()
         if self.graph is not None:
             self.graph.replay()
         else:

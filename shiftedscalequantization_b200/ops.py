@@ -54,9 +54,36 @@ def _ws(t: torch.Tensor, nchan: int = 1, tag: str = "default") -> torch.Tensor:
     return workspace(t.device, _lib.load().ssq_ws_bytes(int(nchan)), tag)
 
 
+_prof = None               # when a list: (name, start_event, end_event) per launch, for bench.py's kernel shares
+
+
+def profile_begin() -> None:
+    global _prof
+    _prof = []
+
+
+def profile_end() -> dict:
+    """{entry point: (launches, total ms)} measured with CUDA events on the launching stream"""
+    global _prof
+    rec, _prof = _prof or [], None
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1 in rec:
+        n, ms = out.get(name, (0, 0.0))
+        out[name] = (n + 1, ms + e0.elapsed_time(e1))
+    return out
+
+
 def _call(name: str, *args) -> None:
     global _launch_count
-    _lib.check(getattr(_lib.load(), name)(*args), name)
+    if _prof is not None:
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(getattr(_lib.load(), name)(*args), name)
+        e1.record()
+        _prof.append((name, e0, e1))
+    else:
+        _lib.check(getattr(_lib.load(), name)(*args), name)
     _launch_count += 1
 
 
