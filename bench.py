@@ -292,6 +292,7 @@ def kernel_microbench(dev, peak_gbs):
     res["fq_affine_fwd(acts,per-tensor)"] = timeit(lambda: ops.fq_affine_fwd(x, ds, zs, 0.0, 15.0), 8 * na)
     res["fq_affine_bwd(acts,per-tensor)"] = timeit(lambda: ops.fq_affine_bwd(t, x, ds, zs, 0.0, 15.0), 12 * na)
     res["recon_loss(fwd+dpred)"] = timeit(lambda: ops.recon_loss(x, t, 2.0), 12 * na)
+    res["recon_loss(fwd+dpred,p=2.4)"] = timeit(lambda: ops.recon_loss(x, t, 2.4), 12 * na)
     idx = torch.randperm(256, device=dev)
     res["gather_rows"] = timeit(lambda: ops.gather_rows(x, idx, out=t), 8 * na)
     del x, t
@@ -344,6 +345,11 @@ def run_ours(args):
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
 
+    if args.micro_only:
+        micro = kernel_microbench(dev, peak_gbs)
+        for k, v in micro.items():
+            print(f"{k:40s} {v['ms']:8.4f} ms  {v['gbs']:8.1f} GB/s  {v['frac']:.3f} of {peak_gbs:.0f}")
+        return
     n_total = args.images
     lo, hi = D.shard_range(n_total, rank, world)
     t_setup = time.perf_counter()
@@ -458,6 +464,7 @@ def main():
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-act", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--micro-only", action="store_true", help="only the DRAM-resident kernel microbench")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -17,7 +17,7 @@ struct AdaOut { float y, q, reg; };
 template <bool SOFT, bool REG>
 __device__ __forceinline__ AdaOut ada_fwd_one(float w, float a, float d, float z, float qmin, float qmax, float b) {
     AdaOut o;
-    float fl = floorf(__fdiv_rn(w, d));
+    float fl = floorf(div_exact(w, d));
     float r;
     o.reg = 0.f;
     if (SOFT) {
@@ -39,7 +39,7 @@ __device__ __forceinline__ float ada_bwd_one(float g, float w, float a, float d,
     float dh = rect_sigmoid_grad(a, h);
     float out = 0.f;
     if (REC) {
-        float xi = __fadd_rn(__fadd_rn(floorf(__fdiv_rn(w, d)), h), z);
+        float xi = __fadd_rn(__fadd_rn(floorf(div_exact(w, d)), h), z);
         bool inside = (xi >= qmin) && (xi <= qmax);
         out = inside ? (g * d) * dh : 0.f;
     }
@@ -143,9 +143,9 @@ ada_init_alpha_kernel(const float* __restrict__ w, const float* __restrict__ del
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         int64_t c = (nchan == 1) ? 0 : ((i / inner) % nchan);
-        float u = __fdiv_rn(w[i], __ldg(delta + c));
+        float u = div_exact(w[i], __ldg(delta + c));
         float rest = __fsub_rn(u, floorf(u));
-        float t = __fsub_rn(__fdiv_rn(SSQ_STRETCH, __fsub_rn(rest, SSQ_GAMMA)), 1.0f);
+        float t = __fsub_rn(div_exact(SSQ_STRETCH, __fsub_rn(rest, SSQ_GAMMA)), 1.0f);
         alpha[i] = -logf(t);
     }
 }

@@ -14,7 +14,7 @@ __device__ __forceinline__ float clampf(float v, float lo, float hi) {
 
 template <bool INSCALE>
 __device__ __forceinline__ float fq_one(float x, float d, float z, float s, float qmin, float qmax, float& q) {
-    float u = INSCALE ? __fdiv_rn(__fdiv_rn(x, s), d) : __fdiv_rn(x, d);
+    float u = INSCALE ? div_exact(div_exact(x, s), d) : div_exact(x, d);
     q = clampf(__fadd_rn(rintf(u), z), qmin, qmax);
     float y = __fmul_rn(__fsub_rn(q, z), d);
     return INSCALE ? __fmul_rn(y, s) : y;
@@ -98,7 +98,7 @@ fq_affine_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x, 
     double acc[2] = {0.0, 0.0};
     float sd = 0.f, sz = 0.f;  // fp32 running sums flushed to double every few vectors
     auto one = [&](float g, float xv, float& gxo) {
-        float u = __fdiv_rn(xv, d);
+        float u = div_exact(xv, d);
         float r = rintf(u);
         float xi = __fadd_rn(r, z);
         bool inside = (xi >= qmin) && (xi <= qmax);

@@ -20,7 +20,7 @@ __device__ __forceinline__ void probs_one(const float* a, int S, float* sm, floa
     float den = 0.f;
     _Pragma("unroll") for (int i = 0; i < MS; ++i) if (i < S) { sm[i] = expf(a[i] - m); den += sm[i]; }
     _Pragma("unroll") for (int i = 0; i < MS; ++i) if (i < S) {
-        sm[i] = __fdiv_rn(sm[i], den);
+        sm[i] = div_exact(sm[i], den);
         v[i] = __fadd_rn(__fmul_rn(sm[i], SSQ_STRETCH), SSQ_GAMMA);
         p[i] = fminf(fmaxf(v[i], 0.f), 1.f);
     }
@@ -67,7 +67,7 @@ shift_probs_bwd_kernel(const float* __restrict__ alpha, const float* __restrict_
         _Pragma("unroll") for (int i = 0; i < MS; ++i) if (i < S) {
             float gpi = gp ? gp[g * S + i] : 0.f;
             if (reg_on) {
-                float dr = (reg_mode == 0) ? -(logf(p[i] + 1e-10f) + __fdiv_rn(p[i], p[i] + 1e-10f)) : reg_term_grad(p[i], b);
+                float dr = (reg_mode == 0) ? -(logf(p[i] + 1e-10f) + div_exact(p[i], p[i] + 1e-10f)) : reg_term_grad(p[i], b);
                 gpi += lam_g * dr;
             }
             float gv = (v[i] >= 0.f && v[i] <= 1.f) ? gpi : 0.f;   // clamp backward, bounds inclusive
@@ -91,7 +91,7 @@ __device__ __forceinline__ float shift_one(float w, const ShiftCtx& c, const flo
                                            float* terms, bool& inside, float& dh) {
     float t[MS];
     _Pragma("unroll") for (int i = 0; i < MS; ++i) if (i < S) {
-        float u = __fdiv_rn(w, c.ds[i]);
+        float u = div_exact(w, c.ds[i]);
         if (MODE == SSQ_SHIFT_DEQUANT) {
             float q = clampk(__fadd_rn(rintf(u), c.z), qmin, qmax);
             t[i] = __fmul_rn(__fsub_rn(q, c.z), c.ds[i]);

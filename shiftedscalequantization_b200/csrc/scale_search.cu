@@ -27,9 +27,9 @@ __device__ __forceinline__ Cand make_cand(int i, float x_min, float x_max, float
     return c;
 }
 __device__ __forceinline__ float cand_err(float x, const Cand& c, float lm1, float p) {
-    float q = clampq(__fadd_rn(rintf(__fdiv_rn(x, c.d)), c.z), 0.f, lm1);
+    float q = clampq(__fadd_rn(rintf(div_exact(x, c.d)), c.z), 0.f, lm1);
     float xq = __fmul_rn(__fsub_rn(q, c.z), c.d);
-    return pow_scalar(fabsf(__fsub_rn(x, xq)), p);
+    return pow_scalar_accurate(fabsf(__fsub_rn(x, xq)), p);
 }
 __device__ __forceinline__ void apply_sym(float& x_min, float& x_max, int symmetric) {
     if (symmetric) {
@@ -273,8 +273,8 @@ using namespace ssq;
 
 extern "C" size_t ssq_mse_scale_search_ws_bytes(int64_t rows, int64_t k) {
     (void)rows; (void)k;
-    // ticket block + min/max slot + per-CTA min/max partials + per-CTA candidate partials
-    return 256 + 256 + (size_t)SSQ_NUM_SMS * SSQ_CTAS_PER_SM * 2 * sizeof(float) + (size_t)TENSOR_GRID * NC * sizeof(double);
+    // fixed ticket header + min/max slot + per-CTA min/max partials + per-CTA candidate partials
+    return ws_ticket_bytes(1) + 256 + (size_t)SSQ_NUM_SMS * SSQ_CTAS_PER_SM * 2 * sizeof(float) + (size_t)TENSOR_GRID * NC * sizeof(double);
 }
 
 static int minmax_launch(const float* x, int64_t rows, int64_t k, float* row_min, float* row_max,
@@ -322,11 +322,11 @@ extern "C" int ssq_mse_scale_search(const float* x, int64_t rows, int64_t k, int
         return launch_status();
     }
     if (!ws || ws_bytes < ssq_mse_scale_search_ws_bytes(rows, k)) return SSQ_ERR_WORKSPACE;
-    char* base = reinterpret_cast<char*>(ws);
-    unsigned int* tickets = reinterpret_cast<unsigned int*>(base);        // [0] minmax, [1] scores
-    float* mm = reinterpret_cast<float*>(base + 256);
-    float* mm_partial = reinterpret_cast<float*>(base + 512);
-    double* partial = reinterpret_cast<double*>(base + 512 + (size_t)SSQ_NUM_SMS * SSQ_CTAS_PER_SM * 2 * sizeof(float));
+    unsigned int* tickets = reinterpret_cast<unsigned int*>(ws);          // [0] minmax, [1] scores (shared header)
+    char* base = reinterpret_cast<char*>(ws) + ws_ticket_bytes(1);
+    float* mm = reinterpret_cast<float*>(base);
+    float* mm_partial = reinterpret_cast<float*>(base + 256);
+    double* partial = reinterpret_cast<double*>(base + 256 + (size_t)SSQ_NUM_SMS * SSQ_CTAS_PER_SM * 2 * sizeof(float));
     for (int64_t r = 0; r < rows; ++r) {
         const float* xr = x + r * k;
         int e = minmax_launch(xr, 1, k, mm, mm + 1, tickets, mm_partial, st);

@@ -410,3 +410,21 @@ def test_bad_arguments_raise(ops):
     with pytest.raises(SsqError):
         ops.fq_affine_fwd(torch.zeros(4, device="cuda").double(), torch.ones(1, device="cuda"),
                           torch.zeros(1, device="cuda"), 0.0, 3.0)
+
+
+def test_workspace_reuse_across_channel_counts(ops):
+    """regression: reductions with different channel counts share one workspace; the ticket header must not move"""
+    r = rng(99)
+    for rows, k in [(64, 576), (128, 576), (512, 4608), (3, 36), (1000, 512), (128, 1152)]:
+        x = torch.as_tensor(r.standard_normal((rows, k)).astype(np.float32)).cuda()
+        mn, mx = ops.row_minmax(x)
+        assert torch.equal(mn, x.min(1)[0]) and torch.equal(mx, x.max(1)[0]), (rows, k)
+        d = (x.abs().amax(1, keepdim=True) / 7).contiguous(); z = torch.full_like(d, 3.0)
+        gy = torch.as_tensor(r.standard_normal((rows, k)).astype(np.float32)).cuda()
+        _, gd, gz = ops.fq_affine_bwd(gy, x, d, z, 0.0, 15.0)
+        _, gd_ref, gz_ref = O.uaq_backward(host(gy), host(x), host(d), host(z), 0, 15)
+        assert_close(host(gd), gd_ref, what=f"gdelta {rows}x{k}"); assert_close(host(gz), gz_ref, what=f"gzp {rows}x{k}")
+        # per-tensor reduction on the same workspace in between
+        _, gd1, _ = ops.fq_affine_bwd(gy, x, d[:1].reshape(()), z[:1].reshape(()), 0.0, 15.0)
+        _, gd1_ref, _ = O.uaq_backward(host(gy), host(x), host(d[:1].reshape(())), host(z[:1].reshape(())), 0, 15)
+        assert_close(host(gd1), gd1_ref, what="per-tensor gdelta")
