@@ -1,9 +1,11 @@
-// K1b — AdaRound fake-quant: floor + rectified-sigmoid soft / hard rounding, with the rounding
-// regulariser sum(1-|2h-1|^b) and its gradient folded into the same pass over (w, alpha).
+// K1b — AdaRound fake-quant: floor + rectified-sigmoid soft / hard rounding, with the rounding regulariser
+// sum(1-|2h-1|^b) and its gradient folded into the same pass over (w, alpha).
 //   reference arithmetic: quant/adaptive_rounding.py:49-74, quant/block_recon.py:167-174,
 //   quant/channelQuant.py:66-78 (sym-aware bounds via qmin/qmax)
-// Single-tensor entry points serve the nn.Module surface; the *_mt entry points run every
-// QuantModule of a reconstruction unit in one launch from a device-resident descriptor table.
+// Single-tensor entry points serve the nn.Module surface; the *_mt entry points run every QuantModule of a
+// reconstruction unit in one launch from a descriptor table held in kernel-parameter space.
+// Per element: one exact division (hoisted reciprocal), 2 MUFU for the sigmoid, a 15-instruction log2 and one
+// MUFU.EX2 for t^b — about 45 instructions, under the ~66/element an HBM-bound 12 B/element kernel can issue.
 #include "ssq_common.cuh"
 
 namespace ssq {
@@ -15,9 +17,9 @@ __device__ __forceinline__ float clampf_(float v, float lo, float hi) {
 struct AdaOut { float y, q, reg; };
 
 template <bool SOFT, bool REG>
-__device__ __forceinline__ AdaOut ada_fwd_one(float w, float a, float d, float z, float qmin, float qmax, float b) {
+__device__ __forceinline__ AdaOut ada_fwd_one(float w, float a, const Recip& R, float z, float qmin, float qmax, float b) {
     AdaOut o;
-    float fl = floorf(div_exact(w, d));
+    const float fl = floorf(div_exact(w, R));
     float r;
     o.reg = 0.f;
     if (SOFT) {
@@ -27,126 +29,183 @@ __device__ __forceinline__ AdaOut ada_fwd_one(float w, float a, float d, float z
         r = (a >= 0.f) ? 1.f : 0.f;
     }
     o.q = clampf_(__fadd_rn(__fadd_rn(fl, r), z), qmin, qmax);
-    o.y = __fmul_rn(__fsub_rn(o.q, z), d);
+    o.y = __fmul_rn(__fsub_rn(o.q, z), R.d);
     return o;
 }
 
 // galpha for one element: reconstruction path + regulariser path
 template <bool REC, bool REG>
-__device__ __forceinline__ float ada_bwd_one(float g, float w, float a, float d, float z, float qmin, float qmax,
+__device__ __forceinline__ float ada_bwd_one(float g, float w, float a, const Recip& R, float z, float qmin, float qmax,
                                              float b, float lam_g) {
     float h;
-    float dh = rect_sigmoid_grad(a, h);
+    const float dh = rect_sigmoid_grad(a, h);
     float out = 0.f;
     if (REC) {
-        float xi = __fadd_rn(__fadd_rn(floorf(div_exact(w, d)), h), z);
-        bool inside = (xi >= qmin) && (xi <= qmax);
-        out = inside ? (g * d) * dh : 0.f;
+        const float xi = __fadd_rn(__fadd_rn(floorf(div_exact(w, R)), h), z);
+        const bool inside = (xi >= qmin) && (xi <= qmax);
+        out = inside ? (g * R.d) * dh : 0.f;
     }
     if (REG) out += lam_g * reg_term_grad(h, b) * dh;
     return out;
 }
 
-// ---- single tensor, forward -------------------------------------------------------------------
-// VEC: inner % 4 == 0 and 16B-aligned pointers. Each CTA walks tiles of SSQ_THREADS*4 elements.
-template <bool VEC, bool SOFT, bool REG>
+// body shared by the single-tensor and multi-tensor forward kernels: elements [e0, e1) of one tensor, visited by
+// `nthr` threads of which this is number `tid`; REGON is decided once per launch from *b_dev.
+template <bool SOFT, bool REGON>
+__device__ __forceinline__ double ada_fwd_span(const float* __restrict__ w, const float* __restrict__ alpha,
+                                               const float* __restrict__ delta, const float* __restrict__ zp,
+                                               float* __restrict__ wq, float* __restrict__ codes, int64_t e0, int64_t e1,
+                                               int64_t inner, int64_t nchan, float qmin, float qmax, float b,
+                                               int64_t tid, int64_t nthr, bool vec) {
+    double acc = 0.0;
+    ChanWalk cw;
+    if (vec) {
+        constexpr int U = 2;
+        const int64_t i0 = (e0 >> 2) + tid, i1 = e1 >> 2;
+        cw.init(i0, nthr, inner >> 2, nchan);
+        for (int64_t i = i0; i < i1; i += nthr * U) {
+            float4 wv[U], av[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t j = i + u * nthr;
+                if (j < i1) { wv[u] = ld_stream4(w + j * 4); av[u] = ld_stream4(alpha + j * 4); }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t j = i + u * nthr;
+                if (j < i1) {
+                    const Recip R = make_recip(__ldg(delta + cw.c));
+                    const float z = __ldg(zp + cw.c);
+                    float4 y, q;
+                    AdaOut o;
+                    float rsum = 0.f;
+#define ONE(F) o = ada_fwd_one<SOFT, REGON>(wv[u].F, av[u].F, R, z, qmin, qmax, b); y.F = o.y; q.F = o.q; rsum += o.reg;
+                    ONE(x) ONE(y) ONE(z) ONE(w)
+#undef ONE
+                    st_stream4(wq + j * 4, y);
+                    if (codes) st_stream4(codes + j * 4, q);
+                    if (REGON) acc += (double)rsum;
+                }
+                cw.next();
+            }
+        }
+    } else {
+        cw.init(e0 + tid, nthr, inner, nchan);
+        for (int64_t i = e0 + tid; i < e1; i += nthr) {
+            const Recip R = make_recip(__ldg(delta + cw.c));
+            const AdaOut o = ada_fwd_one<SOFT, REGON>(w[i], alpha[i], R, __ldg(zp + cw.c), qmin, qmax, b);
+            wq[i] = o.y;
+            if (codes) codes[i] = o.q;
+            if (REGON) acc += (double)o.reg;
+            cw.next();
+        }
+    }
+    return acc;
+}
+
+template <bool REC, bool REGON>
+__device__ __forceinline__ void ada_bwd_span(const float* __restrict__ gwq, const float* __restrict__ w,
+                                             const float* __restrict__ alpha, const float* __restrict__ delta,
+                                             const float* __restrict__ zp, float* __restrict__ galpha, int64_t e0, int64_t e1,
+                                             int64_t inner, int64_t nchan, float qmin, float qmax, float b, float lam_g,
+                                             int accumulate, int64_t tid, int64_t nthr, bool vec) {
+    ChanWalk cw;
+    if (vec) {
+        constexpr int U = 2;
+        const int64_t i0 = (e0 >> 2) + tid, i1 = e1 >> 2;
+        cw.init(i0, nthr, inner >> 2, nchan);
+        for (int64_t i = i0; i < i1; i += nthr * U) {
+            float4 wv[U], av[U], gv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t j = i + u * nthr;
+                if (j < i1) {
+                    wv[u] = ld_stream4(w + j * 4); av[u] = ld_stream4(alpha + j * 4);
+                    gv[u] = REC ? ld_stream4(gwq + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t j = i + u * nthr;
+                if (j < i1) {
+                    const Recip R = make_recip(__ldg(delta + cw.c));
+                    const float z = __ldg(zp + cw.c);
+                    float4 o;
+                    o.x = ada_bwd_one<REC, REGON>(gv[u].x, wv[u].x, av[u].x, R, z, qmin, qmax, b, lam_g);
+                    o.y = ada_bwd_one<REC, REGON>(gv[u].y, wv[u].y, av[u].y, R, z, qmin, qmax, b, lam_g);
+                    o.z = ada_bwd_one<REC, REGON>(gv[u].z, wv[u].z, av[u].z, R, z, qmin, qmax, b, lam_g);
+                    o.w = ada_bwd_one<REC, REGON>(gv[u].w, wv[u].w, av[u].w, R, z, qmin, qmax, b, lam_g);
+                    if (accumulate) {
+                        const float4 p = *reinterpret_cast<const float4*>(galpha + j * 4);
+                        o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+                    }
+                    st_stream4(galpha + j * 4, o);
+                }
+                cw.next();
+            }
+        }
+    } else {
+        cw.init(e0 + tid, nthr, inner, nchan);
+        for (int64_t i = e0 + tid; i < e1; i += nthr) {
+            const Recip R = make_recip(__ldg(delta + cw.c));
+            const float o = ada_bwd_one<REC, REGON>(REC ? gwq[i] : 0.f, w[i], alpha[i], R, __ldg(zp + cw.c), qmin, qmax, b, lam_g);
+            galpha[i] = accumulate ? galpha[i] + o : o;
+            cw.next();
+        }
+    }
+}
+
+// ---- single tensor ----------------------------------------------------------------------------------------
+template <bool SOFT, bool REG>
 __global__ void __launch_bounds__(SSQ_THREADS)
 ada_fwd_kernel(const float* __restrict__ w, const float* __restrict__ alpha, const float* __restrict__ delta,
                const float* __restrict__ zp, float* __restrict__ wq, float* __restrict__ codes,
-               int64_t n, int64_t inner, int64_t nchan, float qmin, float qmax,
+               int64_t n, int64_t inner, int64_t nchan, float qmin, float qmax, bool vec,
                const float* __restrict__ b_dev, float lambda, float* __restrict__ reg_out, WsView ws) {
     __shared__ double smem[32];
-    float b = 0.f;
-    if (REG) b = __ldg(b_dev);
+    const float b = REG ? __ldg(b_dev) : 0.f;
     const bool reg_on = REG && (b > 0.f);
-    double acc[1] = {0.0};
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    if (VEC) {
-        const int64_t n4 = n >> 2, inner4 = inner >> 2;
-        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-            int64_t c = (nchan == 1) ? 0 : ((i / inner4) % nchan);
-            float d = __ldg(delta + c), z = __ldg(zp + c);
-            float4 wv = ld_stream4(w + i * 4), av = ld_stream4(alpha + i * 4), y, q;
-            float rsum = 0.f;
-            AdaOut o;
-#define ONE(F) o = reg_on ? ada_fwd_one<SOFT, true>(wv.F, av.F, d, z, qmin, qmax, b) \
-                          : ada_fwd_one<SOFT, false>(wv.F, av.F, d, z, qmin, qmax, b); \
-               y.F = o.y; q.F = o.q; rsum += o.reg;
-            ONE(x) ONE(y) ONE(z) ONE(w)
-#undef ONE
-            st_stream4(wq + i * 4, y);
-            if (codes) st_stream4(codes + i * 4, q);
-            acc[0] += (double)rsum;
-        }
-    } else {
-        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-            int64_t c = (nchan == 1) ? 0 : ((i / inner) % nchan);
-            float d = __ldg(delta + c), z = __ldg(zp + c);
-            AdaOut o = reg_on ? ada_fwd_one<SOFT, true>(w[i], alpha[i], d, z, qmin, qmax, b)
-                              : ada_fwd_one<SOFT, false>(w[i], alpha[i], d, z, qmin, qmax, b);
-            wq[i] = o.y;
-            if (codes) codes[i] = o.q;
-            acc[0] += (double)o.reg;
-        }
-    }
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+    double acc[1];
+    acc[0] = reg_on ? ada_fwd_span<SOFT, true>(w, alpha, delta, zp, wq, codes, 0, n, inner, nchan, qmin, qmax, b, tid, nthr, vec)
+                    : ada_fwd_span<SOFT, false>(w, alpha, delta, zp, wq, codes, 0, n, inner, nchan, qmin, qmax, b, tid, nthr, vec);
     if (!REG) return;
     block_sum<1>(acc, smem);
     if (grid_finish<1>(acc, ws, 0, blockIdx.x, gridDim.x, smem) && threadIdx.x == 0)
         reg_out[0] = reg_on ? (float)((double)lambda * acc[0]) : 0.f;
 }
 
-template <bool VEC>
 __global__ void __launch_bounds__(SSQ_THREADS)
 ada_bwd_kernel(const float* __restrict__ gwq, const float* __restrict__ w, const float* __restrict__ alpha,
                const float* __restrict__ delta, const float* __restrict__ zp, float* __restrict__ galpha,
-               int64_t n, int64_t inner, int64_t nchan, float qmin, float qmax,
+               int64_t n, int64_t inner, int64_t nchan, float qmin, float qmax, bool vec,
                const float* __restrict__ b_dev, float lambda, const float* __restrict__ greg, int accumulate) {
-    float b = b_dev ? __ldg(b_dev) : 0.f;
+    const float b = b_dev ? __ldg(b_dev) : 0.f;
     const bool reg_on = b_dev && (b > 0.f);
     const float lam_g = reg_on ? lambda * (greg ? __ldg(greg) : 1.f) : 0.f;
-    const bool rec = gwq != nullptr;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    auto one = [&](float g, float wv, float av, float d, float z) -> float {
-        if (rec) return reg_on ? ada_bwd_one<true, true>(g, wv, av, d, z, qmin, qmax, b, lam_g)
-                               : ada_bwd_one<true, false>(g, wv, av, d, z, qmin, qmax, b, lam_g);
-        return reg_on ? ada_bwd_one<false, true>(g, wv, av, d, z, qmin, qmax, b, lam_g) : 0.f;
-    };
-    if (VEC) {
-        const int64_t n4 = n >> 2, inner4 = inner >> 2;
-        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-            int64_t c = (nchan == 1) ? 0 : ((i / inner4) % nchan);
-            float d = __ldg(delta + c), z = __ldg(zp + c);
-            float4 wv = ld_stream4(w + i * 4), av = ld_stream4(alpha + i * 4);
-            float4 g = rec ? ld_stream4(gwq + i * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 o;
-            o.x = one(g.x, wv.x, av.x, d, z); o.y = one(g.y, wv.y, av.y, d, z);
-            o.z = one(g.z, wv.z, av.z, d, z); o.w = one(g.w, wv.w, av.w, d, z);
-            if (accumulate) {
-                float4 p = *reinterpret_cast<const float4*>(galpha + i * 4);
-                o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
-            }
-            st_stream4(galpha + i * 4, o);
-        }
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+    if (gwq) {
+        if (reg_on) ada_bwd_span<true, true>(gwq, w, alpha, delta, zp, galpha, 0, n, inner, nchan, qmin, qmax, b, lam_g, accumulate, tid, nthr, vec);
+        else ada_bwd_span<true, false>(gwq, w, alpha, delta, zp, galpha, 0, n, inner, nchan, qmin, qmax, b, lam_g, accumulate, tid, nthr, vec);
     } else {
-        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-            int64_t c = (nchan == 1) ? 0 : ((i / inner) % nchan);
-            float o = one(rec ? gwq[i] : 0.f, w[i], alpha[i], __ldg(delta + c), __ldg(zp + c));
-            galpha[i] = accumulate ? galpha[i] + o : o;
-        }
+        if (reg_on) ada_bwd_span<false, true>(gwq, w, alpha, delta, zp, galpha, 0, n, inner, nchan, qmin, qmax, b, lam_g, accumulate, tid, nthr, vec);
+        else ada_bwd_span<false, false>(gwq, w, alpha, delta, zp, galpha, 0, n, inner, nchan, qmin, qmax, b, lam_g, accumulate, tid, nthr, vec);
     }
 }
 
-// alpha init: rest = w/delta - floor(w/delta); alpha = -log((zeta-gamma)/(rest-gamma) - 1)
+// alpha init: rest = w/delta - floor(w/delta); alpha = -log((zeta-gamma)/(rest-gamma) - 1)   (libm logf: one-off)
 __global__ void __launch_bounds__(SSQ_THREADS)
 ada_init_alpha_kernel(const float* __restrict__ w, const float* __restrict__ delta, float* __restrict__ alpha,
                       int64_t n, int64_t inner, int64_t nchan) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        int64_t c = (nchan == 1) ? 0 : ((i / inner) % nchan);
-        float u = div_exact(w[i], __ldg(delta + c));
-        float rest = __fsub_rn(u, floorf(u));
-        float t = __fsub_rn(div_exact(SSQ_STRETCH, __fsub_rn(rest, SSQ_GAMMA)), 1.0f);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    ChanWalk cw;
+    cw.init(first, stride, inner, nchan);
+    for (int64_t i = first; i < n; i += stride) {
+        const float u = __fdiv_rn(w[i], __ldg(delta + cw.c));
+        const float rest = __fsub_rn(u, floorf(u));
+        const float t = __fsub_rn(__fdiv_rn(SSQ_STRETCH, __fsub_rn(rest, SSQ_GAMMA)), 1.0f);
         alpha[i] = -logf(t);
+        cw.next();
     }
 }
 
@@ -177,7 +236,7 @@ round_reg_bwd_kernel(const float* __restrict__ v, int64_t n, const float* __rest
         float o = 0.f;
         if (b > 0.f) {
             float h;
-            float dh = rect_sigmoid_grad(v[i], h);
+            const float dh = rect_sigmoid_grad(v[i], h);
             o = lam_g * reg_term_grad(h, b) * dh;
         }
         gv[i] = accumulate ? gv[i] + o : o;
@@ -193,49 +252,32 @@ __device__ __forceinline__ int find_desc(const MtTable& table, int count, int64_
     for (int i = 1; i < count; ++i) if (table.d[i].tile_begin <= tile) lo = i;
     return lo;
 }
+__device__ __forceinline__ bool desc_vec(const ssq_adaround_desc& D, bool bwd) {
+    bool ok = (D.inner % 4 == 0) && aligned16(D.w) && aligned16(D.alpha);
+    return bwd ? (ok && aligned16(D.gwq) && aligned16(D.galpha)) : (ok && aligned16(D.wq));
+}
 
 template <bool SOFT>
 __global__ void __launch_bounds__(SSQ_THREADS)
 ada_fwd_mt_kernel(const __grid_constant__ MtTable table, int count, int64_t total_tiles,
                   const float* __restrict__ b_dev, float lambda, float* __restrict__ reg_out, WsView ws) {
     __shared__ double smem[32];
-    __shared__ ssq_adaround_desc D;
+    __shared__ int s_which;
     const float b = (SOFT && b_dev) ? __ldg(b_dev) : 0.f;
     const bool reg_on = SOFT && reg_out && (b > 0.f);
     double acc[1] = {0.0};
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         __syncthreads();
-        if (threadIdx.x == 0) D = table.d[find_desc(table, count, tile)];
+        if (threadIdx.x == 0) s_which = find_desc(table, count, tile);
         __syncthreads();
+        const ssq_adaround_desc& D = table.d[s_which];
         const int64_t e0 = (tile - D.tile_begin) * SSQ_MT_TILE;
         const int64_t e1 = e0 + SSQ_MT_TILE < D.n ? e0 + SSQ_MT_TILE : D.n;
-        const bool vec = (D.inner % 4 == 0) && aligned16(D.w) && aligned16(D.alpha) && aligned16(D.wq);
-        if (vec) {
-            const int64_t inner4 = D.inner >> 2;
-            for (int64_t i = (e0 >> 2) + threadIdx.x; i < (e1 >> 2); i += blockDim.x) {
-                int64_t c = (D.nchan == 1) ? 0 : ((i / inner4) % D.nchan);
-                float d = __ldg(D.delta + c), z = __ldg(D.zero_point + c);
-                float4 wv = ld_stream4(D.w + i * 4), av = ld_stream4(D.alpha + i * 4), y;
-                float rsum = 0.f;
-                AdaOut o;
-#define ONE(F) o = reg_on ? ada_fwd_one<SOFT, true>(wv.F, av.F, d, z, D.qmin, D.qmax, b) \
-                          : ada_fwd_one<SOFT, false>(wv.F, av.F, d, z, D.qmin, D.qmax, b); \
-               y.F = o.y; rsum += o.reg;
-                ONE(x) ONE(y) ONE(z) ONE(w)
-#undef ONE
-                st_stream4(D.wq + i * 4, y);
-                acc[0] += (double)rsum;
-            }
-        } else {
-            for (int64_t i = e0 + threadIdx.x; i < e1; i += blockDim.x) {
-                int64_t c = (D.nchan == 1) ? 0 : ((i / D.inner) % D.nchan);
-                float d = __ldg(D.delta + c), z = __ldg(D.zero_point + c);
-                AdaOut o = reg_on ? ada_fwd_one<SOFT, true>(D.w[i], D.alpha[i], d, z, D.qmin, D.qmax, b)
-                                  : ada_fwd_one<SOFT, false>(D.w[i], D.alpha[i], d, z, D.qmin, D.qmax, b);
-                D.wq[i] = o.y;
-                acc[0] += (double)o.reg;
-            }
-        }
+        const bool vec = desc_vec(D, false);
+        acc[0] += reg_on ? ada_fwd_span<SOFT, true>(D.w, D.alpha, D.delta, D.zero_point, D.wq, nullptr, e0, e1, D.inner, D.nchan,
+                                                    D.qmin, D.qmax, b, threadIdx.x, blockDim.x, vec)
+                         : ada_fwd_span<SOFT, false>(D.w, D.alpha, D.delta, D.zero_point, D.wq, nullptr, e0, e1, D.inner, D.nchan,
+                                                     D.qmin, D.qmax, b, threadIdx.x, blockDim.x, vec);
     }
     if (!reg_out) return;
     block_sum<1>(acc, smem);
@@ -246,37 +288,22 @@ ada_fwd_mt_kernel(const __grid_constant__ MtTable table, int count, int64_t tota
 __global__ void __launch_bounds__(SSQ_THREADS)
 ada_bwd_mt_kernel(const __grid_constant__ MtTable table, int count, int64_t total_tiles,
                   const float* __restrict__ b_dev, float lambda) {
-    __shared__ ssq_adaround_desc D;
+    __shared__ int s_which;
     const float b = b_dev ? __ldg(b_dev) : 0.f;
     const bool reg_on = b_dev && (b > 0.f);
     const float lam_g = reg_on ? lambda : 0.f;
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         __syncthreads();
-        if (threadIdx.x == 0) D = table.d[find_desc(table, count, tile)];
+        if (threadIdx.x == 0) s_which = find_desc(table, count, tile);
         __syncthreads();
+        const ssq_adaround_desc& D = table.d[s_which];
         const int64_t e0 = (tile - D.tile_begin) * SSQ_MT_TILE;
         const int64_t e1 = e0 + SSQ_MT_TILE < D.n ? e0 + SSQ_MT_TILE : D.n;
-        const bool vec = (D.inner % 4 == 0) && aligned16(D.w) && aligned16(D.alpha) && aligned16(D.gwq) && aligned16(D.galpha);
-        auto one = [&](float g, float wv, float av, float d, float z) -> float {
-            return reg_on ? ada_bwd_one<true, true>(g, wv, av, d, z, D.qmin, D.qmax, b, lam_g)
-                          : ada_bwd_one<true, false>(g, wv, av, d, z, D.qmin, D.qmax, b, lam_g);
-        };
-        if (vec) {
-            const int64_t inner4 = D.inner >> 2;
-            for (int64_t i = (e0 >> 2) + threadIdx.x; i < (e1 >> 2); i += blockDim.x) {
-                int64_t c = (D.nchan == 1) ? 0 : ((i / inner4) % D.nchan);
-                float d = __ldg(D.delta + c), z = __ldg(D.zero_point + c);
-                float4 wv = ld_stream4(D.w + i * 4), av = ld_stream4(D.alpha + i * 4), g = ld_stream4(D.gwq + i * 4), o;
-                o.x = one(g.x, wv.x, av.x, d, z); o.y = one(g.y, wv.y, av.y, d, z);
-                o.z = one(g.z, wv.z, av.z, d, z); o.w = one(g.w, wv.w, av.w, d, z);
-                st_stream4(D.galpha + i * 4, o);
-            }
-        } else {
-            for (int64_t i = e0 + threadIdx.x; i < e1; i += blockDim.x) {
-                int64_t c = (D.nchan == 1) ? 0 : ((i / D.inner) % D.nchan);
-                D.galpha[i] = one(D.gwq[i], D.w[i], D.alpha[i], __ldg(D.delta + c), __ldg(D.zero_point + c));
-            }
-        }
+        const bool vec = desc_vec(D, true);
+        if (reg_on) ada_bwd_span<true, true>(D.gwq, D.w, D.alpha, D.delta, D.zero_point, D.galpha, e0, e1, D.inner, D.nchan,
+                                             D.qmin, D.qmax, b, lam_g, 0, threadIdx.x, blockDim.x, vec);
+        else ada_bwd_span<true, false>(D.gwq, D.w, D.alpha, D.delta, D.zero_point, D.galpha, e0, e1, D.inner, D.nchan,
+                                       D.qmin, D.qmax, b, lam_g, 0, threadIdx.x, blockDim.x, vec);
     }
 }
 
@@ -302,18 +329,13 @@ extern "C" int ssq_fq_adaround_fwd(const float* w, const float* alpha, const flo
     if (reg && (!ws || ws_bytes < ssq_ws_bytes(1))) return SSQ_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     bool vec = aligned16(w) && aligned16(alpha) && aligned16(wq) && (!codes || aligned16(codes)) && (inner % 4 == 0);
-    int64_t per_cta = (int64_t)SSQ_THREADS * (vec ? 4 : 1);
+    int64_t per_cta = (int64_t)SSQ_THREADS * (vec ? 8 : 1);
     int grid = grid_for((n + per_cta - 1) / per_cta);
     WsView v = ws_view(ws, 1);
-#define LAUNCH(V, S, R) ada_fwd_kernel<V, S, R><<<grid, SSQ_THREADS, 0, st>>>( \
-        w, alpha, delta, zero_point, wq, codes, n, inner, nchan, qmin, qmax, b_dev, lambda, reg_out, v)
-    if (vec) {
-        if (soft) { if (reg) LAUNCH(true, true, true); else LAUNCH(true, true, false); }
-        else LAUNCH(true, false, false);
-    } else {
-        if (soft) { if (reg) LAUNCH(false, true, true); else LAUNCH(false, true, false); }
-        else LAUNCH(false, false, false);
-    }
+#define LAUNCH(S, R) ada_fwd_kernel<S, R><<<grid, SSQ_THREADS, 0, st>>>( \
+        w, alpha, delta, zero_point, wq, codes, n, inner, nchan, qmin, qmax, vec, b_dev, lambda, reg_out, v)
+    if (soft) { if (reg) LAUNCH(true, true); else LAUNCH(true, false); }
+    else LAUNCH(false, false);
 #undef LAUNCH
     return launch_status();
 }
@@ -327,11 +349,10 @@ extern "C" int ssq_fq_adaround_bwd(const float* gwq, const float* w, const float
     if (!w || !alpha || !delta || !zero_point || !galpha) return SSQ_ERR_NULL;
     if (int e = check_layout(n, inner, nchan)) return e;
     bool vec = (!gwq || aligned16(gwq)) && aligned16(w) && aligned16(alpha) && aligned16(galpha) && (inner % 4 == 0);
-    int64_t per_cta = (int64_t)SSQ_THREADS * (vec ? 4 : 1);
+    int64_t per_cta = (int64_t)SSQ_THREADS * (vec ? 8 : 1);
     int grid = grid_for((n + per_cta - 1) / per_cta);
-    cudaStream_t st = (cudaStream_t)stream;
-    if (vec) ada_bwd_kernel<true><<<grid, SSQ_THREADS, 0, st>>>(gwq, w, alpha, delta, zero_point, galpha, n, inner, nchan, qmin, qmax, b_dev, lambda, greg, accumulate);
-    else ada_bwd_kernel<false><<<grid, SSQ_THREADS, 0, st>>>(gwq, w, alpha, delta, zero_point, galpha, n, inner, nchan, qmin, qmax, b_dev, lambda, greg, accumulate);
+    ada_bwd_kernel<<<grid, SSQ_THREADS, 0, (cudaStream_t)stream>>>(gwq, w, alpha, delta, zero_point, galpha, n, inner, nchan,
+                                                                   qmin, qmax, vec, b_dev, lambda, greg, accumulate);
     return launch_status();
 }
 

@@ -1,6 +1,7 @@
-// K1a — uniform affine fake-quant forward / STE backward, and the per-output-channel
-// activation affine. HBM-bound streaming kernels: 128-bit loads/stores, 4 vectors in flight per
-// thread, persistent grid = 148 SMs x 8 CTAs.
+// K1a — uniform affine fake-quant forward / STE backward, and the per-output-channel activation affine.
+// HBM-bound streaming kernels: 128-bit loads/stores, several vectors in flight per thread, persistent grid of
+// 148 SMs x 8 CTAs, channel index tracked incrementally (no integer division in the loop), reciprocal of delta
+// hoisted per vector.
 //   reference arithmetic: quant/quant_layer.py:92-97, quant/channelQuantMSE.py:134-143,
 //   quant/channelQuant.py:79-94, quant/quant_layer.py:258-259
 #include "ssq_common.cuh"
@@ -12,12 +13,14 @@ __device__ __forceinline__ float clampf(float v, float lo, float hi) {
     return v < lo ? lo : (v > hi ? hi : v);
 }
 
-template <bool INSCALE>
-__device__ __forceinline__ float fq_one(float x, float d, float z, float s, float qmin, float qmax, float& q) {
-    float u = INSCALE ? div_exact(div_exact(x, s), d) : div_exact(x, d);
-    q = clampf(__fadd_rn(rintf(u), z), qmin, qmax);
-    float y = __fmul_rn(__fsub_rn(q, z), d);
-    return INSCALE ? __fmul_rn(y, s) : y;
+__device__ __forceinline__ float fq_one(float x, const Recip& R, float z, float qmin, float qmax, float& q) {
+    q = clampf(__fadd_rn(rintf(div_exact(x, R)), z), qmin, qmax);
+    return __fmul_rn(__fsub_rn(q, z), R.d);
+}
+// ChannelQuantMSE: two successive divisions x/s/delta, dequant ((q-z)*delta)*s
+__device__ __forceinline__ float fq_one_inscale(float x, float s, const Recip& R, float z, float qmin, float qmax, float& q) {
+    q = clampf(__fadd_rn(rintf(div_exact(div_exact(x, s), R)), z), qmin, qmax);
+    return __fmul_rn(__fmul_rn(__fsub_rn(q, z), R.d), s);
 }
 
 constexpr int UNROLL = 4;
@@ -28,10 +31,13 @@ __global__ void __launch_bounds__(SSQ_THREADS)
 fq_affine_fwd_vec(const float* __restrict__ x, const float* __restrict__ delta, const float* __restrict__ zp,
                   const float* __restrict__ in_scale, float* __restrict__ y, float* __restrict__ codes,
                   uint32_t n4, uint32_t inner4, uint32_t nchan, float qmin, float qmax) {
-    float d0 = 0.f, z0 = 0.f;
-    if (CHAN == 0) { d0 = __ldg(delta); z0 = __ldg(zp); }
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t base = blockIdx.x * blockDim.x + threadIdx.x; base < n4; base += stride * UNROLL) {
+    const uint32_t first = blockIdx.x * blockDim.x + threadIdx.x;
+    Recip R0; float z0 = 0.f;
+    if (CHAN == 0) { R0 = make_recip(__ldg(delta)); z0 = __ldg(zp); }
+    ChanWalk cw;
+    if (CHAN == 1) cw.init(first, stride, inner4, nchan);
+    for (uint32_t base = first; base < n4; base += stride * UNROLL) {
         float4 v[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
@@ -41,22 +47,26 @@ fq_affine_fwd_vec(const float* __restrict__ x, const float* __restrict__ delta, 
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             uint32_t i = base + u * stride;
-            if (i >= n4) break;
-            float d = d0, z = z0;
-            float4 s = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (CHAN == 1) {
-                uint32_t row = i / inner4;
-                uint32_t c = row % nchan;
-                d = __ldg(delta + c); z = __ldg(zp + c);
-                if (INSCALE) s = __ldg(reinterpret_cast<const float4*>(in_scale) + (i - row * inner4));
+            if (i < n4) {
+                Recip R = R0; float z = z0;
+                float4 q, o;
+                if (CHAN == 1) { R = make_recip(__ldg(delta + cw.c)); z = __ldg(zp + cw.c); }
+                if (INSCALE) {
+                    const float4 s = __ldg(reinterpret_cast<const float4*>(in_scale) + cw.col);
+                    o.x = fq_one_inscale(v[u].x, s.x, R, z, qmin, qmax, q.x);
+                    o.y = fq_one_inscale(v[u].y, s.y, R, z, qmin, qmax, q.y);
+                    o.z = fq_one_inscale(v[u].z, s.z, R, z, qmin, qmax, q.z);
+                    o.w = fq_one_inscale(v[u].w, s.w, R, z, qmin, qmax, q.w);
+                } else {
+                    o.x = fq_one(v[u].x, R, z, qmin, qmax, q.x);
+                    o.y = fq_one(v[u].y, R, z, qmin, qmax, q.y);
+                    o.z = fq_one(v[u].z, R, z, qmin, qmax, q.z);
+                    o.w = fq_one(v[u].w, R, z, qmin, qmax, q.w);
+                }
+                st_stream4(y + (size_t)i * 4, o);
+                if (CODES) st_stream4(codes + (size_t)i * 4, q);
             }
-            float4 q, o;
-            o.x = fq_one<INSCALE>(v[u].x, d, z, s.x, qmin, qmax, q.x);
-            o.y = fq_one<INSCALE>(v[u].y, d, z, s.y, qmin, qmax, q.y);
-            o.z = fq_one<INSCALE>(v[u].z, d, z, s.z, qmin, qmax, q.z);
-            o.w = fq_one<INSCALE>(v[u].w, d, z, s.w, qmin, qmax, q.w);
-            st_stream4(y + (size_t)i * 4, o);
-            if (CODES) st_stream4(codes + (size_t)i * 4, q);
+            if (CHAN == 1) cw.next();
         }
     }
 }
@@ -66,22 +76,26 @@ template <bool INSCALE>
 __global__ void __launch_bounds__(SSQ_THREADS)
 fq_affine_fwd_scalar(const float* __restrict__ x, const float* __restrict__ delta, const float* __restrict__ zp,
                      const float* __restrict__ in_scale, float* __restrict__ y, float* __restrict__ codes,
-                     int64_t begin, int64_t n, int64_t inner, int64_t nchan, float qmin, float qmax) {
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        int64_t row = i / inner;
-        int64_t c = row % nchan;
-        float s = INSCALE ? __ldg(in_scale + (i - row * inner)) : 1.f;
+                     int64_t n, int64_t inner, int64_t nchan, float qmin, float qmax) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    ChanWalk cw;
+    cw.init(first, stride, inner, nchan);
+    for (int64_t i = first; i < n; i += stride) {
+        const Recip R = make_recip(__ldg(delta + cw.c));
+        const float z = __ldg(zp + cw.c);
         float q;
-        float o = fq_one<INSCALE>(x[i], __ldg(delta + c), __ldg(zp + c), s, qmin, qmax, q);
+        const float o = INSCALE ? fq_one_inscale(x[i], __ldg(in_scale + cw.col), R, z, qmin, qmax, q)
+                                : fq_one(x[i], R, z, qmin, qmax, q);
         y[i] = o;
         if (codes) codes[i] = q;
+        cw.next();
     }
 }
 
 // ------------------------------------------------------------------------------- backward
-// One CTA per (split, channel): streams its slice of gy/x, writes gx, reduces
-// (gdelta, gzp) partials in double; last CTA of the channel finishes in fixed order.
+// One CTA per (split, channel): streams its slice of gy/x (outer slabs x a range of the channel's inner extent),
+// writes gx, reduces (gdelta, gzp) partials in double; the last CTA of the channel finishes in fixed order.
 template <bool VEC>
 __global__ void __launch_bounds__(SSQ_THREADS)
 fq_affine_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x, const float* __restrict__ delta,
@@ -91,40 +105,52 @@ fq_affine_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x, 
     __shared__ double smem[2 * 32];
     const int64_t c = blockIdx.y;
     const int split = blockIdx.x, nsplit = gridDim.x;
-    const float d = __ldg(delta + c), z = __ldg(zp + c);
-    const int64_t per_chan = outer * inner;
-    int64_t j0 = (int64_t)split * chunk;
-    int64_t j1 = j0 + chunk < per_chan ? j0 + chunk : per_chan;
+    const Recip R = make_recip(__ldg(delta + c));
+    const float d = R.d, z = __ldg(zp + c);
+    // this CTA's [k0,k1) of the inner extent, for every outer slab
+    const int64_t k0 = (int64_t)split * chunk;
+    const int64_t k1 = k0 + chunk < inner ? k0 + chunk : inner;
     double acc[2] = {0.0, 0.0};
-    float sd = 0.f, sz = 0.f;  // fp32 running sums flushed to double every few vectors
+    float sd = 0.f, sz = 0.f;  // fp32 running sums flushed to double after every vector
     auto one = [&](float g, float xv, float& gxo) {
-        float u = div_exact(xv, d);
-        float r = rintf(u);
-        float xi = __fadd_rn(r, z);
-        bool inside = (xi >= qmin) && (xi <= qmax);
-        float q = clampf(xi, qmin, qmax);
+        const float u = div_exact(xv, R);
+        const float r = rintf(u);
+        const float xi = __fadd_rn(r, z);
+        const bool inside = (xi >= qmin) && (xi <= qmax);
+        const float q = clampf(xi, qmin, qmax);
         gxo = inside ? g : 0.f;
         sd += g * (inside ? (r - u) : (q - z));
         sz += inside ? 0.f : -(g * d);
     };
-    if (VEC) {
-        // inner % 4 == 0, pointers 16B aligned; j runs in units of 4 within the channel
-        for (int64_t j = j0 + (int64_t)threadIdx.x * 4; j < j1; j += (int64_t)blockDim.x * 4) {
-            int64_t o = j / inner;
-            int64_t off = (o * nchan + c) * inner + (j - o * inner);
-            float4 g = ld_stream4(gy + off), xv = ld_stream4(x + off), r4;
-            one(g.x, xv.x, r4.x); one(g.y, xv.y, r4.y); one(g.z, xv.z, r4.z); one(g.w, xv.w, r4.w);
-            if (gx) st_stream4(gx + off, r4);
-            acc[0] += (double)sd; acc[1] += (double)sz; sd = 0.f; sz = 0.f;
-        }
-    } else {
-        for (int64_t j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
-            int64_t o = j / inner;
-            int64_t off = (o * nchan + c) * inner + (j - o * inner);
-            float r;
-            one(gy[off], x[off], r);
-            if (gx) gx[off] = r;
-            acc[0] += (double)sd; acc[1] += (double)sz; sd = 0.f; sz = 0.f;
+    for (int64_t o = 0; o < outer; ++o) {
+        const int64_t base = (o * nchan + c) * inner;
+        if (VEC) {
+            constexpr int U = 2;
+            for (int64_t k = k0 + (int64_t)threadIdx.x * 4; k < k1; k += (int64_t)blockDim.x * 4 * U) {
+                float4 g[U], xv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int64_t kk = k + (int64_t)u * blockDim.x * 4;
+                    if (kk < k1) { g[u] = ld_stream4(gy + base + kk); xv[u] = ld_stream4(x + base + kk); }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int64_t kk = k + (int64_t)u * blockDim.x * 4;
+                    if (kk < k1) {
+                        float4 r4;
+                        one(g[u].x, xv[u].x, r4.x); one(g[u].y, xv[u].y, r4.y); one(g[u].z, xv[u].z, r4.z); one(g[u].w, xv[u].w, r4.w);
+                        if (gx) st_stream4(gx + base + kk, r4);
+                        acc[0] += (double)sd; acc[1] += (double)sz; sd = 0.f; sz = 0.f;
+                    }
+                }
+            }
+        } else {
+            for (int64_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
+                float r;
+                one(gy[base + k], x[base + k], r);
+                if (gx) gx[base + k] = r;
+                acc[0] += (double)sd; acc[1] += (double)sz; sd = 0.f; sz = 0.f;
+            }
         }
     }
     if (gdelta == nullptr && gzp == nullptr) return;
@@ -139,10 +165,13 @@ fq_affine_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x, 
 __global__ void __launch_bounds__(SSQ_THREADS)
 chan_affine_fwd_kernel(const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b,
                        float* __restrict__ y, int64_t n, int64_t inner, int64_t nchan) {
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        int64_t c = (i / inner) % nchan;
-        y[i] = __fadd_rn(__fmul_rn(x[i], __ldg(a + c)), __ldg(b + c));
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    ChanWalk cw;
+    cw.init(first, stride, inner, nchan);
+    for (int64_t i = first; i < n; i += stride) {
+        y[i] = __fadd_rn(__fmul_rn(x[i], __ldg(a + cw.c)), __ldg(b + cw.c));
+        cw.next();
     }
 }
 
@@ -154,17 +183,17 @@ chan_affine_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x
     const int64_t c = blockIdx.y;
     const int split = blockIdx.x, nsplit = gridDim.x;
     const float av = __ldg(a + c);
-    const int64_t per_chan = outer * inner;
-    int64_t j0 = (int64_t)split * chunk;
-    int64_t j1 = j0 + chunk < per_chan ? j0 + chunk : per_chan;
+    const int64_t k0 = (int64_t)split * chunk;
+    const int64_t k1 = k0 + chunk < inner ? k0 + chunk : inner;
     double acc[2] = {0.0, 0.0};
-    for (int64_t j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
-        int64_t o = j / inner;
-        int64_t off = (o * nchan + c) * inner + (j - o * inner);
-        float g = gy[off];
-        if (gx) gx[off] = g * av;
-        acc[0] += (double)(g * x[off]);
-        acc[1] += (double)g;
+    for (int64_t o = 0; o < outer; ++o) {
+        const int64_t base = (o * nchan + c) * inner;
+        for (int64_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
+            const float g = gy[base + k];
+            if (gx) gx[base + k] = g * av;
+            acc[0] += (double)(g * x[base + k]);
+            acc[1] += (double)g;
+        }
     }
     block_sum<2>(acc, smem);
     if (grid_finish<2>(acc, ws, c, split, nsplit, smem) && threadIdx.x == 0) {
@@ -173,17 +202,17 @@ chan_affine_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x
     }
 }
 
-// split a channel's outer*inner elements into CTAs so the grid fills the machine
-static inline void chan_split(int64_t per_chan, int64_t nchan, int vec, int64_t& chunk, int& nsplit) {
-    int64_t cap = (int64_t)SSQ_NUM_SMS * SSQ_CTAS_PER_SM;
-    int64_t want = (cap + nchan - 1) / nchan;
-    int64_t per_cta = (int64_t)SSQ_THREADS * 4 * (vec ? 4 : 1);
-    int64_t by_work = (per_chan + per_cta - 1) / per_cta;
+// split a channel's inner extent into CTAs so that nchan x nsplit CTAs fill the machine
+static inline void chan_split(int64_t inner, int64_t outer, int64_t nchan, int vec, int64_t& chunk, int& nsplit) {
+    const int64_t cap = (int64_t)SSQ_NUM_SMS * SSQ_CTAS_PER_SM;
+    const int64_t want = (cap + nchan - 1) / nchan;
+    const int64_t per_cta = (int64_t)SSQ_THREADS * 4 * (vec ? 2 : 1);
+    const int64_t by_work = (inner * outer + per_cta * outer - 1) / (per_cta * outer);
     int64_t s = want < by_work ? want : by_work;
     if (s < 1) s = 1;
-    chunk = (per_chan + s - 1) / s;
+    chunk = (inner + s - 1) / s;
     chunk = (chunk + 3) / 4 * 4;  // keep float4 alignment of every split
-    nsplit = (int)((per_chan + chunk - 1) / chunk);
+    nsplit = (int)((inner + chunk - 1) / chunk);
     if (nsplit < 1) nsplit = 1;
 }
 
@@ -222,8 +251,8 @@ extern "C" int ssq_fq_affine_fwd(const float* x, const float* delta, const float
     } else {
         int64_t ctas = (n + SSQ_THREADS - 1) / SSQ_THREADS;
         int grid = grid_for(ctas);
-        if (in_scale) fq_affine_fwd_scalar<true><<<grid, SSQ_THREADS, 0, st>>>(x, delta, zero_point, in_scale, y, codes, 0, n, inner, nchan, qmin, qmax);
-        else fq_affine_fwd_scalar<false><<<grid, SSQ_THREADS, 0, st>>>(x, delta, zero_point, in_scale, y, codes, 0, n, inner, nchan, qmin, qmax);
+        if (in_scale) fq_affine_fwd_scalar<true><<<grid, SSQ_THREADS, 0, st>>>(x, delta, zero_point, in_scale, y, codes, n, inner, nchan, qmin, qmax);
+        else fq_affine_fwd_scalar<false><<<grid, SSQ_THREADS, 0, st>>>(x, delta, zero_point, in_scale, y, codes, n, inner, nchan, qmin, qmax);
     }
     return launch_status();
 }
@@ -241,7 +270,7 @@ extern "C" int ssq_fq_affine_bwd(const float* gy, const float* x, const float* d
     int64_t outer = n / inner / nchan;
     bool vec = aligned16(gy) && aligned16(x) && (!gx || aligned16(gx)) && (inner % 4 == 0);
     int64_t chunk; int nsplit;
-    chan_split(outer * inner, nchan, vec, chunk, nsplit);
+    chan_split(inner, outer, nchan, vec, chunk, nsplit);
     dim3 grid(nsplit, (unsigned)nchan);
     WsView v = ws_view(ws, nchan);
     if (vec) fq_affine_bwd_kernel<true><<<grid, SSQ_THREADS, 0, st>>>(gy, x, delta, zero_point, gx, gdelta, gzp, outer, inner, nchan, chunk, qmin, qmax, v);
@@ -267,7 +296,7 @@ extern "C" int ssq_chan_affine_bwd(const float* gy, const float* x, const float*
     if (!ws || ws_bytes < ssq_ws_bytes(nchan)) return SSQ_ERR_WORKSPACE;
     int64_t outer = n / inner / nchan;
     int64_t chunk; int nsplit;
-    chan_split(outer * inner, nchan, 0, chunk, nsplit);
+    chan_split(inner, outer, nchan, 0, chunk, nsplit);
     dim3 grid(nsplit, (unsigned)nchan);
     chan_affine_bwd_kernel<<<grid, SSQ_THREADS, 0, (cudaStream_t)stream>>>(gy, x, a, gx, ga, gb, outer, inner, nchan, chunk, ws_view(ws, nchan));
     return launch_status();

@@ -15,7 +15,8 @@ struct LossArgs {
     float p; const float* gscale;
 };
 
-// mode 0 lp, 1 fisher_diag. One persistent grid; fixed-order reduction.
+// MODE 0: lp with p == 2 (d*d, exact as ATen's pow(2) shortcut); 1: fisher_diag; 2: lp with general p, where
+// |d|^p and |d|^(p-1) share one log2 (2 MUFU.EX2). One persistent grid; fixed-order reduction.
 template <int MODE, bool VEC, bool GRAD, bool FWD>
 __global__ void __launch_bounds__(SSQ_THREADS)
 recon_loss_kernel(LossArgs a, WsView ws) {
@@ -31,8 +32,12 @@ recon_loss_kernel(LossArgs a, WsView ws) {
         float ad = fabsf(d);
         float term;
         if (MODE == 0) {
-            term = pow_scalar(ad, p);
-            if (GRAD) go = (inv * (p * pow_scalar(ad, pm1))) * sgnf(d);
+            term = d * d;
+            if (GRAD) go = (inv * (2.0f * ad)) * sgnf(d);
+        } else if (MODE == 2) {
+            const float l2 = log2_pos(ad);
+            term = ex2_approx(p * l2);
+            if (GRAD) go = (inv * (p * ex2_approx(pm1 * l2))) * sgnf(d);
         } else {
             float f2 = fi * fi;
             term = (d * d) * f2;
@@ -40,14 +45,14 @@ recon_loss_kernel(LossArgs a, WsView ws) {
         }
         return term;
     };
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    ChanWalk cw;      // c = sample, col = offset inside the sample (only needed to follow tgt_index)
     if (VEC) {
         const int64_t ps4 = a.per_sample >> 2, total4 = total >> 2;
-        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
+        if (a.tgt_index) cw.init(first, stride, ps4, a.batch);
+        for (int64_t i = first; i < total4; i += stride) {
             int64_t toff = i;
-            if (a.tgt_index) {
-                int64_t n = i / ps4;
-                toff = __ldg(a.tgt_index + n) * ps4 + (i - n * ps4);
-            }
+            if (a.tgt_index) { toff = __ldg(a.tgt_index + cw.c) * ps4 + cw.col; cw.next(); }
             float4 pr = ld_stream4(a.pred + i * 4), tg = ld_stream4(a.tgt + toff * 4);
             float4 fi = make_float4(0.f, 0.f, 0.f, 0.f), go;
             if (MODE == 1) fi = ld_stream4(a.fisher + toff * 4);
@@ -57,12 +62,10 @@ recon_loss_kernel(LossArgs a, WsView ws) {
             acc[0] += (double)s;
         }
     } else {
-        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        if (a.tgt_index) cw.init(first, stride, a.per_sample, a.batch);
+        for (int64_t i = first; i < total; i += stride) {
             int64_t toff = i;
-            if (a.tgt_index) {
-                int64_t n = i / a.per_sample;
-                toff = __ldg(a.tgt_index + n) * a.per_sample + (i - n * a.per_sample);
-            }
+            if (a.tgt_index) { toff = __ldg(a.tgt_index + cw.c) * a.per_sample + cw.col; cw.next(); }
             float go = 0.f;
             float s = one(a.pred[i], a.tgt[toff], MODE == 1 ? a.fisher[toff] : 0.f, go);
             if (GRAD) a.dpred[i] = go;
@@ -119,19 +122,21 @@ fisher_full_grad_kernel(LossArgs a, const double* dots) {
 __global__ void __launch_bounds__(SSQ_THREADS)
 gather_rows_kernel(const float* __restrict__ src, const int64_t* __restrict__ index, float* __restrict__ dst,
                    int64_t batch, int64_t per_sample, bool vec) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    ChanWalk cw;
     if (vec) {
         const int64_t ps4 = per_sample >> 2, total4 = batch * ps4;
-        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
-            int64_t n = i / ps4;
-            int64_t s = __ldg(index + n) * ps4 + (i - n * ps4);
-            st_stream4(dst + i * 4, ld_stream4(src + s * 4));
+        cw.init(first, stride, ps4, batch);
+        for (int64_t i = first; i < total4; i += stride) {
+            st_stream4(dst + i * 4, ld_stream4(src + (__ldg(index + cw.c) * ps4 + cw.col) * 4));
+            cw.next();
         }
     } else {
         const int64_t total = batch * per_sample;
-        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-            int64_t n = i / per_sample;
-            dst[i] = src[__ldg(index + n) * per_sample + (i - n * per_sample)];
+        cw.init(first, stride, per_sample, batch);
+        for (int64_t i = first; i < total; i += stride) {
+            dst[i] = src[__ldg(index + cw.c) * per_sample + cw.col];
+            cw.next();
         }
     }
 }
@@ -174,7 +179,7 @@ static int launch_loss(LossArgs a, int mode, bool fwd, void* ws, size_t ws_bytes
                               else L(M, true, true, false); } \
                    else { if (fwd) { if (grad) L(M, false, true, true); else L(M, false, false, true); } \
                           else L(M, false, true, false); } } while (0)
-    if (mode == 0) LM(0); else LM(1);
+    if (mode == 0) { if (a.p == 2.0f) LM(0); else LM(2); } else LM(1);
 #undef LM
 #undef L
     return launch_status();
