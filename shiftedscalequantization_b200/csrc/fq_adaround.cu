@@ -16,10 +16,11 @@ __device__ __forceinline__ float clampf_(float v, float lo, float hi) {
 
 struct AdaOut { float y, q, reg; };
 
+// u = w/delta already divided
 template <bool SOFT, bool REG>
-__device__ __forceinline__ AdaOut ada_fwd_one(float w, float a, const Recip& R, float z, float qmin, float qmax, float b) {
+__device__ __forceinline__ AdaOut ada_fwd_one(float u, float a, const Recip& R, float z, float qmin, float qmax, float b) {
     AdaOut o;
-    const float fl = floorf(div_exact(w, R));
+    const float fl = floorf(u);
     float r;
     o.reg = 0.f;
     if (SOFT) {
@@ -35,13 +36,13 @@ __device__ __forceinline__ AdaOut ada_fwd_one(float w, float a, const Recip& R, 
 
 // galpha for one element: reconstruction path + regulariser path
 template <bool REC, bool REG>
-__device__ __forceinline__ float ada_bwd_one(float g, float w, float a, const Recip& R, float z, float qmin, float qmax,
+__device__ __forceinline__ float ada_bwd_one(float g, float u, float a, const Recip& R, float z, float qmin, float qmax,
                                              float b, float lam_g) {
     float h;
     const float dh = rect_sigmoid_grad(a, h);
     float out = 0.f;
     if (REC) {
-        const float xi = __fadd_rn(__fadd_rn(floorf(div_exact(w, R)), h), z);
+        const float xi = __fadd_rn(__fadd_rn(floorf(u), h), z);
         const bool inside = (xi >= qmin) && (xi <= qmax);
         out = inside ? (g * R.d) * dh : 0.f;
     }
@@ -79,7 +80,8 @@ __device__ __forceinline__ double ada_fwd_span(const float* __restrict__ w, cons
                     float4 y, q;
                     AdaOut o;
                     float rsum = 0.f;
-#define ONE(F) o = ada_fwd_one<SOFT, REGON>(wv[u].F, av[u].F, R, z, qmin, qmax, b); y.F = o.y; q.F = o.q; rsum += o.reg;
+                    const float4 t = div4_exact(wv[u], R);
+#define ONE(F) o = ada_fwd_one<SOFT, REGON>(t.F, av[u].F, R, z, qmin, qmax, b); y.F = o.y; q.F = o.q; rsum += o.reg;
                     ONE(x) ONE(y) ONE(z) ONE(w)
 #undef ONE
                     st_stream4(wq + j * 4, y);
@@ -93,7 +95,7 @@ __device__ __forceinline__ double ada_fwd_span(const float* __restrict__ w, cons
         cw.init(e0 + tid, nthr, inner, nchan);
         for (int64_t i = e0 + tid; i < e1; i += nthr) {
             const Recip R = make_recip(__ldg(delta + cw.c));
-            const AdaOut o = ada_fwd_one<SOFT, REGON>(w[i], alpha[i], R, __ldg(zp + cw.c), qmin, qmax, b);
+            const AdaOut o = ada_fwd_one<SOFT, REGON>(div_exact(w[i], R), alpha[i], R, __ldg(zp + cw.c), qmin, qmax, b);
             wq[i] = o.y;
             if (codes) codes[i] = o.q;
             if (REGON) acc += (double)o.reg;
@@ -130,11 +132,12 @@ __device__ __forceinline__ void ada_bwd_span(const float* __restrict__ gwq, cons
                 if (j < i1) {
                     const Recip R = make_recip(__ldg(delta + cw.c));
                     const float z = __ldg(zp + cw.c);
-                    float4 o;
-                    o.x = ada_bwd_one<REC, REGON>(gv[u].x, wv[u].x, av[u].x, R, z, qmin, qmax, b, lam_g);
-                    o.y = ada_bwd_one<REC, REGON>(gv[u].y, wv[u].y, av[u].y, R, z, qmin, qmax, b, lam_g);
-                    o.z = ada_bwd_one<REC, REGON>(gv[u].z, wv[u].z, av[u].z, R, z, qmin, qmax, b, lam_g);
-                    o.w = ada_bwd_one<REC, REGON>(gv[u].w, wv[u].w, av[u].w, R, z, qmin, qmax, b, lam_g);
+                    float4 o, t = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (REC) t = div4_exact(wv[u], R);
+                    o.x = ada_bwd_one<REC, REGON>(gv[u].x, t.x, av[u].x, R, z, qmin, qmax, b, lam_g);
+                    o.y = ada_bwd_one<REC, REGON>(gv[u].y, t.y, av[u].y, R, z, qmin, qmax, b, lam_g);
+                    o.z = ada_bwd_one<REC, REGON>(gv[u].z, t.z, av[u].z, R, z, qmin, qmax, b, lam_g);
+                    o.w = ada_bwd_one<REC, REGON>(gv[u].w, t.w, av[u].w, R, z, qmin, qmax, b, lam_g);
                     if (accumulate) {
                         const float4 p = *reinterpret_cast<const float4*>(galpha + j * 4);
                         o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
@@ -148,7 +151,8 @@ __device__ __forceinline__ void ada_bwd_span(const float* __restrict__ gwq, cons
         cw.init(e0 + tid, nthr, inner, nchan);
         for (int64_t i = e0 + tid; i < e1; i += nthr) {
             const Recip R = make_recip(__ldg(delta + cw.c));
-            const float o = ada_bwd_one<REC, REGON>(REC ? gwq[i] : 0.f, w[i], alpha[i], R, __ldg(zp + cw.c), qmin, qmax, b, lam_g);
+            const float o = ada_bwd_one<REC, REGON>(REC ? gwq[i] : 0.f, REC ? div_exact(w[i], R) : 0.f, alpha[i], R, __ldg(zp + cw.c),
+                                                    qmin, qmax, b, lam_g);
             galpha[i] = accumulate ? galpha[i] + o : o;
             cw.next();
         }
@@ -157,7 +161,7 @@ __device__ __forceinline__ void ada_bwd_span(const float* __restrict__ gwq, cons
 
 // ---- single tensor ----------------------------------------------------------------------------------------
 template <bool SOFT, bool REG>
-__global__ void __launch_bounds__(SSQ_THREADS)
+__global__ void __launch_bounds__(SSQ_THREADS, 4)
 ada_fwd_kernel(const float* __restrict__ w, const float* __restrict__ alpha, const float* __restrict__ delta,
                const float* __restrict__ zp, float* __restrict__ wq, float* __restrict__ codes,
                int64_t n, int64_t inner, int64_t nchan, float qmin, float qmax, bool vec,
@@ -258,7 +262,7 @@ __device__ __forceinline__ bool desc_vec(const ssq_adaround_desc& D, bool bwd) {
 }
 
 template <bool SOFT>
-__global__ void __launch_bounds__(SSQ_THREADS)
+__global__ void __launch_bounds__(SSQ_THREADS, 4)
 ada_fwd_mt_kernel(const __grid_constant__ MtTable table, int count, int64_t total_tiles,
                   const float* __restrict__ b_dev, float lambda, float* __restrict__ reg_out, WsView ws) {
     __shared__ double smem[32];

@@ -13,9 +13,13 @@ __device__ __forceinline__ float clampf(float v, float lo, float hi) {
     return v < lo ? lo : (v > hi ? hi : v);
 }
 
+// u = x/delta already divided
+__device__ __forceinline__ float fq_post(float u, float d, float z, float qmin, float qmax, float& q) {
+    q = clampf(__fadd_rn(rintf(u), z), qmin, qmax);
+    return __fmul_rn(__fsub_rn(q, z), d);
+}
 __device__ __forceinline__ float fq_one(float x, const Recip& R, float z, float qmin, float qmax, float& q) {
-    q = clampf(__fadd_rn(rintf(div_exact(x, R)), z), qmin, qmax);
-    return __fmul_rn(__fsub_rn(q, z), R.d);
+    return fq_post(div_exact(x, R), R.d, z, qmin, qmax, q);
 }
 // ChannelQuantMSE: two successive divisions x/s/delta, dequant ((q-z)*delta)*s
 __device__ __forceinline__ float fq_one_inscale(float x, float s, const Recip& R, float z, float qmin, float qmax, float& q) {
@@ -58,10 +62,11 @@ fq_affine_fwd_vec(const float* __restrict__ x, const float* __restrict__ delta, 
                     o.z = fq_one_inscale(v[u].z, s.z, R, z, qmin, qmax, q.z);
                     o.w = fq_one_inscale(v[u].w, s.w, R, z, qmin, qmax, q.w);
                 } else {
-                    o.x = fq_one(v[u].x, R, z, qmin, qmax, q.x);
-                    o.y = fq_one(v[u].y, R, z, qmin, qmax, q.y);
-                    o.z = fq_one(v[u].z, R, z, qmin, qmax, q.z);
-                    o.w = fq_one(v[u].w, R, z, qmin, qmax, q.w);
+                    const float4 t = div4_exact(v[u], R);
+                    o.x = fq_post(t.x, R.d, z, qmin, qmax, q.x);
+                    o.y = fq_post(t.y, R.d, z, qmin, qmax, q.y);
+                    o.z = fq_post(t.z, R.d, z, qmin, qmax, q.z);
+                    o.w = fq_post(t.w, R.d, z, qmin, qmax, q.w);
                 }
                 st_stream4(y + (size_t)i * 4, o);
                 if (CODES) st_stream4(codes + (size_t)i * 4, q);
@@ -112,8 +117,7 @@ fq_affine_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x, 
     const int64_t k1 = k0 + chunk < inner ? k0 + chunk : inner;
     double acc[2] = {0.0, 0.0};
     float sd = 0.f, sz = 0.f;  // fp32 running sums flushed to double after every vector
-    auto one = [&](float g, float xv, float& gxo) {
-        const float u = div_exact(xv, R);
+    auto post = [&](float g, float u, float& gxo) {
         const float r = rintf(u);
         const float xi = __fadd_rn(r, z);
         const bool inside = (xi >= qmin) && (xi <= qmax);
@@ -138,7 +142,8 @@ fq_affine_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x, 
                     const int64_t kk = k + (int64_t)u * blockDim.x * 4;
                     if (kk < k1) {
                         float4 r4;
-                        one(g[u].x, xv[u].x, r4.x); one(g[u].y, xv[u].y, r4.y); one(g[u].z, xv[u].z, r4.z); one(g[u].w, xv[u].w, r4.w);
+                        const float4 t = div4_exact(xv[u], R);
+                        post(g[u].x, t.x, r4.x); post(g[u].y, t.y, r4.y); post(g[u].z, t.z, r4.z); post(g[u].w, t.w, r4.w);
                         if (gx) st_stream4(gx + base + kk, r4);
                         acc[0] += (double)sd; acc[1] += (double)sz; sd = 0.f; sz = 0.f;
                     }
@@ -147,7 +152,7 @@ fq_affine_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x, 
         } else {
             for (int64_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
                 float r;
-                one(gy[base + k], x[base + k], r);
+                post(gy[base + k], div_exact(x[base + k], R), r);
                 if (gx) gx[base + k] = r;
                 acc[0] += (double)sd; acc[1] += (double)sz; sd = 0.f; sz = 0.f;
             }
