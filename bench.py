@@ -334,7 +334,7 @@ def run_ours(args):
     rank, local, world = D.init_from_env()
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.benchmark = bool(args.cudnn_benchmark)   # pass 0 under a profiler: autotuning mis-times there
     torch.backends.cudnn.allow_tf32 = bool(args.tf32)       # default: true fp32 convolutions, like the CPU path
     torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
     peaks = {}
@@ -386,7 +386,8 @@ def run_ours(args):
         ms_e2e = timed_steps(eng_h, max(args.steps // 2, 3), max(args.warmup // 2, 3), dev, world, read_loss=True)
         e2e = {"value": world * n_units / (ms_e2e * 1e-3), "unit": "iters/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": sum(e.h2d_bytes_per_step() for e in eng_h), "d2h_bytes_per_step": 4 * n_units,
-               "path": "ReconEngine(host_resident=True): pinned host feature cache -> per-row cudaMemcpyAsync -> captured iteration -> loss .item()"}
+               "path": "ReconEngine(host_resident=True): pinned host feature cache -> ssq_stage_rows_h2d (one cudaMemcpyAsync per row, "
+                       "prefetched one step ahead on a copy stream) -> captured iteration -> loss .item() every iteration"}
         release(eng_h)
     del feats
     torch.cuda.empty_cache()
@@ -417,6 +418,11 @@ def run_ours(args):
     torch.cuda.empty_cache()
 
     # ---- roofline: DRAM-resident microbench of every kernel + in-step shares
+    if args.skip_micro:
+        line = base_line(args, value, ms_step, world, clocks, launches_per_step, e2e, peak_src)
+        line["extra"] = {"weight_scale_search_ms": scale_search_s * 1e3, "setup_s": setup_s, "act_phase": act}
+        print(json.dumps(line), flush=True)
+        return
     micro = kernel_microbench(dev, peak_gbs)
     ours_ms = sum(ms for _n, ms in prof.values())
     shares = {k: {"launches": n, "ms": ms, "share_of_step": ms / eager_ms} for k, (n, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1])}
@@ -447,7 +453,7 @@ def base_line(args, value, ms_step, world, clocks, launches_per_step, e2e, peak_
                                    "mini-batch 32, randn 224x224 calibration images, random-init weights",
                        "calib_images": args.images, "per_rank_batch": BATCH, "global_batch": BATCH * world,
                        "step": "one iteration on each of the 9 units (CUDA-graph replay per unit)",
-                       "conv_math": "tf32" if args.tf32 else "fp32", "cudnn_benchmark": True,
+                       "conv_math": "tf32" if args.tf32 else "fp32", "cudnn_benchmark": bool(args.cudnn_benchmark),
                        "l2": "per-unit working sets are re-read every step; the roofline kernels are timed on inputs larger than L2",
                        "multi_gpu": "calibration images sharded by rank; SUM all-reduce of the flat alpha gradient every iteration" if world > 1 else "single GPU"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * (args.steps + args.warmup)}
@@ -461,10 +467,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images", type=int, default=1024)
     ap.add_argument("--tf32", type=int, default=0)
+    ap.add_argument("--cudnn-benchmark", type=int, default=1)
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-act", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--micro-only", action="store_true", help="only the DRAM-resident kernel microbench")
+    ap.add_argument("--skip-micro", action="store_true", help="no roofline microbench (short profiler runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

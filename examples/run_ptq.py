@@ -1,0 +1,113 @@
+#!/usr/bin/env python
+"""End-to-end PTQ calibration on synthetic data through the reference's public API sequence
+(the flow of Brecq/main_imagenet.py:171-243 / main_cifar10.py:10-104): build QuantModel -> 8-bit stem/head ->
+weight-scale init -> block/layer reconstruction of every unit -> activation-scale init -> activation reconstruction.
+
+    python examples/run_ptq.py --arch resnet18 --n_bits_w 2 --n_bits_a 4 --res 224 --num_samples 1024 --iters_w 20000
+"""
+import argparse
+import os
+import sys
+import time
+
+import torch
+import torch.nn as nn
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from shiftedscalequantization_b200 import quant as Q, zoo          # noqa: E402
+from shiftedscalequantization_b200.quant import (BaseQuantBlock, QuantModel, QuantModule,  # noqa: E402
+                                                   block_reconstruction, layer_reconstruction)
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--arch', default='resnet18', choices=sorted(zoo.ARCHS))
+    ap.add_argument('--seed', default=1005, type=int)
+    ap.add_argument('--res', default=224, type=int)
+    ap.add_argument('--num_classes', default=1000, type=int)
+    ap.add_argument('--n_bits_w', default=2, type=int)
+    ap.add_argument('--n_bits_a', default=4, type=int)
+    ap.add_argument('--channel_wise', default=1, type=int)
+    ap.add_argument('--act_quant', default=1, type=int)
+    ap.add_argument('--scale_method', default='mse')
+    ap.add_argument('--num_samples', default=1024, type=int)
+    ap.add_argument('--iters_w', default=20000, type=int)
+    ap.add_argument('--iters_a', default=5000, type=int)
+    ap.add_argument('--weight', default=0.01, type=float)
+    ap.add_argument('--b_start', default=20, type=int)
+    ap.add_argument('--b_end', default=2, type=int)
+    ap.add_argument('--warmup', default=0.2, type=float)
+    ap.add_argument('--lr', default=4e-4, type=float)
+    ap.add_argument('--p', default=2.4, type=float)
+    ap.add_argument('--batch_size', default=32, type=int)
+    ap.add_argument('--max_units', default=0, type=int, help='reconstruct only the first N units (0 = all)')
+    args = ap.parse_args(argv)
+
+    dev = torch.device('cuda')
+    torch.manual_seed(args.seed)
+    kw = {} if args.arch.startswith('regnet') else ({'n_class': args.num_classes} if args.arch == 'mobilenetv2' else {'num_classes': args.num_classes})
+    cnn = zoo.build(args.arch, **kw).to(dev).eval()
+    wq = {'n_bits': args.n_bits_w, 'channel_wise': bool(args.channel_wise), 'scale_method': args.scale_method}
+    aq = {'n_bits': args.n_bits_a, 'channel_wise': False, 'scale_method': args.scale_method, 'leaf_param': bool(args.act_quant)}
+    qnn = QuantModel(model=cnn, weight_quant_params=wq, act_quant_params=aq).to(dev).eval()
+    qnn.set_first_last_layer_to_8bit()
+    cali = torch.randn(args.num_samples, 3, args.res, args.res)
+
+    t0 = time.time()
+    qnn.set_quant_state(True, False)
+    with torch.no_grad():
+        qnn(cali[:64].to(dev))
+    torch.cuda.synchronize()
+    print(f'weight scale init: {time.time() - t0:.2f}s')
+
+    done = [0]
+
+    def recon_model(model: nn.Module, **kwargs):
+        for name, module in model.named_children():
+            if args.max_units and done[0] >= args.max_units:
+                return
+            if isinstance(module, QuantModule):
+                if not module.ignore_reconstruction:
+                    print(f'Reconstruction for layer {name}')
+                    layer_reconstruction(qnn, module, **kwargs)
+                    done[0] += 1
+            elif isinstance(module, BaseQuantBlock):
+                if not module.ignore_reconstruction:
+                    print(f'Reconstruction for block {name}')
+                    block_reconstruction(qnn, module, **kwargs)
+                    done[0] += 1
+            else:
+                recon_model(module, **kwargs)
+
+    t0 = time.time()
+    recon_model(qnn, cali_data=cali, iters=args.iters_w, weight=args.weight, asym=True, b_range=(args.b_start, args.b_end),
+                warmup=args.warmup, act_quant=False, opt_mode='mse', batch_size=args.batch_size)
+    torch.cuda.synchronize()
+    print(f'weight reconstruction: {time.time() - t0:.2f}s for {done[0]} units x {args.iters_w} iterations')
+    qnn.set_quant_state(weight_quant=True, act_quant=False)
+    with torch.no_grad():
+        out_w = qnn(cali[:32].to(dev))
+    assert torch.isfinite(out_w).all()
+
+    if args.act_quant:
+        qnn.set_quant_state(True, True)
+        with torch.no_grad():
+            qnn(cali[:64].to(dev))
+        qnn.disable_network_output_quantization()
+        done[0] = 0
+        t0 = time.time()
+        recon_model(qnn, cali_data=cali, iters=args.iters_a, act_quant=True, opt_mode='mse', lr=args.lr, p=args.p,
+                    batch_size=args.batch_size)
+        torch.cuda.synchronize()
+        print(f'activation reconstruction: {time.time() - t0:.2f}s for {done[0]} units x {args.iters_a} iterations')
+        qnn.set_quant_state(weight_quant=True, act_quant=True)
+        with torch.no_grad():
+            out_wa = qnn(cali[:32].to(dev))
+        assert torch.isfinite(out_wa).all()
+    sd = qnn.state_dict()
+    print(f'done: state_dict with {len(sd)} tensors; W{args.n_bits_w}A{args.n_bits_a if args.act_quant else 32}')
+    return qnn
+
+
+if __name__ == '__main__':
+    main()

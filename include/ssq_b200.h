@@ -237,6 +237,11 @@ int ssq_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
  * gather rows of a cached feature tensor: dst[n] = src[index[n]] (quant/block_recon.py:91) */
 int ssq_gather_rows(const float* src, const int64_t* index, float* dst,
                     int64_t batch, int64_t per_sample, void* stream);
+/* host-resident feature cache (the reference's keep_gpu=False mode, quant/data_utils.py:34-36 +
+ * `cached_inps[idx].to(device)` at quant/block_recon.py:91-92): dst[n] (device) = src[rows[n]] (PINNED host memory),
+ * one cudaMemcpyAsync per row on `stream`; rows is a HOST array. No host-side gather, no staging copy. */
+int ssq_stage_rows_h2d(const float* host_src, const int64_t* rows, float* dev_dst,
+                       int64_t batch, int64_t per_sample, void* stream);
 /* advance the device-side iteration state used by a graph-captured loop: step += 1, and
  * copy row `step` of idx_table/b_table/lr_table into the live slots. */
 int ssq_loop_advance(int64_t* step_dev, const int64_t* idx_table, int64_t* idx_live, int batch,

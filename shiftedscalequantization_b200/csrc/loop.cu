@@ -85,6 +85,20 @@ extern "C" int ssq_loop_advance(int64_t* step_dev, const int64_t* idx_table, int
     return launch_status();
 }
 
+extern "C" int ssq_stage_rows_h2d(const float* host_src, const int64_t* rows, float* dev_dst,
+                                  int64_t batch, int64_t per_sample, void* stream) {
+    if (batch == 0 || per_sample == 0) return SSQ_OK;
+    if (!host_src || !rows || !dev_dst) return SSQ_ERR_NULL;
+    if (batch < 0 || per_sample < 0) return SSQ_ERR_SIZE;
+    const size_t bytes = (size_t)per_sample * sizeof(float);
+    for (int64_t n = 0; n < batch; ++n) {
+        cudaError_t e = cudaMemcpyAsync(dev_dst + n * per_sample, host_src + rows[n] * per_sample, bytes,
+                                        cudaMemcpyHostToDevice, (cudaStream_t)stream);
+        if (e != cudaSuccess) return (int)e;
+    }
+    return SSQ_OK;
+}
+
 extern "C" int ssq_abi_version(void) { return SSQ_ABI_VERSION; }
 
 extern "C" const char* ssq_status_string(int status) {

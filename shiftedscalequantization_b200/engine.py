@@ -116,6 +116,7 @@ class ReconEngine:
         self.idx_table = tab.to(self.dev)
         self.idx_table_host = tab.cpu()
         self.host_step = 0
+        self._copy_stream = None
         self.b_table = brecq_b_table(self.iters, warmup, b_range, round_loss=not act_quant).to(self.dev)
         lr_tab = cosine_lr_table(lr, self.iters) if act_quant else torch.full((max(self.iters, 1),), 1e-3)
         self.lr_table = lr_tab.to(self.dev)
@@ -220,7 +221,10 @@ class ReconEngine:
         then capture one iteration"""
         snap = self._snapshot()
         if self.host_resident:
-            self._stage_batch_from_host(); self.host_step = 0
+            hs = self.host_step
+            self._stage_batch_from_host()
+            torch.cuda.synchronize(self.dev)
+            self.host_step = hs; self._copy_stream = None        # restart the prefetch pipeline at the right step
         side = torch.cuda.Stream(self.dev)
         side.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(side):
@@ -236,16 +240,41 @@ class ReconEngine:
         self._restore(snap)
 
     # ------------------------------------------------------------------------------------------ driver
+    def _issue_stage(self, step_index: int, slot: int):
+        """H2D of mini-batch `step_index` into staging slot `slot` on the copy stream: one cudaMemcpyAsync per row,
+        straight from the pinned cache (no host gather; the batch-memcpy driver entry points are deliberately unused)"""
+        rows = self.idx_table_host[min(step_index, self.idx_table_host.shape[0] - 1)]
+        cs = self._copy_stream
+        cs.wait_event(self._slot_free[slot])                 # the D2D out of this slot must have finished
+        ops.stage_rows_h2d(self.cached_inps, rows, self._stage_inp[slot], cs)
+        ops.stage_rows_h2d(self.cached_outs, rows, self._stage_out[slot], cs)
+        if self.cur_grad is not None:
+            ops.stage_rows_h2d(self.cached_grads, rows, self._stage_grad[slot], cs)
+        self._slot_ready[slot].record(cs)
+
     def _stage_batch_from_host(self):
-        """H2D copy of this step's mini-batch rows straight from the pinned cache (one async copy per row:
-        no host-side gather; the batch-memcpy driver entry points are deliberately not used)"""
-        rows = self.idx_table_host[min(self.host_step, self.idx_table_host.shape[0] - 1)].tolist()
-        for j, r in enumerate(rows):
-            self.cur_inp[j].copy_(self.cached_inps[r], non_blocking=True)
-            self.cur_out[j].copy_(self.cached_outs[r], non_blocking=True)
-            if self.cur_grad is not None:
-                self.cur_grad[j].copy_(self.cached_grads[r], non_blocking=True)
+        """make the staged mini-batch current (device-to-device) and start the transfer of the next one, so the
+        PCIe copy of step i+1 overlaps the captured iteration of step i"""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.dev)
+            mk = lambda t: [torch.empty_like(t) for _ in range(2)]
+            self._stage_inp, self._stage_out = mk(self.cur_inp), mk(self.cur_out)
+            self._stage_grad = mk(self.cur_grad) if self.cur_grad is not None else None
+            self._slot_ready = [torch.cuda.Event() for _ in range(2)]
+            self._slot_free = [torch.cuda.Event() for _ in range(2)]
+            for e in self._slot_free:
+                e.record(torch.cuda.current_stream(self.dev))
+            self._issue_stage(self.host_step, self.host_step % 2)
+        slot = self.host_step % 2
+        main = torch.cuda.current_stream(self.dev)
+        main.wait_event(self._slot_ready[slot])
+        self.cur_inp.copy_(self._stage_inp[slot], non_blocking=True)
+        self.cur_out.copy_(self._stage_out[slot], non_blocking=True)
+        if self.cur_grad is not None:
+            self.cur_grad.copy_(self._stage_grad[slot], non_blocking=True)
+        self._slot_free[slot].record(main)
         self.host_step += 1
+        self._issue_stage(self.host_step, self.host_step % 2)
 
     def h2d_bytes_per_step(self) -> int:
         if not self.host_resident:

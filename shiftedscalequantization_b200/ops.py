@@ -566,6 +566,17 @@ def gather_rows(src, index, out=None):
     return out
 
 
+def stage_rows_h2d(host_src: torch.Tensor, rows: torch.Tensor, dev_dst: torch.Tensor, stream=None):
+    """dev_dst[n] = host_src[rows[n]]; host_src pinned fp32, rows a CPU int64 tensor; async on `stream`"""
+    if host_src.is_cuda or not host_src.is_pinned() or host_src.dtype != torch.float32:
+        raise _lib.SsqError("host_src must be a pinned fp32 host tensor")
+    rows = rows.contiguous()
+    per_sample = host_src.numel() // host_src.shape[0]
+    st = (stream or torch.cuda.current_stream(dev_dst.device)).cuda_stream
+    _lib.check(_lib.load().ssq_stage_rows_h2d(host_src.data_ptr(), rows.data_ptr(), dev_dst.data_ptr(), rows.numel(),
+                                               per_sample, st), "ssq_stage_rows_h2d")
+
+
 def loop_advance(step_dev, idx_table, idx_live, b_table, b_live, lr_table, lr_live, n_steps: int):
     batch = 0 if idx_live is None else idx_live.numel()
     _call("ssq_loop_advance", step_dev.data_ptr(), _ptr(idx_table), _ptr(idx_live), batch, _ptr(b_table), _ptr(b_live),
