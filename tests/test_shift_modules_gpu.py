@@ -1,0 +1,187 @@
+"""GPU tests of the shifted-scale module surface (ChannelQuant / ChannelQuantMSE / ChannelQuantAct), the shifted
+reconstruction loops, and the example driver — module-level parity against the reference golden vectors."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from conftest import ROOT, assert_close, assert_exact, golden
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    a = np.asarray(a, dtype=np.float32)
+    return torch.from_numpy(np.ascontiguousarray(a)).reshape(a.shape).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def make_uaq(bits, delta, zp, raw=None):
+    from shiftedscalequantization_b200.quant.quant_layer import UniformAffineQuantizer
+    q = UniformAffineQuantizer(n_bits=bits, channel_wise=True, scale_method='mse')
+    q.delta = nn.Parameter(dev(delta)); q.zero_point = nn.Parameter(dev(zp))
+    q.raw_zero_point = None if raw is None else dev(raw)
+    q.inited = True
+    return q.cuda()
+
+
+@pytest.mark.parametrize("case", golden("channelquant").cases())
+def test_channelquant_module_matches_reference(case):
+    from shiftedscalequantization_b200.quant.channelQuant import ChannelQuant
+    g = golden("channelquant").case(case)
+    bits = int(g["bits"]); shifts = [float(s) for s in g["shifts"]]
+    w = dev(g["w"])
+    uaq = make_uaq(bits, g["delta"], g["zp"])
+    q = ChannelQuant(1.0, uaq, w, shiftTarget=list(shifts))
+    assert_exact(host(q(w)), g["y_none"], "'none' forward")
+    q.init_v(w.clone())
+    assert q.opt_mode == 'learned_hard_sigmoid' and len(q.x_q) == 3
+    assert_exact(np.stack([host(t) for t in q.x_q], -1), g["xq"], "x_q of init_v")
+    assert_close(host(q.alpha), g["alpha_init"], atol=5e-7, what="alpha init (difference of logs: 1-ulp of log(0.36))")
+    with torch.no_grad():
+        q.alpha.copy_(dev(g["alpha"]))
+    y = q(w)
+    assert_close(host(y), g["y_soft"], what="soft mixture")
+    y.backward(dev(g["gy"]))
+    assert_close(host(q.alpha.grad), g["galpha_soft"], rtol=3e-5, what="galpha")
+    q.hard_targets = True
+    assert_exact(host(q(w)), g["y_hard"], "hard targets")
+    q.hard_targets = False
+    # AdaRound on top of the learned shift
+    q.update_delta(); q.init_beta(w.clone()); q.opt_mode = 'adaround'
+    assert_exact(host(q.delta), g["ar_delta"], "selected delta")
+    with torch.no_grad():
+        q.beta.copy_(dev(g["ar_beta"]))
+    y = q(w); y.backward(dev(g["gy"]))
+    assert_close(host(y), g["ar_y"], what="adaround forward"); assert_close(host(q.beta.grad), g["ar_gbeta"], what="gbeta")
+    q.hard_round = True
+    assert_exact(host(q(w)), g["ar_y_hard"], "adaround hard")
+    # fused path
+    q2 = ChannelQuant(1.0, uaq, w, shiftTarget=list(shifts))
+    q2.init_v_beta(w.clone()); q2.opt_mode = 'adaShift'
+    assert_exact(np.stack([host(t) for t in q2.x_q], -1), g["as_xq"], "x_q of init_v_beta")
+    assert_close(host(q2.alpha), g["as_alpha_init"], atol=5e-7, what="adaShift alpha init")
+    assert_close(host(q2.beta), g["as_beta_init"], rtol=3e-5, what="adaShift beta init")
+    with torch.no_grad():
+        q2.alpha.copy_(dev(g["as_alpha"])); q2.beta.copy_(dev(g["as_beta"]))
+    y = q2(w); y.backward(dev(g["gy"]))
+    assert_close(host(y), g["as_y"], what="adaShift forward")
+    assert_close(host(q2.alpha.grad), g["as_galpha"], rtol=3e-5, what="adaShift galpha")
+    assert_close(host(q2.beta.grad), g["as_gbeta"], what="adaShift gbeta")
+    q2.hard_round = q2.hard_targets = True
+    assert_exact(host(q2(w)), g["as_y_hard"], "adaShift hard")
+    q2.opt_mode = 'bogus'
+    with pytest.raises(ValueError, match='opt_mode is not defined'):
+        q2(w)
+
+
+@pytest.mark.parametrize("case", golden("channelquantmse").cases())
+def test_channelquantmse_module_matches_reference(case):
+    from shiftedscalequantization_b200.quant.channelQuantMSE import ChannelQuantMSE
+    g = golden("channelquantmse").case(case)
+    bits = int(g["bits"]); w = dev(g["w"])
+    zp = np.round(g["raw"] / g["delta"])
+    uaq = make_uaq(bits, g["delta"], zp, g["raw"])
+    for level in (1, 4, 16, 64):
+        q = ChannelQuantMSE(1.0, uaq, w, level=level, threshold=float(g[f"thr_l{level}"]), opt_mode='max')
+        q.init_scale(w)
+        assert_exact(host(q.inp_scale), g[f"inp_scale_l{level}"], f"inp_scale level {level}")
+        assert_exact(host(q.quant(w)), g[f"codes_l{level}"], "codes")
+        assert_close(host(q(w)), g[f"y_l{level}"], what="forward")
+    with pytest.raises(NotImplementedError):
+        ChannelQuantMSE(1.0, uaq, w, opt_mode='mse').init_scale(w)
+
+
+def test_channelquantact_modes():
+    from shiftedscalequantization_b200.quant.channelQuantAct import ChannelQuantAct
+    from shiftedscalequantization_b200.quant.quant_layer import UniformAffineQuantizer
+    from oracle import ssq_oracle as O
+    uaq = UniformAffineQuantizer(n_bits=4, channel_wise=False, scale_method='mse', leaf_param=True).cuda()
+    x = torch.relu(torch.randn(4, 8, 6, 6, device='cuda'))
+    uaq(x)
+    q = ChannelQuantAct(uaq)
+    y_ref, _ = O.uaq_forward(host(x), host(uaq.delta), host(uaq.zero_point), 0, 15)
+    assert_exact(host(q(x)), y_ref, "'none' mode")
+    with pytest.raises(NameError):
+        q.init_v()
+    q.opt_mode = 'adaShift'
+    with pytest.raises(AttributeError):
+        q(x)
+
+
+def _cache_block_features(Q, qnn, block, cali, bs=16):
+    """the 'if' / 'of' cache protocol of ShiftedScaleQuant.py:244-255"""
+    dev_ = next(qnn.parameters()).device
+    qnn.set_quant_state(True, False)
+    block.cache_features = 'if'
+    with torch.no_grad():
+        for i in range(0, cali.shape[0], bs):
+            qnn(cali[i:i + bs].to(dev_))
+    block.cache_features = 'none'
+    qnn.set_quant_state(False, False)
+    block.cache_features = 'of'
+    with torch.no_grad():
+        for i in range(0, cali.shape[0], bs):
+            qnn(cali[i:i + bs].to(dev_))
+    block.cache_features = 'none'
+    block.set_quant_state(True, False)
+
+
+def _shift_qnn():
+    from shiftedscalequantization_b200 import quant as Q, zoo
+    from shiftedscalequantization_b200.quant.channelQuant import ChannelQuant
+    torch.manual_seed(1005)
+    cnn = zoo.resnet18(num_classes=10).cuda().eval()
+    qnn = Q.QuantModel(cnn, {'n_bits': 2, 'channel_wise': True, 'scale_method': 'max'},
+                       {'n_bits': 4, 'channel_wise': False, 'scale_method': 'mse', 'leaf_param': True}).cuda().eval()
+    qnn.set_first_last_layer_to_8bit()
+    cali = torch.randn(64, 3, 32, 32)
+    qnn.set_quant_state(True, False)
+    with torch.no_grad():
+        qnn(cali[:32].cuda())
+    block = qnn.model.layer2[0]
+    for m in block.modules():
+        if isinstance(m, Q.QuantModule):
+            m.weight_quantizer = ChannelQuant(1.0, uaq=m.weight_quantizer, weight_tensor=m.org_weight.data,
+                                              shiftTarget=[0.96875, 1.03125, 1.0], name=m.pathName)
+    return Q, qnn, block, cali
+
+
+def test_block_recon_shifted_scale_then_adaround():
+    from shiftedscalequantization_b200.quant.layer_recon_shiftedScale import block_recon_shiftedScale
+    Q, qnn, block, cali = _shift_qnn()
+    _cache_block_features(Q, qnn, block, cali)
+    soft, hard = block_recon_shiftedScale(block, iters=40, lmda=0.01, model=qnn)
+    assert np.isfinite([soft, hard]).all() and soft > 0
+    assert all(m.weight_quantizer.hard_targets for m in block.modules() if isinstance(m, Q.QuantModule))
+    soft2, hard2 = block_recon_shiftedScale(block, iters=40, lmda=0.01, model=qnn, adaround=True)
+    assert np.isfinite([soft2, hard2]).all()
+    q = block.conv1.weight_quantizer
+    assert q.opt_mode == 'adaround' and q.hard_round and tuple(q.delta.shape[:2]) == tuple(block.conv1.weight.shape[:2])
+
+
+def test_block_recon_fused_shifted_scale():
+    from shiftedscalequantization_b200.quant.layer_recon_fused_shiftedScale import block_recon_fused_shiftedScale
+    Q, qnn, block, cali = _shift_qnn()
+    _cache_block_features(Q, qnn, block, cali)
+    a0 = None
+    soft, hard = block_recon_fused_shiftedScale(block, iters=40, lmda=(0.01, 0.01), model=qnn)
+    assert np.isfinite([soft, hard]).all()
+    q = block.conv2.weight_quantizer
+    assert q.opt_mode == 'adaShift' and q.hard_round and q.hard_targets and q.alpha.shape == (block.conv2.weight.shape[1], 3)
+
+
+def test_example_driver_cifar_config():
+    """BASELINE configs[0]: CIFAR-style ResNet-18, W4A8, channel-wise + MSE init, 256 synthetic 32x32 images"""
+    sys.path.insert(0, os.path.join(ROOT, "examples"))
+    import run_ptq
+    qnn = run_ptq.main(['--arch', 'resnet18', '--num_classes', '10', '--res', '32', '--n_bits_w', '4', '--n_bits_a', '8',
+                        '--num_samples', '256', '--iters_w', '24', '--iters_a', '16', '--max_units', '3'])
+    keys = qnn.state_dict().keys()
+    assert any(k.endswith('weight_quantizer.alpha') for k in keys) and any(k.endswith('act_quantizer.delta') for k in keys)
