@@ -428,8 +428,18 @@ def run_ours(args):
     shares = {k: {"launches": n, "ms": ms, "share_of_step": ms / eager_ms} for k, (n, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1])}
     dominant = next(iter(shares))
     mk = ENTRY_TO_MICRO.get(dominant, "recon_loss(fwd+dpred)")
+    traffic = None
+    try:    # dram__bytes_read+write of one launch at this microbench shape, from the committed ncu --set full capture
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_kernels_ncu_full.json")))
+        key = {"fq_adaround_fwd(+reg)": "ada_fwd_kernel", "fq_adaround_bwd(+reg grad)": "ada_bwd_kernel", "adam_step": "adam_kernel",
+               "recon_loss(fwd+dpred)": "recon_loss_kernel", "fq_affine_fwd(acts,per-tensor)": "fq_affine_fwd_vec",
+               "fq_affine_bwd(acts,per-tensor)": "fq_affine_bwd_kernel"}.get(mk)
+        if key in prof:
+            traffic = prof[key]["traffic_MB"] * 1e6
+    except Exception:
+        pass
     roof = {"bound": "hbm", "kernel": dominant, "achieved": micro[mk]["gbs"], "peak": peak_gbs, "unit": "GB/s",
-            "frac": micro[mk]["frac"], "traffic": None, "peak_source": peak_src,
+            "frac": micro[mk]["frac"], "traffic": traffic, "algorithmic_bytes": micro[mk]["bytes"], "peak_source": peak_src,
             "measured_on": f"{mk}: DRAM-resident microbench ({micro[mk]['bytes'] / 1e6:.0f} MB algorithmic per launch, inputs > L2), "
                            "CUDA events, 3 warm-ups + 10 timed launches",
             "in_step": {"eager_step_ms": eager_ms, "ssq_kernels_ms": ours_ms, "shares": shares},
