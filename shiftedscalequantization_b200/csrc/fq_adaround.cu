@@ -61,36 +61,36 @@ __device__ __forceinline__ double ada_fwd_span(const float* __restrict__ w, cons
     double acc = 0.0;
     ChanWalk cw;
     if (vec) {
-        constexpr int U = 2;
-        const int64_t i0 = (e0 >> 2) + tid, i1 = e1 >> 2;
-        cw.init(i0, nthr, inner >> 2, nchan);
-        for (int64_t i = i0; i < i1; i += nthr * U) {
-            float4 wv[U], av[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int64_t j = i + u * nthr;
-                if (j < i1) { wv[u] = ld_stream4(w + j * 4); av[u] = ld_stream4(alpha + j * 4); }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int64_t j = i + u * nthr;
-                if (j < i1) {
-                    const Recip R = make_recip(__ldg(delta + cw.c));
-                    const float z = __ldg(zp + cw.c);
-                    float4 y, q;
-                    AdaOut o;
-                    float rsum = 0.f;
-                    const float4 t = div4_exact(wv[u], R);
-#define ONE(F) o = ada_fwd_one<SOFT, REGON>(t.F, av[u].F, R, z, qmin, qmax, b); y.F = o.y; q.F = o.q; rsum += o.reg;
-                    ONE(x) ONE(y) ONE(z) ONE(w)
+        // local 32-bit vector indices relative to e0 (host guarantees (e1-e0)/4 < 2^31)
+        const float4* __restrict__ w4 = reinterpret_cast<const float4*>(w + e0);
+        const float4* __restrict__ a4 = reinterpret_cast<const float4*>(alpha + e0);
+        float4* __restrict__ y4 = reinterpret_cast<float4*>(wq + e0);
+        float4* __restrict__ c4 = codes ? reinterpret_cast<float4*>(codes + e0) : nullptr;
+        const uint32_t n4 = (uint32_t)((e1 - e0) >> 2), step = (uint32_t)nthr;
+        cw.init((uint64_t)(e0 >> 2) + (uint64_t)tid, nthr, inner >> 2, nchan);
+        auto body = [&](uint32_t j, const float4& wv, const float4& av) {
+            const Recip R = make_recip(__ldg(delta + cw.c));
+            const float z = __ldg(zp + cw.c);
+            float4 y, q;
+            AdaOut o;
+            float rsum = 0.f;
+            const float4 t = div4_exact(wv, R);
+#define ONE(F) o = ada_fwd_one<SOFT, REGON>(t.F, av.F, R, z, qmin, qmax, b); y.F = o.y; q.F = o.q; rsum += o.reg;
+            ONE(x) ONE(y) ONE(z) ONE(w)
 #undef ONE
-                    st_stream4(wq + j * 4, y);
-                    if (codes) st_stream4(codes + j * 4, q);
-                    if (REGON) acc += (double)rsum;
-                }
-                cw.next();
-            }
+            st_stream4(reinterpret_cast<float*>(y4 + j), y);
+            if (c4) st_stream4(reinterpret_cast<float*>(c4 + j), q);
+            if (REGON) acc += (double)rsum;
+            cw.next();
+        };
+        uint32_t j = (uint32_t)tid;
+        for (; j + step < n4 && j < n4; j += 2 * step) {          // two vectors in flight, no per-vector bounds test
+            const float4 w0 = ld_stream4(reinterpret_cast<const float*>(w4 + j)), a0 = ld_stream4(reinterpret_cast<const float*>(a4 + j));
+            const float4 w1 = ld_stream4(reinterpret_cast<const float*>(w4 + j + step)), a1 = ld_stream4(reinterpret_cast<const float*>(a4 + j + step));
+            body(j, w0, a0);
+            body(j + step, w1, a1);
         }
+        if (j < n4) body(j, ld_stream4(reinterpret_cast<const float*>(w4 + j)), ld_stream4(reinterpret_cast<const float*>(a4 + j)));
     } else {
         cw.init(e0 + tid, nthr, inner, nchan);
         for (int64_t i = e0 + tid; i < e1; i += nthr) {
@@ -113,40 +113,38 @@ __device__ __forceinline__ void ada_bwd_span(const float* __restrict__ gwq, cons
                                              int accumulate, int64_t tid, int64_t nthr, bool vec) {
     ChanWalk cw;
     if (vec) {
-        constexpr int U = 2;
-        const int64_t i0 = (e0 >> 2) + tid, i1 = e1 >> 2;
-        cw.init(i0, nthr, inner >> 2, nchan);
-        for (int64_t i = i0; i < i1; i += nthr * U) {
-            float4 wv[U], av[U], gv[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int64_t j = i + u * nthr;
-                if (j < i1) {
-                    wv[u] = ld_stream4(w + j * 4); av[u] = ld_stream4(alpha + j * 4);
-                    gv[u] = REC ? ld_stream4(gwq + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+        const float4* __restrict__ w4 = reinterpret_cast<const float4*>(w + e0);
+        const float4* __restrict__ a4 = reinterpret_cast<const float4*>(alpha + e0);
+        const float4* __restrict__ g4 = REC ? reinterpret_cast<const float4*>(gwq + e0) : nullptr;
+        float4* __restrict__ o4 = reinterpret_cast<float4*>(galpha + e0);
+        const uint32_t n4 = (uint32_t)((e1 - e0) >> 2), step = (uint32_t)nthr;
+        cw.init((uint64_t)(e0 >> 2) + (uint64_t)tid, nthr, inner >> 2, nchan);
+        auto body = [&](uint32_t j, const float4& wv, const float4& av, const float4& gv) {
+            const Recip R = make_recip(__ldg(delta + cw.c));
+            const float z = __ldg(zp + cw.c);
+            float4 o, t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (REC) t = div4_exact(wv, R);
+            o.x = ada_bwd_one<REC, REGON>(gv.x, t.x, av.x, R, z, qmin, qmax, b, lam_g);
+            o.y = ada_bwd_one<REC, REGON>(gv.y, t.y, av.y, R, z, qmin, qmax, b, lam_g);
+            o.z = ada_bwd_one<REC, REGON>(gv.z, t.z, av.z, R, z, qmin, qmax, b, lam_g);
+            o.w = ada_bwd_one<REC, REGON>(gv.w, t.w, av.w, R, z, qmin, qmax, b, lam_g);
+            if (accumulate) {
+                const float4 p = o4[j];
+                o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
             }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int64_t j = i + u * nthr;
-                if (j < i1) {
-                    const Recip R = make_recip(__ldg(delta + cw.c));
-                    const float z = __ldg(zp + cw.c);
-                    float4 o, t = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (REC) t = div4_exact(wv[u], R);
-                    o.x = ada_bwd_one<REC, REGON>(gv[u].x, t.x, av[u].x, R, z, qmin, qmax, b, lam_g);
-                    o.y = ada_bwd_one<REC, REGON>(gv[u].y, t.y, av[u].y, R, z, qmin, qmax, b, lam_g);
-                    o.z = ada_bwd_one<REC, REGON>(gv[u].z, t.z, av[u].z, R, z, qmin, qmax, b, lam_g);
-                    o.w = ada_bwd_one<REC, REGON>(gv[u].w, t.w, av[u].w, R, z, qmin, qmax, b, lam_g);
-                    if (accumulate) {
-                        const float4 p = *reinterpret_cast<const float4*>(galpha + j * 4);
-                        o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
-                    }
-                    st_stream4(galpha + j * 4, o);
-                }
-                cw.next();
-            }
+            st_stream4(reinterpret_cast<float*>(o4 + j), o);
+            cw.next();
+        };
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto ld = [&](const float4* p, uint32_t j) { return ld_stream4(reinterpret_cast<const float*>(p + j)); };
+        uint32_t j = (uint32_t)tid;
+        for (; j + step < n4 && j < n4; j += 2 * step) {
+            const float4 w0 = ld(w4, j), a0 = ld(a4, j), g0 = REC ? ld(g4, j) : zero4;
+            const float4 w1 = ld(w4, j + step), a1 = ld(a4, j + step), g1 = REC ? ld(g4, j + step) : zero4;
+            body(j, w0, a0, g0);
+            body(j + step, w1, a1, g1);
         }
+        if (j < n4) body(j, ld(w4, j), ld(a4, j), REC ? ld(g4, j) : zero4);
     } else {
         cw.init(e0 + tid, nthr, inner, nchan);
         for (int64_t i = e0 + tid; i < e1; i += nthr) {
@@ -332,7 +330,8 @@ extern "C" int ssq_fq_adaround_fwd(const float* w, const float* alpha, const flo
     if (reg && (!b_dev || !soft)) return SSQ_ERR_MODE;
     if (reg && (!ws || ws_bytes < ssq_ws_bytes(1))) return SSQ_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
-    bool vec = aligned16(w) && aligned16(alpha) && aligned16(wq) && (!codes || aligned16(codes)) && (inner % 4 == 0);
+    bool vec = aligned16(w) && aligned16(alpha) && aligned16(wq) && (!codes || aligned16(codes)) && (inner % 4 == 0) &&
+               (n / 4 < (int64_t)0x7fffffff);
     int64_t per_cta = (int64_t)SSQ_THREADS * (vec ? 8 : 1);
     int grid = grid_for((n + per_cta - 1) / per_cta);
     WsView v = ws_view(ws, 1);
@@ -352,7 +351,8 @@ extern "C" int ssq_fq_adaround_bwd(const float* gwq, const float* w, const float
     if (n == 0) return SSQ_OK;
     if (!w || !alpha || !delta || !zero_point || !galpha) return SSQ_ERR_NULL;
     if (int e = check_layout(n, inner, nchan)) return e;
-    bool vec = (!gwq || aligned16(gwq)) && aligned16(w) && aligned16(alpha) && aligned16(galpha) && (inner % 4 == 0);
+    bool vec = (!gwq || aligned16(gwq)) && aligned16(w) && aligned16(alpha) && aligned16(galpha) && (inner % 4 == 0) &&
+               (n / 4 < (int64_t)0x7fffffff);
     int64_t per_cta = (int64_t)SSQ_THREADS * (vec ? 8 : 1);
     int grid = grid_for((n + per_cta - 1) / per_cta);
     ada_bwd_kernel<<<grid, SSQ_THREADS, 0, (cudaStream_t)stream>>>(gwq, w, alpha, delta, zero_point, galpha, n, inner, nchan,

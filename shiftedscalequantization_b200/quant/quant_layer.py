@@ -132,7 +132,18 @@ class UniformAffineQuantizer(nn.Module):
         return mk(deltas), mk(zps), mk(raws)
 
     def _init_mse(self, rows: torch.Tensor):
-        delta, zp, raw, _score, idx = ops.mse_scale_search(rows, self.n_levels, self.sym, 2.4)
+        # multi-GPU: the per-channel search is sharded by output channel (rows) and all-gathered; replicas hold the
+        # same weights, the kernel is deterministic, so every rank ends with bit-identical parameters
+        from .. import dist as ssq_dist
+        world = ssq_dist.world_size()
+        if world > 1 and self.channel_wise and rows.shape[0] >= world:
+            lo, hi = ssq_dist.shard_range(rows.shape[0])
+            parts = ops.mse_scale_search(rows[lo:hi].contiguous(), self.n_levels, self.sym, 2.4)
+            packed = torch.stack([parts[0], parts[1], parts[2], parts[4].to(torch.float32)], dim=1)
+            full = ssq_dist.all_gather_rows(packed, rows.shape[0])
+            delta, zp, raw, idx = full[:, 0].contiguous(), full[:, 1].contiguous(), full[:, 2].contiguous(), full[:, 3]
+        else:
+            delta, zp, raw, _score, idx = ops.mse_scale_search(rows, self.n_levels, self.sym, 2.4)
         if bool((idx < 0).any()):
             # upstream: every score is NaN (all-zero channel) so delta stays None and the assignment
             # `delta[c] = None` raises TypeError (quant_layer.py:114)
