@@ -313,6 +313,10 @@ def main():
     with torch.no_grad():
         rl["final_logits"] = npy(qnn(cali[:8]))
     save("recon_loop", **rl)
+    # checkpoint compatibility: parameter/buffer names and shapes of the reference's state_dict at this point
+    import json
+    with open(os.path.join(OUT, "state_dict_keys.json"), "w") as f:
+        json.dump({k: list(v.shape) for k, v in qnn.state_dict().items()}, f, indent=0, sort_keys=True)
 
 
 if __name__ == "__main__":

@@ -192,6 +192,12 @@ def test_full_api_matches_reference_loops():
     qnn.set_quant_state(True, False)
     with torch.no_grad():
         logits = qnn(cali[:8].cuda()).cpu().numpy()
+    # checkpoint compatibility: same parameter names and shapes as the reference's state_dict after the same flow
+    import json, os
+    from conftest import GOLDEN_DIR
+    ref_keys = json.load(open(os.path.join(GOLDEN_DIR, "state_dict_keys.json")))
+    mine = {k: list(v.shape) for k, v in qnn.state_dict().items()}
+    assert mine == ref_keys, (sorted(set(ref_keys) - set(mine))[:5], sorted(set(mine) - set(ref_keys))[:5])
     # a few flipped 2-bit codes move individual logits; the vectors must still agree closely in norm
     rel = np.linalg.norm(logits - g["final_logits"]) / np.linalg.norm(g["final_logits"])
     flips = sum(int((np.sign(m.weight_quantizer.alpha.detach().cpu().numpy()) != np.sign(g[f"block.{n}.alpha"])).sum())

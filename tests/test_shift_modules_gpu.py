@@ -185,3 +185,42 @@ def test_example_driver_cifar_config():
                         '--num_samples', '256', '--iters_w', '24', '--iters_a', '16', '--max_units', '3'])
     keys = qnn.state_dict().keys()
     assert any(k.endswith('weight_quantizer.alpha') for k in keys) and any(k.endswith('act_quantizer.delta') for k in keys)
+
+
+def test_channel_shift_mse_flow_mobilenetv2_w3():
+    """BASELINE configs[3] at small scale: MobileNetV2 W3 (depthwise-heavy) + ChannelQuantMSE input-scale search"""
+    from shiftedscalequantization_b200 import scaled_methods as SM, zoo
+    from shiftedscalequantization_b200.quant.channelQuantMSE import ChannelQuantMSE
+    from shiftedscalequantization_b200 import quant as Q
+    from oracle import ssq_oracle as O
+    torch.manual_seed(1005)
+    cnn = zoo.mobilenetv2().cuda().eval()
+    qnn = SM.build_qnn_from_model(cnn, n_bits_w=3, n_bits_a=3, w_scale_method='max')
+    cali = torch.randn(64, 3, 64, 64)
+    # upstream builds per QuantBasicBlock; MobileNetV2's blocks are QuantInvertedResidual, so its layers are reached by recursion
+    SM.channelShift_wMSE_flow(qnn, cali, level=8, threshold=1.5, layerDisabled=('.model.classifier.1',))
+    mods = [m for m in qnn.modules() if isinstance(m, Q.QuantModule)]
+    built = [m for m in mods if isinstance(m.weight_quantizer, ChannelQuantMSE)]
+    assert len(built) >= 50
+    dw = next(m for m in built if m.fwd_kwargs.get('groups', 1) > 1)           # a depthwise layer: rows of 9
+    q = dw.weight_quantizer
+    ref = O.inp_scale_search(host(dw.org_weight), host(q.delta), host(q.raw_zero_point), q.n_levels, 8, 1.5)
+    assert_exact(host(q.inp_scale), ref, "depthwise inp_scale vs oracle")
+    y_ref, _ = O.channelquantmse_forward(host(dw.org_weight), host(q.delta), host(q.raw_zero_point), ref, q.n_levels)
+    assert_exact(host(q(dw.weight)), y_ref, "depthwise ChannelQuantMSE forward vs oracle")
+    with torch.no_grad():
+        assert torch.isfinite(qnn(cali[:4].cuda())).all()
+
+
+def test_channel_shift_loss_flow_resnet18():
+    from shiftedscalequantization_b200 import scaled_methods as SM, zoo
+    torch.manual_seed(1005)
+    cnn = zoo.resnet18(num_classes=10).cuda().eval()
+    qnn = SM.build_qnn_from_model(cnn, n_bits_w=2, n_bits_a=4, w_scale_method='max')
+    cali = torch.randn(64, 3, 32, 32)
+    qnn, losses = SM.channelShift_wLoss_flow(qnn, cali, ['.model.layer1.0'], iters=30, lmda=0.01,
+                                             shiftTarget=[0.96875, 1.03125, 1.0], batch_size=32)
+    (soft, hard), = losses['.model.layer1.0']
+    assert np.isfinite([soft, hard]).all()
+    blk = qnn.model.layer1[0]
+    assert blk.conv1.weight_quantizer.opt_mode == 'adaShift' and blk.conv1.weight_quantizer.hard_targets
