@@ -300,6 +300,29 @@ def kernel_microbench(dev, peak_gbs):
     return res
 
 
+def scale_search_bench(Q, qnn, dev):
+    """K2a alone: the 80-candidate MSE clip search over every weight tensor of the model (per-channel rows) and over
+    one activation-sized tensor (per-tensor, grid-wide variant); CUDA events, after one warm-up pass"""
+    from shiftedscalequantization_b200 import ops
+    mods = [m for m in qnn.modules() if isinstance(m, Q.QuantModule)]
+    rows = [(m.org_weight.reshape(m.org_weight.shape[0], -1).contiguous(), m.weight_quantizer.n_levels) for m in mods]
+    def run():
+        for r, nl in rows:
+            ops.mse_scale_search(r, nl, False)
+    run(); torch.cuda.synchronize(dev)
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(); run(); e1.record(); torch.cuda.synchronize(dev)
+    w_ms = e0.elapsed_time(e1)
+    act = torch.relu(torch.randn(64, 64, 112, 112, device=dev)).reshape(1, -1)
+    ops.mse_scale_search(act, 16, False); torch.cuda.synchronize(dev)
+    e0.record(); ops.mse_scale_search(act, 16, False); e1.record(); torch.cuda.synchronize(dev)
+    a_ms = e0.elapsed_time(e1)
+    return {"weights_all_layers_ms": w_ms, "channels": int(sum(r.shape[0] for r, _ in rows)),
+            "weight_elems": int(sum(r.numel() for r, _ in rows)),
+            "activation_tensor_ms": a_ms, "activation_elems": int(act.numel()),
+            "note": "powf-bound (80 x |d|^2.4 per element), not HBM-bound; reference: Python loop, 48.5 s on 8 CPU cores (SURVEY probe)"}
+
+
 ENTRY_TO_MICRO = {"ssq_recon_loss": "recon_loss(fwd+dpred)", "ssq_gather_rows": "gather_rows", "ssq_adam_step": "adam_step",
                   "ssq_fq_adaround_fwd_mt": "fq_adaround_fwd(+reg)", "ssq_fq_adaround_bwd_mt": "fq_adaround_bwd(+reg grad)",
                   "ssq_fq_affine_fwd": "fq_affine_fwd(acts,per-tensor)", "ssq_fq_affine_bwd": "fq_affine_bwd(acts,per-tensor)"}
@@ -362,6 +385,7 @@ def run_ours(args):
         qnn(cali[:64].to(dev))
     torch.cuda.synchronize(dev); scale_search_s = time.perf_counter() - t0
     log(f"[rank {rank}] weight scale search (5800 channels x 80 candidates): {scale_search_s * 1e3:.1f} ms")
+    search = scale_search_bench(Q, qnn, dev) if world == 1 else None
     engines, feats = make_engines(Q, qnn, cali, dev, act_quant=False, multi_gpu=world > 1)
     setup_s = time.perf_counter() - t_setup
     launches_per_step = sum(e.launches_per_iter for e in engines)
@@ -389,7 +413,6 @@ def run_ours(args):
                "path": "ReconEngine(host_resident=True): pinned host feature cache -> ssq_stage_rows_h2d (one cudaMemcpyAsync per row, "
                        "prefetched one step ahead on a copy stream) -> captured iteration -> loss .item() every iteration"}
         release(eng_h)
-    del feats
     torch.cuda.empty_cache()
 
     if world > 1:
@@ -414,13 +437,26 @@ def run_ours(args):
         release(eng_a)
         del eng_a
         torch.cuda.empty_cache()
+    tf32_extra = None
+    if not args.skip_tf32 and not args.tf32:
+        # PyTorch's own default (cudnn.allow_tf32=True) for the convolutions the path does not own; reported beside the
+        # fp32 headline, never instead of it
+        torch.backends.cudnn.allow_tf32 = True
+        qnn.set_quant_state(True, False)
+        eng_t, _ = make_engines(Q, qnn, cali, dev, act_quant=False, multi_gpu=False, feats=feats)
+        ms_t = timed_steps(eng_t, max(args.steps // 2, 3), 3, dev, 1)
+        tf32_extra = {"iters_per_s": n_units / (ms_t * 1e-3), "ms_per_step": ms_t, "conv_math": "tf32 (torch default)"}
+        release(eng_t)
+        del eng_t
+        torch.backends.cudnn.allow_tf32 = False
+    del feats
     del engines, qnn
     torch.cuda.empty_cache()
 
     # ---- roofline: DRAM-resident microbench of every kernel + in-step shares
     if args.skip_micro:
         line = base_line(args, value, ms_step, world, clocks, launches_per_step, e2e, peak_src)
-        line["extra"] = {"weight_scale_search_ms": scale_search_s * 1e3, "setup_s": setup_s, "act_phase": act}
+        line["extra"] = {"first_quantised_forward_ms": scale_search_s * 1e3, "scale_search": search, "setup_s": setup_s, "act_phase": act}
         print(json.dumps(line), flush=True)
         return
     micro = kernel_microbench(dev, peak_gbs)
@@ -449,7 +485,10 @@ def run_ours(args):
     line["roofline"] = roof
     if cpu:
         line["cpu_baseline"] = {"value": cpu["iters_per_s"], "unit": "iters/s", "cores": cpu["cores"], "kind": "port", "sample": cpu["sample"]}
-    line["extra"] = {"weight_scale_search_ms": scale_search_s * 1e3, "setup_s": setup_s, "act_phase": act,
+    fq = {k: round(v["gbs"], 1) for k, v in micro.items() if k.startswith("fq_")}
+    line["extra"] = {"first_quantised_forward_ms": scale_search_s * 1e3, "scale_search": search, "setup_s": setup_s, "act_phase": act,
+                     "fake_quant_hbm_gbs": fq, "fake_quant_hbm_frac_min": round(min(v["frac"] for k, v in micro.items() if k.startswith("fq_")), 3),
+                     "tf32": tf32_extra,
                      "projected_full_run_s": (9 * 20000) / value + ((9 * 5000) / act["iters_per_s"] if act else 0)}
     print(json.dumps(line), flush=True)
 
@@ -480,6 +519,7 @@ def main():
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-act", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-tf32", action="store_true")
     ap.add_argument("--micro-only", action="store_true", help="only the DRAM-resident kernel microbench")
     ap.add_argument("--skip-micro", action="store_true", help="no roofline microbench (short profiler runs)")
     args = ap.parse_args()
