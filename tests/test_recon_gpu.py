@@ -251,3 +251,37 @@ def test_engine_vs_oracle_loop_on_identical_features(which):
         moved = np.abs(ref - R.init_alpha(spec["layers"][n]["weight"], spec["layers"][n]["delta"]).numpy())
         print(which, n, "max |alpha-ref|", np.abs(a - ref).max(), "max movement", moved.max())
         assert_close(a, ref, rtol=2e-3, what=f"alpha {n} engine vs oracle loop")
+
+
+def test_act_phase_engine_vs_oracle_loop():
+    """Activation step-size learning (LSQ, cosine lr, p=2.4): ReconEngine against the oracle's CPU restatement of the
+    reference loop on identical cached features, index stream and initial step sizes."""
+    from oracle import ref_loop_torch as R
+    from shiftedscalequantization_b200.engine import ReconEngine, index_table
+    from shiftedscalequantization_b200.quant.data_utils import save_inp_oup_data
+    Q, qnn, cali = build_qnn(res=32, n_cali=32)
+    block = qnn.model.layer1[0]
+    Q.block_reconstruction(qnn, block, cali_data=cali, iters=8, weight=0.01, asym=True, warmup=0.2, batch_size=16)
+    qnn.set_quant_state(True, True)
+    with torch.no_grad():
+        qnn(cali[:32].cuda())                                    # act-quantiser scale init (per-tensor MSE search)
+    iters, bs = 16, 16
+    qnn.set_quant_state(False, False); block.set_quant_state(True, True)
+    mods = [m for m in block.modules() if isinstance(m, Q.QuantModule)]
+    inps, outs = save_inp_oup_data(qnn, block, cali, True, True, bs)
+    torch.manual_seed(11)
+    tab = index_table(inps.shape[0], bs, iters)
+    spec = _unit_spec(Q, block)
+    alphas = {n: m.weight_quantizer.alpha.detach().cpu() for n, m in block.named_modules() if isinstance(m, Q.QuantModule)}
+    aq = {"conv1": block.conv1.act_quantizer, "__block__": block.act_quantizer}
+    act_state = {k: (q.delta.detach().cpu().clone().requires_grad_(True), q.zero_point.detach().cpu(), q.n_levels) for k, q in aq.items()}
+    d0 = {k: float(v[0]) for k, v in act_state.items()}
+    R.recon_act_loop(spec, inps.cpu(), outs.cpu(), tab, iters, act_state, alphas, lr=4e-4, p=2.4)
+    eng = ReconEngine(block, mods, inps, outs, None, act_quant=True, iters=iters, weight=0.0, p=2.4, lr=4e-4, batch_size=bs,
+                      act_quantizers=[block.act_quantizer] + [m.act_quantizer for m in mods if m.act_quantizer.delta is not None],
+                      use_graph=True, idx_table=tab, verbose=False)
+    eng.run(); eng.close()
+    for k, q in aq.items():
+        ref, got = float(act_state[k][0]), float(q.delta)
+        assert ref != d0[k], "reference step size did not move"
+        assert abs(got - ref) <= 2e-3 * abs(ref - d0[k]) + 1e-5 * abs(ref), (k, d0[k], ref, got)
