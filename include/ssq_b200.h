@@ -140,7 +140,8 @@ int ssq_fq_adaround_bwd_mt(const ssq_adaround_desc* table, int count, int64_t to
  * element: alpha [OC*IC,S] (pass ic_groups = OC*IC, kk = 1, per_element = 1).
  * probs: p = clamp(softmax(alpha,-1)*1.2-0.1,0,1) (channelQuant.py:120-121) -> p [G,S];
  * also entropy regulariser -sum p*log(p+1e-10) (layer_recon_shiftedScale.py:393, mode 0) or
- * sum(1-|2p-1|^b) (layer_recon_fused_shiftedScale.py:281-282, mode 1) into reg_out (nullable). */
+ * sum(1-|2p-1|^b) (layer_recon_fused_shiftedScale.py:281-282, mode 1) into reg_out (nullable).
+ * When b_dev is given, *b_dev <= 0 switches the regulariser off in either mode (the losses' warm-up gate). */
 int ssq_shift_probs_fwd(const float* alpha, float* p, int64_t groups, int nshift,
                         int reg_mode, const float* b_dev, float lambda, float* reg_out,
                         void* ws, size_t ws_bytes, void* stream);

@@ -30,8 +30,10 @@ __global__ void __launch_bounds__(SSQ_THREADS)
 shift_probs_fwd_kernel(const float* __restrict__ alpha, float* __restrict__ p_out, int64_t groups, int S,
                        int reg_mode, const float* __restrict__ b_dev, float lambda, float* __restrict__ reg_out, WsView ws) {
     __shared__ double smem[32];
-    const float b = (reg_mode == 1 && b_dev) ? __ldg(b_dev) : 0.f;
-    const bool reg_on = reg_out && (reg_mode == 0 || (reg_mode == 1 && b > 0.f));
+    // b_dev given: b <= 0 switches the regulariser off in BOTH modes (warm-up gate of the shifted losses,
+    // layer_recon_shiftedScale.py:379-380); the entropy mode without b_dev is always on
+    const float b = b_dev ? __ldg(b_dev) : 0.f;
+    const bool reg_on = reg_out && (b_dev ? (b > 0.f) : (reg_mode == 0));
     double acc[1] = {0.0};
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
@@ -55,8 +57,8 @@ __global__ void __launch_bounds__(SSQ_THREADS)
 shift_probs_bwd_kernel(const float* __restrict__ alpha, const float* __restrict__ gp, float* __restrict__ galpha,
                        int64_t groups, int S, int reg_mode, const float* __restrict__ b_dev, float lambda,
                        const float* __restrict__ greg) {
-    const float b = (reg_mode == 1 && b_dev) ? __ldg(b_dev) : 0.f;
-    const bool reg_on = (reg_mode == 0 || (reg_mode == 1 && b > 0.f));
+    const float b = b_dev ? __ldg(b_dev) : 0.f;
+    const bool reg_on = (reg_mode >= 0) && (b_dev ? (b > 0.f) : (reg_mode == 0));
     const float lam_g = reg_on ? lambda * (greg ? __ldg(greg) : 1.f) : 0.f;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
