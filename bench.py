@@ -214,12 +214,15 @@ def release(engines):
 
 def timed_steps(engines, steps, warmup, dev, world, read_loss=False):
     import torch.distributed as td
+    if read_loss:
+        for e in engines:
+            e.enable_loss_readback()
     for _ in range(warmup):
         for e in engines:
             e.unit.set_quant_state(True, e.act_quant)
             e.step()
             if read_loss:
-                float(e.loss_dev)
+                e.read_loss()
     torch.cuda.synchronize(dev)
     if world > 1:
         td.barrier()
@@ -231,7 +234,10 @@ def timed_steps(engines, steps, warmup, dev, world, read_loss=False):
         for e in engines:
             e.step()
             if read_loss:
-                float(e.loss_dev)                        # D2H read of the step's result
+                e.read_loss()                            # D2H read of this unit's previous result (pinned ring, lag 1)
+    if read_loss:
+        for e in engines:
+            e.read_loss(latest=True)                     # drain: the last step's results are read inside the timed region
     t1.record()
     torch.cuda.synchronize(dev)
     if world > 1:
@@ -410,8 +416,10 @@ def run_ours(args):
         ms_e2e = timed_steps(eng_h, max(args.steps // 2, 3), max(args.warmup // 2, 3), dev, world, read_loss=True)
         e2e = {"value": world * n_units / (ms_e2e * 1e-3), "unit": "iters/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": sum(e.h2d_bytes_per_step() for e in eng_h), "d2h_bytes_per_step": 4 * n_units,
-               "path": "ReconEngine(host_resident=True): pinned host feature cache -> ssq_stage_rows_h2d (one cudaMemcpyAsync per row, "
-                       "prefetched one step ahead on a copy stream) -> captured iteration -> loss .item() every iteration"}
+               "path": "ReconEngine(host_resident=True, host_stage='pull'): pinned host feature cache; inside each captured iteration a 16-CTA "
+                       "kernel (ssq_pull_rows_host) reads the NEXT mini-batch's input and target rows out of mapped host memory over PCIe "
+                       "beside the current iteration's kernels; every iteration's loss is copied to a pinned 2-deep ring and read on the "
+                       "host one launch later (all losses read inside the timed region)"}
         release(eng_h)
     torch.cuda.empty_cache()
 

@@ -243,6 +243,14 @@ int ssq_gather_rows(const float* src, const int64_t* index, float* dst,
  * one cudaMemcpyAsync per row on `stream`; rows is a HOST array. No host-side gather, no staging copy. */
 int ssq_stage_rows_h2d(const float* host_src, const int64_t* rows, float* dev_dst,
                        int64_t batch, int64_t per_sample, void* stream);
+/* same mode, pull variant: the SMs read the rows out of MAPPED pinned host memory (cudaHostAlloc/UVA: the host
+ * pointer is valid on the device) and write them to dev_dst. The rows are row `min(*step_dev + lookahead,
+ * n_steps-1)` of the DEVICE index table (the reference's torch.randperm(N)[:B] stream, quant/block_recon.py:90), so
+ * the transfer needs no host work per iteration and can be a node of a captured graph. max_ctas caps the grid
+ * (<= 0: 32) so it can run beside the iteration it prefetches for. */
+int ssq_pull_rows_host(const float* host_src_mapped, const int64_t* idx_table, const int64_t* step_dev,
+                       int64_t lookahead, int64_t n_steps, float* dev_dst, int64_t batch, int64_t per_sample,
+                       int max_ctas, void* stream);
 /* advance the device-side iteration state used by a graph-captured loop: step += 1, and
  * copy row `step` of idx_table/b_table/lr_table into the live slots. */
 int ssq_loop_advance(int64_t* step_dev, const int64_t* idx_table, int64_t* idx_live, int batch,

@@ -66,6 +66,7 @@ PROTOTYPES = {
     "ssq_adam_step": (_i32, [_p, _p, _p, _p, _i64, _p, _d, _d, _d, _p, _p]),
     "ssq_gather_rows": (_i32, [_p, _p, _p, _i64, _i64, _p]),
     "ssq_stage_rows_h2d": (_i32, [_p, _p, _p, _i64, _i64, _p]),
+    "ssq_pull_rows_host": (_i32, [_p, _p, _p, _i64, _i64, _p, _i64, _i64, _i32, _p]),
     "ssq_loop_advance": (_i32, [_p, _p, _p, _i32, _p, _p, _p, _p, _i64, _p]),
 }
 

@@ -61,6 +61,47 @@ __global__ void loop_advance_kernel(int64_t* step_dev, const int64_t* __restrict
     if (threadIdx.x == 0) *step_dev = *step_dev + 1;
 }
 
+// Host-resident feature cache, pull variant: the SMs read the mini-batch rows straight out of mapped pinned host
+// memory (UVA) with 128-bit loads, 4 in flight per thread, and write them to HBM. The row numbers come from the
+// device-side index table at *step_dev + lookahead, so the transfer is a node of the captured iteration graph
+// (forked beside the iteration it prefetches for) and costs the host nothing per step. PCIe-bound: a few dozen
+// CTAs keep > 200 KB in flight, which is what a Gen5 x16 link needs; the grid is capped so the convolutions
+// running beside it keep their SMs.
+__global__ void __launch_bounds__(SSQ_THREADS)
+pull_rows_kernel(const float* __restrict__ host_src, const int64_t* __restrict__ idx_table,
+                 const int64_t* __restrict__ step_dev, int64_t lookahead, int64_t n_steps,
+                 float* __restrict__ dst, int64_t batch, int64_t per_sample, bool vec) {
+    int64_t s = *step_dev + lookahead;
+    if (s >= n_steps) s = n_steps - 1;
+    if (s < 0) s = 0;
+    const int64_t* __restrict__ rows = idx_table + s * batch;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (vec) {
+        const int64_t ps4 = per_sample >> 2, total4 = batch * ps4;
+        int64_t i = first;
+        for (; i + 3 * stride < total4; i += 4 * stride) {
+            float4 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int64_t j = i + k * stride, r = j / ps4;
+                v[k] = ld_stream4(host_src + (__ldg(rows + r) * ps4 + (j - r * ps4)) * 4);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) st_stream4(dst + (i + k * stride) * 4, v[k]);
+        }
+        for (; i < total4; i += stride) {
+            const int64_t r = i / ps4;
+            st_stream4(dst + i * 4, ld_stream4(host_src + (__ldg(rows + r) * ps4 + (i - r * ps4)) * 4));
+        }
+    } else {
+        const int64_t total = batch * per_sample;
+        for (int64_t i = first; i < total; i += stride) {
+            const int64_t r = i / per_sample;
+            dst[i] = host_src[__ldg(rows + r) * per_sample + (i - r * per_sample)];
+        }
+    }
+}
+
 }  // namespace ssq
 
 using namespace ssq;
@@ -97,6 +138,24 @@ extern "C" int ssq_stage_rows_h2d(const float* host_src, const int64_t* rows, fl
         if (e != cudaSuccess) return (int)e;
     }
     return SSQ_OK;
+}
+
+extern "C" int ssq_pull_rows_host(const float* host_src_mapped, const int64_t* idx_table, const int64_t* step_dev,
+                                  int64_t lookahead, int64_t n_steps, float* dev_dst, int64_t batch, int64_t per_sample,
+                                  int max_ctas, void* stream) {
+    if (batch == 0 || per_sample == 0) return SSQ_OK;
+    if (!host_src_mapped || !idx_table || !step_dev || !dev_dst) return SSQ_ERR_NULL;
+    if (batch < 0 || per_sample < 0 || n_steps <= 0) return SSQ_ERR_SIZE;
+    const bool vec = (per_sample % 4 == 0) && aligned16(host_src_mapped) && aligned16(dev_dst);
+    const int64_t total = batch * per_sample;
+    const int64_t per_cta = (int64_t)SSQ_THREADS * (vec ? 16 : 1);
+    int64_t grid = (total + per_cta - 1) / per_cta;
+    const int64_t cap = max_ctas > 0 ? max_ctas : 32;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    pull_rows_kernel<<<(int)grid, SSQ_THREADS, 0, (cudaStream_t)stream>>>(host_src_mapped, idx_table, step_dev, lookahead, n_steps,
+                                                                      dev_dst, batch, per_sample, vec);
+    return launch_status();
 }
 
 extern "C" int ssq_abi_version(void) { return SSQ_ABI_VERSION; }

@@ -87,12 +87,18 @@ class ReconEngine:
                  lr: float = 4e-5, opt_mode: str = 'mse', batch_size: int = 32, multi_gpu: bool = False,
                  act_quantizers: Sequence[nn.Module] = (), use_graph: Optional[bool] = None,
                  idx_table: Optional[torch.Tensor] = None, verbose: bool = True,
-                 host_resident: bool = False, device: Optional[torch.device] = None):
+                 host_resident: bool = False, device: Optional[torch.device] = None, host_stage: str = 'pull'):
         """host_resident=True keeps the cached features in (pinned) host memory, as the reference does with
         keep_gpu=False (quant/data_utils.py:34-36, `cached_inps[idx].to(device)` at block_recon.py:91-92): every
-        step copies its mini-batch rows host->device before the captured iteration runs."""
+        step moves its mini-batch rows host->device. host_stage='pull' (default): a kernel inside the captured
+        iteration reads the NEXT mini-batch's rows out of the mapped pinned cache while the current iteration
+        computes (no host work per step); 'dma': one cudaMemcpyAsync per row on a copy stream, issued by the host."""
         self.unit, self.modules = unit, list(modules)
         self.host_resident = bool(host_resident)
+        if host_stage not in ('pull', 'dma'):
+            raise ValueError('host_stage must be "pull" or "dma"')
+        self.host_pull = self.host_resident and host_stage == 'pull'
+        self.host_dma = self.host_resident and host_stage == 'dma'
         self.dev = torch.device(device) if device is not None else cached_inps.device
         if self.dev.type != 'cuda':
             raise ops._lib.SsqError('reconstruction runs on CUDA only (no CPU fallback)')
@@ -117,6 +123,7 @@ class ReconEngine:
         self.idx_table_host = tab.cpu()
         self.host_step = 0
         self._copy_stream = None
+        self._loss_ring = None
         self.b_table = brecq_b_table(self.iters, warmup, b_range, round_loss=not act_quant).to(self.dev)
         lr_tab = cosine_lr_table(lr, self.iters) if act_quant else torch.full((max(self.iters, 1),), 1e-3)
         self.lr_table = lr_tab.to(self.dev)
@@ -130,6 +137,12 @@ class ReconEngine:
             if (self.host_resident and self.cached_grads is not None) else None
         self.loss_dev = torch.zeros(1, device=self.dev)
         self.reg_dev = torch.zeros(1, device=self.dev)
+        if self.host_pull:
+            self._pull_stream = torch.cuda.Stream(self.dev)
+            self._pull_bufs = [(src, torch.empty_like(cur), cur) for src, cur in
+                               ((self.cached_inps, self.cur_inp), (self.cached_outs, self.cur_out), (self.cached_grads, self.cur_grad))
+                               if src is not None]
+            self._pull_primed = False
         # ---- freeze everything that is not optimised (no wasted wgrad / bias-grad kernels) ---------------
         self._frozen = [(q, q.requires_grad) for q in unit.parameters()]
         for q, _ in self._frozen:
@@ -184,6 +197,14 @@ class ReconEngine:
                          self.lr_table, self.lr_live, max(self.iters, 1))
         if not self.host_resident:
             ops.gather_rows(self.cached_inps, self.idx_live, out=self.cur_inp)
+        elif self.host_pull:
+            # the rows pulled during the previous iteration become current (HBM->HBM); then fork: the SMs pull the
+            # next mini-batch (row *step_dev of the table, already advanced) over PCIe beside this iteration's kernels
+            main = torch.cuda.current_stream(self.dev)
+            for _src, stage, cur in self._pull_bufs:
+                cur.copy_(stage, non_blocking=True)
+            self._pull_stream.wait_stream(main)
+            self._pull(0)
         if not self.act_quant:
             self.table.forward(True, self.b_live, self.weight, self.reg_dev)
         with torch.enable_grad():
@@ -208,6 +229,21 @@ class ReconEngine:
         if self.multi_gpu:
             ssq_dist.all_reduce_sum_(self.gflat)                     # SUM, as link.allreduce at block_recon.py:100-102
         ops.adam_step(self.flat, self.gflat, self.exp_avg, self.exp_avg_sq, self.lr_live, self.step_dev)
+        if self.host_pull:
+            torch.cuda.current_stream(self.dev).wait_stream(self._pull_stream)      # join the prefetch branch
+
+    def _pull(self, lookahead: int):
+        for src, stage, _cur in self._pull_bufs:
+            ops.pull_rows_host(src, self.idx_table, self.step_dev, lookahead, self.idx_table.shape[0], stage,
+                               max_ctas=16, stream=self._pull_stream)
+
+    def _prime_pull(self):
+        """first mini-batch of a run: pull row *step_dev (not yet advanced) before the first iteration"""
+        main = torch.cuda.current_stream(self.dev)
+        self._pull_stream.wait_stream(main)
+        self._pull(0)
+        main.wait_stream(self._pull_stream)
+        self._pull_primed = True
 
     # ------------------------------------------------------------------------------------------ graph capture
     def _snapshot(self):
@@ -215,12 +251,14 @@ class ReconEngine:
 
     def _restore(self, snap):
         self.flat.copy_(snap[0]); self.exp_avg.copy_(snap[1]); self.exp_avg_sq.copy_(snap[2]); self.step_dev.copy_(snap[3])
+        if self.host_pull:
+            self._pull_primed = False                            # the staged rows belong to another step now
 
     def capture(self, warm: int = 3):
         """warm up eagerly on a side stream (allocations, cuDNN plans, workspaces), roll the state back,
         then capture one iteration"""
         snap = self._snapshot()
-        if self.host_resident:
+        if self.host_dma:
             hs = self.host_step
             self._stage_batch_from_host()
             torch.cuda.synchronize(self.dev)
@@ -228,6 +266,8 @@ class ReconEngine:
         side = torch.cuda.Stream(self.dev)
         side.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(side):
+            if self.host_pull:
+                self._prime_pull()
             for _ in range(warm):
                 self._iteration()
         torch.cuda.current_stream(self.dev).wait_stream(side)
@@ -252,9 +292,10 @@ class ReconEngine:
             ops.stage_rows_h2d(self.cached_grads, rows, self._stage_grad[slot], cs)
         self._slot_ready[slot].record(cs)
 
-    def _stage_batch_from_host(self):
-        """make the staged mini-batch current (device-to-device) and start the transfer of the next one, so the
-        PCIe copy of step i+1 overlaps the captured iteration of step i"""
+    def _stage_batch_from_host(self, prefetch: bool = True):
+        """make the staged mini-batch current (device-to-device); with prefetch=True also start the transfer of the
+        next one. step() defers the prefetch until the captured iteration has been launched, so the host time spent
+        issuing the row copies and the PCIe transfer of step i+1 both overlap the iteration of step i."""
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(self.dev)
             mk = lambda t: [torch.empty_like(t) for _ in range(2)]
@@ -274,6 +315,10 @@ class ReconEngine:
             self.cur_grad.copy_(self._stage_grad[slot], non_blocking=True)
         self._slot_free[slot].record(main)
         self.host_step += 1
+        if prefetch:
+            self._prefetch_next()
+
+    def _prefetch_next(self):
         self._issue_stage(self.host_step, self.host_step % 2)
 
     def h2d_bytes_per_step(self) -> int:
@@ -283,14 +328,37 @@ class ReconEngine:
         return 4 * n
 
     def step(self):
-        if self.host_resident:
-            self._stage_batch_from_host()
+        if self.host_dma:
+            self._stage_batch_from_host(prefetch=False)
+        elif self.host_pull and not self._pull_primed:
+            self._prime_pull()
         if self.graph is not None:
             self.graph.replay()
         else:
             before = ops.launch_count()
             self._iteration()
             self.launches_per_iter = ops.launch_count() - before
+        if self.host_dma:
+            self._prefetch_next()            # issued after the iteration's launch: host + PCIe time hide behind it
+        if self._loss_ring is not None:
+            k = self._loss_k
+            self._loss_ring[k].copy_(self.loss_dev, non_blocking=True)
+            self._loss_evt[k].record(torch.cuda.current_stream(self.dev))
+            self._loss_k = k ^ 1
+
+    def enable_loss_readback(self):
+        """device->host read of every iteration's loss through a 2-deep pinned ring: read_loss() returns the loss of
+        the iteration before the one just launched, so the read never drains the device queue"""
+        self._loss_ring = [torch.zeros(1).pin_memory() for _ in range(2)]
+        self._loss_evt = [torch.cuda.Event() for _ in range(2)]
+        self._loss_k, self._loss_seen = 0, [False, False]
+
+    def read_loss(self, latest: bool = False):
+        """loss of the previous step() (latest=False, lagged by one launch) or of the last one (latest=True, waits)"""
+        k = (self._loss_k ^ 1) if latest else self._loss_k
+        if not self._loss_evt[k].query():
+            self._loss_evt[k].synchronize()
+        return float(self._loss_ring[k])
 
     def run(self):
         if self.iters <= 0:

@@ -577,6 +577,24 @@ def stage_rows_h2d(host_src: torch.Tensor, rows: torch.Tensor, dev_dst: torch.Te
                                                per_sample, st), "ssq_stage_rows_h2d")
 
 
+def pull_rows_host(host_src: torch.Tensor, idx_table: torch.Tensor, step_dev: torch.Tensor, lookahead: int, n_steps: int,
+                   dev_dst: torch.Tensor, max_ctas: int = 32, stream=None):
+    """dev_dst[n] = host_src[idx_table[min(step_dev + lookahead, n_steps-1), n]], read by the SMs out of mapped pinned
+    host memory; idx_table / step_dev live on the device, so the call is capturable and needs no host work per step"""
+    if host_src.is_cuda or not host_src.is_pinned() or host_src.dtype != torch.float32:
+        raise _lib.SsqError("host_src must be a pinned fp32 host tensor")
+    _req(dev_dst, "dev_dst")
+    if not (idx_table.is_cuda and step_dev.is_cuda and idx_table.dtype == torch.int64 and step_dev.dtype == torch.int64):
+        raise _lib.SsqError("idx_table / step_dev must be int64 device tensors")
+    per_sample = host_src.numel() // host_src.shape[0]
+    batch = idx_table.shape[-1]
+    if dev_dst.numel() != batch * per_sample:
+        raise _lib.SsqError("dev_dst does not hold one mini-batch of rows")
+    st = (stream or torch.cuda.current_stream(dev_dst.device)).cuda_stream
+    _call("ssq_pull_rows_host", host_src.data_ptr(), idx_table.data_ptr(), step_dev.data_ptr(), int(lookahead), int(n_steps),
+          dev_dst.data_ptr(), batch, per_sample, int(max_ctas), st)
+
+
 def loop_advance(step_dev, idx_table, idx_live, b_table, b_live, lr_table, lr_live, n_steps: int):
     batch = 0 if idx_live is None else idx_live.numel()
     _call("ssq_loop_advance", step_dev.data_ptr(), _ptr(idx_table), _ptr(idx_live), batch, _ptr(b_table), _ptr(b_live),

@@ -99,6 +99,54 @@ def test_engine_matches_compat_autograd_loop(use_graph):
         assert (np.sign(a) == np.sign(b)).mean() > 0.999      # hard-rounding decisions agree
 
 
+def test_host_resident_engine_is_bit_identical_and_reads_every_loss(monkeypatch):
+    """keep_gpu=False mode (quant/data_utils.py:34-36): pinned host cache, the mini-batch rows cross PCIe every step —
+    pulled by an in-graph kernel from mapped host memory ('pull') or by per-row cudaMemcpyAsync ('dma'). Same bytes
+    into the same kernels => with deterministic cuDNN algorithms (the reference's setting, common.py:84-85) the
+    trajectory must be bit-identical to the HBM-resident engine; the pinned loss ring must hand back every
+    iteration's loss, lagged by exactly one launch."""
+    monkeypatch.setattr(torch.backends.cudnn, "deterministic", True)
+    monkeypatch.setattr(torch.backends.cudnn, "benchmark", False)
+    from shiftedscalequantization_b200.engine import ReconEngine, index_table
+    from shiftedscalequantization_b200.quant.adaptive_rounding import AdaRoundQuantizer
+    from shiftedscalequantization_b200.quant.data_utils import save_inp_oup_data
+    iters, bs = 20, 16
+    out = {}
+    for host in (False, 'pull', 'dma'):
+        Q, qnn, cali = build_qnn()
+        block = qnn.model.layer2[0]
+        qnn.set_quant_state(False, False); block.set_quant_state(True, False)
+        mods = [m for m in block.modules() if isinstance(m, Q.QuantModule)]
+        for m in mods:
+            m.weight_quantizer = AdaRoundQuantizer(uaq=m.weight_quantizer, round_mode='learned_hard_sigmoid',
+                                                   weight_tensor=m.org_weight.data)
+            m.weight_quantizer.soft_targets = True
+        inps, outs = save_inp_oup_data(qnn, block, cali, True, False, bs)
+        torch.manual_seed(7)
+        tab = index_table(inps.shape[0], bs, iters)
+        eng = ReconEngine(block, mods, inps, outs, None, act_quant=False, iters=iters, weight=0.01, b_range=(20, 2),
+                          warmup=0.2, p=2.0, batch_size=bs, use_graph=True, idx_table=tab, verbose=False,
+                          host_resident=bool(host), host_stage=host or 'pull', device=torch.device('cuda'))
+        if host:
+            assert eng.cached_inps.is_pinned() and not eng.cached_inps.is_cuda
+            assert eng.h2d_bytes_per_step() == 4 * (inps[:bs].numel() + outs[:bs].numel())
+        eng.capture()
+        eng.enable_loss_readback()
+        direct, lagged = [], []
+        for i in range(iters):
+            eng.step()
+            lagged.append(eng.read_loss())                  # loss of iteration i-1 (0.0 before the first)
+            direct.append(float(eng.loss_dev))
+        last = eng.read_loss(latest=True)
+        eng.close()
+        assert lagged[0] == 0.0 and lagged[1:] == direct[:-1] and last == direct[-1]
+        out[host] = ([m.weight_quantizer.alpha.detach().cpu().numpy().copy() for m in mods], direct)
+    for mode in ('pull', 'dma'):
+        for a, b in zip(out[False][0], out[mode][0]):
+            assert_exact(b, a, f"alpha, host-resident ({mode}) vs HBM-resident cache")
+        assert out[False][1] == out[mode][1], mode
+
+
 def test_block_reconstruction_weight_then_act_phase():
     Q, qnn, cali = build_qnn()
     dev = torch.device('cuda')
