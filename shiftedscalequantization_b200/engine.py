@@ -385,3 +385,176 @@ class ReconEngine:
             for m in self.modules:
                 m.weight_quantizer.alpha.requires_grad_(True)
         self.graph = None
+
+
+class AutogradReconEngine:
+    """The same captured-iteration design for the loops whose forward is NOT the plain AdaRound multi-tensor launch:
+    the shifted-scale loops (reference: quant/layer_recon_shiftedScale.py:52-95,282-318,
+    quant/layer_recon_fused_shiftedScale.py:84-110), their activation phases, and reconstruction with the output-channel
+    affine gamma^z / varphi^z trainable (README `--bias_cal`).
+
+    The unit's forward runs through the quantisers' own autograd functions (K1a/K1b/K1c kernels); what changes against
+    the eager loop is everything around it: every trainable tensor is a view of ONE flat buffer (`slots` = the
+    (owner, attribute) pairs holding the nn.Parameters), the index / temperature / lr schedules are device tables read
+    through device step counters, the regulariser gates are device scalars (b <= 0 = off), the loss is the fused
+    K3 kernel reading its targets in place, Adam is one fused launch, and the whole iteration replays as one CUDA graph —
+    no host synchronisation per iteration (upstream: two .item() calls, a CPU randperm + index H2D, ~20 optimizer launches).
+
+    reg_fn(live) -> sequence of 0-dim tensors built from `live` (the device temperature scalars, one per entry of
+    `b_tables`); their sum is the rounding / group regulariser of the loss.
+    """
+
+    def __init__(self, unit: nn.Module, slots, cached_inps: torch.Tensor, cached_outs: torch.Tensor, *, iters: int,
+                 batch_size: int = 32, p: float = 2.0, lr_table: torch.Tensor, b_tables: Sequence[torch.Tensor] = (),
+                 reg_fn=None, multi_gpu: bool = False, idx_table: Optional[torch.Tensor] = None,
+                 use_graph: Optional[bool] = None, adam_betas=(0.9, 0.999), adam_eps: float = 1e-8):
+        self.unit, self.iters, self.p = unit, int(iters), float(p)
+        self.dev = cached_inps.device
+        if self.dev.type != 'cuda':
+            raise ops._lib.SsqError('reconstruction runs on CUDA only (no CPU fallback)')
+        self.cached_inps, self.cached_outs = cached_inps.contiguous(), cached_outs.contiguous()
+        n = self.cached_inps.shape[0]
+        self.batch = min(int(batch_size), n)
+        self.multi_gpu = bool(multi_gpu) and ssq_dist.world_size() > 1
+        self.use_graph = (self.iters >= 8) if use_graph is None else bool(use_graph)
+        self.reg_fn, self.betas, self.eps = reg_fn, adam_betas, adam_eps
+        self.n_steps = max(self.iters, 1)
+        tab = idx_table if idx_table is not None else index_table(n, self.batch, self.iters)
+        self.idx_table = tab.to(self.dev)
+        self.lr_table = lr_table.to(self.dev, torch.float32).contiguous()
+        self.b_tables = [t.to(self.dev, torch.float32).contiguous() for t in b_tables]
+        for t in [self.lr_table] + self.b_tables:
+            if t.numel() < self.n_steps:
+                raise ValueError('schedule table shorter than the loop')
+        # one device step counter per temperature table: ssq_loop_advance copies row `step` and increments
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self.extra_steps = [torch.zeros(1, dtype=torch.int64, device=self.dev) for _ in self.b_tables[1:]]
+        self.idx_live = torch.zeros(self.batch, dtype=torch.int64, device=self.dev)
+        self.lr_live = torch.zeros(1, device=self.dev)
+        self.live = [torch.zeros(1, device=self.dev) for _ in self.b_tables]
+        self.cur_inp = torch.empty((self.batch,) + tuple(self.cached_inps.shape[1:]), device=self.dev)
+        self.loss_dev = torch.zeros(1, device=self.dev)
+        self.reg_vals: List[torch.Tensor] = []
+        # ---- flat parameter buffer; the API-visible nn.Parameters become views of it.
+        # A tensor listed k times is stepped k times per iteration with its own step count, which is what
+        # torch.optim.Adam's per-tensor loop does with a duplicated entry (upstream lists every QuantModule's activation
+        # step size twice in the act phase: layer_recon_shiftedScale.py:24-33 walks named_modules() and meets the
+        # module's act_quantizer again as a UniformAffineQuantizer).
+        self.slots = list(slots)
+        uniq, mult = [], {}
+        for owner, attr in self.slots:
+            old = getattr(owner, attr)
+            if id(old) in mult:
+                mult[id(old)] += 1
+            else:
+                mult[id(old)] = 1
+                uniq.append((owner, attr, old))
+        uniq.sort(key=lambda e: mult[id(e[2])] > 1)              # singles first (stable), repeated ones behind them
+        sizes = [_pad4(old.numel()) for _o, _a, old in uniq]
+        self.flat = torch.zeros(sum(sizes), device=self.dev)
+        self.gflat = torch.zeros_like(self.flat)
+        self.params, self.gviews, self.repeats, off = [], [], [], 0
+        self.n_single = 0
+        for (owner, attr, old), sz in zip(uniq, sizes):
+            k = old.numel()
+            view = self.flat[off:off + k].view(old.shape)
+            view.copy_(old.detach())
+            par = nn.Parameter(view, requires_grad=True)
+            for o2, a2 in self.slots:                            # every slot that held this tensor now holds the view
+                if getattr(o2, a2) is old:
+                    setattr(o2, a2, par)
+            self.params.append(par)
+            self.gviews.append(self.gflat[off:off + k].view(old.shape))
+            if mult[id(old)] > 1:
+                self.repeats.append((off, sz, mult[id(old)], torch.zeros(1, dtype=torch.int64, device=self.dev)))
+            else:
+                self.n_single = off + sz
+            off += sz
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        mine = {id(q) for q in self.params}
+        self._frozen = [(q, q.requires_grad) for q in unit.parameters() if id(q) not in mine]
+        for q, _ in self._frozen:
+            q.requires_grad_(False)
+        self.graph = None
+        self.launches_per_iter = 0
+
+    # ------------------------------------------------------------------------------------------ one iteration
+    def _iteration(self):
+        ops.loop_advance(self.step_dev, self.idx_table, self.idx_live, self.b_tables[0] if self.b_tables else None,
+                         self.live[0] if self.live else None, self.lr_table, self.lr_live, self.n_steps)
+        for st, tab, lv in zip(self.extra_steps, self.b_tables[1:], self.live[1:]):
+            ops.loop_advance(st, None, None, tab, lv, None, None, self.n_steps)
+        ops.gather_rows(self.cached_inps, self.idx_live, out=self.cur_inp)
+        with torch.enable_grad():
+            out = self.unit(self.cur_inp)
+            regs = list(self.reg_fn(self.live)) if self.reg_fn is not None else []
+        loss, dpred = ops.recon_loss(out.detach(), self.cached_outs, self.p, 'mse', tgt_index=self.idx_live)
+        self.loss_dev, self.reg_vals = loss, [r.detach() for r in regs]
+        heads, seeds = [], []
+        if out.requires_grad:
+            heads.append(out); seeds.append(dpred.view_as(out))
+        for r in regs:
+            if r.requires_grad:
+                heads.append(r); seeds.append(torch.ones_like(r))
+        grads = torch.autograd.grad(heads, self.params, seeds, allow_unused=True) if heads else [None] * len(self.params)
+        for view, g in zip(self.gviews, grads):
+            if g is None:
+                view.zero_()
+            else:
+                view.copy_(g.view_as(view))
+        if self.multi_gpu:
+            ssq_dist.all_reduce_sum_(self.gflat)
+        n1 = self.n_single
+        ops.adam_step(self.flat[:n1], self.gflat[:n1], self.exp_avg[:n1], self.exp_avg_sq[:n1], self.lr_live, self.step_dev,
+                      self.betas, self.eps)
+        for off, sz, k, ctr in self.repeats:
+            for _ in range(k):
+                ops.loop_advance(ctr, None, None, None, None, None, None, 1 << 62)
+                ops.adam_step(self.flat[off:off + sz], self.gflat[off:off + sz], self.exp_avg[off:off + sz],
+                              self.exp_avg_sq[off:off + sz], self.lr_live, ctr, self.betas, self.eps)
+
+    def _state(self):
+        return [self.flat, self.exp_avg, self.exp_avg_sq, self.step_dev] + self.extra_steps + [r[3] for r in self.repeats]
+
+    def capture(self, warm: int = 3):
+        snap = [t.clone() for t in self._state()]
+        restore = lambda: [t.copy_(s) for t, s in zip(self._state(), snap)]
+        side = torch.cuda.Stream(self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            for _ in range(warm):
+                self._iteration()
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        restore()
+        before = ops.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._iteration()
+        self.launches_per_iter = ops.launch_count() - before
+        restore()
+
+    def step(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            before = ops.launch_count()
+            self._iteration()
+            self.launches_per_iter = ops.launch_count() - before
+
+    def run(self, every: int = 500, on_report=None):
+        """runs the loop; on_report(i) is called after iteration i whenever i % every == 0 (the reference's read-out
+        cadence) — the only points where the host looks at device values"""
+        if self.iters <= 0:
+            return
+        if self.use_graph and self.graph is None:
+            self.capture()
+        for i in range(self.iters):
+            self.step()
+            if on_report is not None and i % every == 0:
+                on_report(i)
+
+    def close(self):
+        for q, flag in self._frozen:
+            q.requires_grad_(flag)
+        self.graph = None

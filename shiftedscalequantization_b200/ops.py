@@ -39,12 +39,17 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+_ws_retired = []
+
+
 def workspace(device: torch.device, nbytes: int, tag: str = "default") -> torch.Tensor:
     """Zero-initialised scratch for the deterministic reductions (tickets reset themselves).
     One buffer per (device, tag); callers on the same stream may share it."""
     key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
+        if buf is not None:
+            _ws_retired.append(buf)      # a captured graph may still point at it: never hand it back to the allocator
         buf = torch.zeros(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
         _ws_cache[key] = buf
     return buf
@@ -552,6 +557,8 @@ class ChanAffine(torch.autograd.Function):
 
 
 def adam_step(param, grad, exp_avg, exp_avg_sq, lr_dev, step_dev, betas=(0.9, 0.999), eps=1e-8):
+    if param.numel() == 0:
+        return
     _call("ssq_adam_step", param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel(),
           lr_dev.data_ptr(), float(betas[0]), float(betas[1]), float(eps), step_dev.data_ptr(), _stream(param))
 

@@ -12,7 +12,8 @@ import torch
 
 from .. import ops
 from .channelQuantAct import ChannelQuantAct
-from .layer_recon_shiftedScale import _LazyScalars, _probe, _run_loop
+from . import layer_recon_shiftedScale as _ls
+from .layer_recon_shiftedScale import _LazyScalars, _probe, _run_loop, _run_captured, shifted_b_table
 from .quant_block import BaseQuantBlock
 from .quant_layer import QuantModule, UniformAffineQuantizer, lp_loss
 
@@ -90,6 +91,29 @@ class FusedScaleLossFunction(_LazyScalars):
             float(self.total_loss), float(self.rec_loss), self.round_loss_val, self.b)
 
 
+def _fused_captured(unit, loss_func, quantizers, lr, cached_inp, cached_out, iters, batch_size, describe):
+    """captured-graph version of the loop at upstream :84-110: temperature b for h(beta), b2 (3/4-length schedule) for the
+    group probabilities, both gated off during warm-up through their device tables"""
+    lr_table = torch.full((max(iters, 1),), float(lr))
+    b_tables = [shifted_b_table(loss_func, iters, loss_func.temp_decay), shifted_b_table(loss_func, iters, loss_func.temp_decay_shift)]
+    lmdaR, lmdaS = loss_func.lmdaR, loss_func.lmdaS
+
+    def reg_fn(live):
+        if loss_func.round_loss != 'relaxation':
+            return []
+        return [sum(ops.RoundReg.apply(q.beta, live[0], lmdaR) for q in quantizers),
+                sum(ops.ShiftProbsReg.apply(q.alpha, 1, live[1], lmdaS) for q in quantizers)]
+
+    def on_regs(vals):
+        if vals:
+            loss_func._r, loss_func._s = vals[0].reshape(()), vals[1].reshape(())
+
+    slots = [(q, 'alpha') for q in quantizers]
+    start_loss, _eng = _run_captured(unit, loss_func, slots, lr_table, b_tables, reg_fn, cached_inp, cached_out, iters,
+                                     batch_size, describe, on_regs)
+    return start_loss
+
+
 def block_recon_fused_shiftedScale(block: BaseQuantBlock, iters: int = 20000, lmda: list = [1., 1.], model=None,
                                    test_loader=None, act=False, adaround=False, useShiftedScale=True):
     block.train()
@@ -111,14 +135,18 @@ def block_recon_fused_shiftedScale(block: BaseQuantBlock, iters: int = 20000, lm
             opt_params.append(q.alpha)
             quantizers.append(q)
             q.opt_mode = 'adaShift'
-    optimizer = torch.optim.Adam(opt_params, lr=lr)
     print("number of elements in opt_params: {}".format(sum(q.numel() for q in opt_params)))
     loss_func = FusedScaleLossFunction(block, quantizers, round_loss='none' if act else 'relaxation', lmda=lmda,
                                        max_count=iters, b_range=b_range, decay_start=0, warmup=warmup, p=p)
     cached_inp = torch.cat(block.cached_inp_features).to(device)
     cached_out = torch.cat(block.cached_out_features).to(device)
     describe = lambda s0, lf: f"{s0:.6f} -> {lf.rec_loss:.6f} {lf.round_loss_val} "
-    start_loss = _run_loop(block, loss_func, optimizer, None, cached_inp, cached_out, iters, batch_size, describe)
+    if _ls.USE_CAPTURED_LOOP and iters >= 8 and opt_params:
+        start_loss = _fused_captured(block, loss_func, quantizers, lr, cached_inp, cached_out, iters, batch_size, describe)
+        optimizer = torch.optim.Adam([q.alpha for q in quantizers], lr=lr)
+    else:
+        optimizer = torch.optim.Adam(opt_params, lr=lr)
+        start_loss = _run_loop(block, loss_func, optimizer, None, cached_inp, cached_out, iters, batch_size, describe)
     out = [_probe(block, loss_func, optimizer, cached_inp, cached_out, batch_size)]
     print(f"Soft Round : {start_loss:.6f} -> {loss_func.rec_loss:.6f} {loss_func.round_loss_val}")
     if not act:
@@ -146,14 +174,18 @@ def layer_recon_fused_shiftedScale(layer: QuantModule, iters: int = 20000, lmda:
     q.init_v_beta(x=layer.org_weight.data.clone().detach())
     opt_params = [q.alpha]
     q.opt_mode = 'adaShift'
-    optimizer = torch.optim.Adam(opt_params)
     loss_func = FusedScaleLossFunction(layer, [q], round_loss='none' if act else 'relaxation', lmda=lmda, max_count=iters,
                                        b_range=b_range, decay_start=0, warmup=warmup, p=p, adaround=adaround)
     cached_inp = torch.cat(layer.cached_inp_features).to(device)
     cached_out = torch.cat(layer.cached_out_features).to(device)
     print("number of elements in opt_params: {}".format(sum(t.numel() for t in opt_params)))
     describe = lambda s0, lf: f"{s0:.6f} -> {lf.rec_loss:.6f} {lf.round_loss_val} "
-    start_loss = _run_loop(layer, loss_func, optimizer, None, cached_inp, cached_out, iters, batch_size, describe)
+    if _ls.USE_CAPTURED_LOOP and iters >= 8:
+        start_loss = _fused_captured(layer, loss_func, [q], 1e-3, cached_inp, cached_out, iters, batch_size, describe)
+        optimizer = torch.optim.Adam([q.alpha])
+    else:
+        optimizer = torch.optim.Adam(opt_params)
+        start_loss = _run_loop(layer, loss_func, optimizer, None, cached_inp, cached_out, iters, batch_size, describe)
     out = [_probe(layer, loss_func, optimizer, cached_inp, cached_out, batch_size)]
     print(f"Soft Round : {start_loss:.6f} -> {loss_func.rec_loss:.6f} {loss_func.round_loss_val}")
     if adaround:

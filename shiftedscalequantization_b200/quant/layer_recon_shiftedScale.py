@@ -106,8 +106,8 @@ class ScaleLossFunction(ScaleLossBlockFunction):
 
 
 def _prepare_weight_params(modules, adaround):
-    """quantiser state + the tensors Adam steps (upstream :37-50 / :270-279)"""
-    opt_params = []
+    """quantiser state + the (owner, attribute) slots of the tensors Adam steps (upstream :37-50 / :270-279)"""
+    slots = []
     for m in modules:
         q = m.weight_quantizer
         w = m.org_weight.data
@@ -116,23 +116,63 @@ def _prepare_weight_params(modules, adaround):
                 q.update_delta()
             q.init_beta(x=w.clone().detach())
             q.opt_mode = 'adaround'
-            opt_params.append(q.beta)
+            slots.append((q, 'beta'))
         else:
             q.init_v(x=w.clone().detach())
-            opt_params.append(q.alpha)
-    return opt_params
+            slots.append((q, 'alpha'))
+    return slots
 
 
 def _act_delta_params(unit):
-    params = []
+    """upstream :24-33. named_modules() yields every QuantModule and then its act_quantizer again as a
+    UniformAffineQuantizer, so those step sizes are listed — and stepped by Adam — twice per iteration; kept."""
+    slots = []
     for _n, m in unit.named_modules():
         if isinstance(m, QuantModule):
             if not m.act_quantizer.disable_act_quant:
-                params.append(m.act_quantizer.delta)
+                slots.append((m.act_quantizer, 'delta'))
         elif isinstance(m, UniformAffineQuantizer):
             if not m.disable_act_quant:
-                params.append(m.delta)
-    return params
+                slots.append((m, 'delta'))
+    return slots
+
+
+USE_CAPTURED_LOOP = True      # False: the eager autograd loop below (kept as the behavioural cross-check)
+
+
+def _run_captured(unit, loss_func, slots, lr_table, b_tables, reg_fn, cached_inp, cached_out, iters, batch_size, describe,
+                  on_regs):
+    """the loop body of upstream :52-95 as one replayed CUDA graph per iteration (engine.AutogradReconEngine): same
+    index stream (torch.randperm(N)[:B] per iteration), same temperature/lr per iteration, same kernels as the eager
+    path; the host reads device scalars only at the i % 500 == 0 read-outs."""
+    from ..engine import AutogradReconEngine
+    from .. import dist as ssq_dist
+    eng = AutogradReconEngine(unit, slots, cached_inp, cached_out, iters=iters, batch_size=batch_size, p=loss_func.p,
+                              lr_table=lr_table, b_tables=b_tables, reg_fn=reg_fn, multi_gpu=ssq_dist.world_size() > 1)
+    state = {'start': 0.0}
+    bar = tqdm(total=iters, desc='', dynamic_ncols=True)
+
+    def sync_loss_object():
+        loss_func._rec = eng.loss_dev.detach().reshape(()).clone()      # clones: the originals live in the graph's pool
+        vals = [v.clone() for v in eng.reg_vals]
+        on_regs(vals)
+        reg_sum = sum(vals) if vals else 0.0
+        loss_func._total = loss_func._rec + reg_sum
+        loss_func.b = float(eng.live[0]) if eng.live else 0
+
+    def report(i):
+        sync_loss_object()
+        state['start'] = max(state['start'], loss_func.rec_loss)
+        bar.update(min(500, iters - i))
+        bar.set_description(describe(state['start'], loss_func))
+
+    eng.run(every=500, on_report=report)
+    if iters > 0:
+        sync_loss_object()
+    loss_func.count += iters
+    bar.close()
+    eng.close()
+    return state['start'], eng
 
 
 def _run_loop(unit, loss_func, optimizer, scheduler, cached_inp, cached_out, iters, batch_size, describe):
@@ -160,23 +200,59 @@ def _probe(unit, loss_func, optimizer, cached_inp, cached_out, batch_size):
     return loss_func.rec_loss
 
 
+def shifted_b_table(loss_func, iters, temp_decay=None, gate_only=False):
+    """temperature seen by iteration i of the shifted losses: count is used BEFORE its increment (upstream :378,:407);
+    0 while count < loss_start or round_loss == 'none' = regulariser off. gate_only: 1.0 where on (entropy has no b)."""
+    tab = torch.zeros(max(iters, 1), dtype=torch.float32)
+    if loss_func.round_loss == 'none':
+        return tab
+    decay = temp_decay or loss_func.temp_decay
+    for i in range(iters):
+        if i >= loss_func.loss_start:
+            tab[i] = 1.0 if gate_only else float(decay(i))
+    return tab
+
+
 def _shifted_recon(unit, modules, iters, lmda, model, act, adaround, loss_cls, train_target, device):
+    from ..engine import cosine_lr_table
     warmup, p, b_range, lr, batch_size = 0.2, 2.0, (20, 2), 4e-4, 32
     scheduler = None
     if act:
-        opt_params = _act_delta_params(unit)
-        optimizer = torch.optim.Adam(opt_params, lr=lr)
-        scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(optimizer, T_max=iters, eta_min=0.)
+        slots = _act_delta_params(unit)
     else:
-        opt_params = _prepare_weight_params(modules, adaround)
-        optimizer = torch.optim.Adam(opt_params)
-        print("number of elements in opt_params: {}".format(sum(q.numel() for q in opt_params)))
+        slots = _prepare_weight_params(modules, adaround)
+        print("number of elements in opt_params: {}".format(sum(getattr(o, a).numel() for o, a in slots)))
     loss_func = loss_cls(unit, round_loss='none' if act else 'relaxation', lmda=lmda, max_count=iters, b_range=b_range,
                          decay_start=0, warmup=warmup, p=p, adaround=adaround)
     cached_inp = torch.cat(unit.cached_inp_features).to(device)
     cached_out = torch.cat(unit.cached_out_features).to(device)
     describe = lambda s0, lf: f"{s0:.6f} -> {lf.rec_loss:.6f} {lf.round_loss_val:.3f} "
-    start_loss = _run_loop(unit, loss_func, optimizer, scheduler, cached_inp, cached_out, iters, batch_size, describe)
+    if USE_CAPTURED_LOOP and iters >= 8:
+        lr_table = cosine_lr_table(lr, iters) if act else torch.full((max(iters, 1),), 1e-3)
+        b_tables = [shifted_b_table(loss_func, iters, gate_only=not adaround)]
+        quantizers = loss_func._quantizers() if not act else []
+
+        def reg_fn(live):
+            if act or not quantizers:
+                return []
+            if adaround:
+                return [sum(ops.RoundReg.apply(q.beta, live[0], lmda) for q in quantizers)]
+            return [sum(ops.ShiftProbsReg.apply(q.alpha, 0, live[0], lmda) for q in quantizers)]
+
+        def on_regs(vals):
+            loss_func._round = vals[0].reshape(()) if vals else 0
+
+        start_loss, _eng = _run_captured(unit, loss_func, slots, lr_table, b_tables, reg_fn, cached_inp, cached_out,
+                                         iters, batch_size, describe, on_regs)
+        optimizer = torch.optim.Adam([getattr(o, a) for o, a in slots], lr=lr if act else 1e-3)
+    else:
+        opt_params = [getattr(o, a) for o, a in slots]
+        # foreach=False: the per-tensor loop, which is how the reference's verified torch 1.11 (and the CPU path) steps a
+        # duplicated entry — two sequential updates
+        optimizer = torch.optim.Adam(opt_params, lr=lr, foreach=False) if act else torch.optim.Adam(opt_params)
+        if act:
+            scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(optimizer, T_max=iters, eta_min=0.)
+        start_loss = _run_loop(unit, loss_func, optimizer, scheduler, cached_inp, cached_out, iters, batch_size, describe)
     out = [_probe(unit, loss_func, optimizer, cached_inp, cached_out, batch_size)]
     print(f"Soft Round : {start_loss:.6f} -> {loss_func.rec_loss:.6f} {loss_func.round_loss_val:.3f}")
     return out, loss_func, optimizer, cached_inp, cached_out, start_loss, batch_size

@@ -208,7 +208,7 @@ rows = torch.arange(9.).reshape(9, 1)
 lo, hi = D.shard_range(9)
 full = D.all_gather_rows(rows[lo:hi] * 2, 9)
 assert torch.equal(full, rows * 2)
-print("rank", rk, "ok")
+sys.stdout.write(f"rank {rk} ok\n"); sys.stdout.flush()      # one write per rank: the two ranks share the pipe
 '''
 
 

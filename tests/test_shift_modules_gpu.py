@@ -224,3 +224,109 @@ def test_channel_shift_loss_flow_resnet18():
     assert np.isfinite([soft, hard]).all()
     blk = qnn.model.layer1[0]
     assert blk.conv1.weight_quantizer.opt_mode == 'adaShift' and blk.conv1.weight_quantizer.hard_targets
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The shifted-scale LOOPS against the real reference's loops (tests/golden/make_golden_shift_loops.py ran
+# quant/layer_recon_shiftedScale.py:12-124 and quant/layer_recon_fused_shiftedScale.py:23-141 on the CPU): same seeded
+# network, the reference's own cached features, the same torch.randperm stream. cuDNN and CPU convolutions differ in the
+# last bits and Adam normalises gradient magnitudes away, so trained tensors are compared to 2e-3 absolute plus agreement
+# of the hard decisions; losses to 2e-3 relative.
+def _golden_shift_setup(tag_feats="A"):
+    from shiftedscalequantization_b200 import quant as Q, zoo
+    from shiftedscalequantization_b200.quant.channelQuant import ChannelQuant
+    g = golden("shift_loops")
+    torch.manual_seed(1005)
+    cnn = zoo.resnet18(num_classes=10).cuda().eval()
+    qnn = Q.QuantModel(cnn, {'n_bits': 2, 'channel_wise': True, 'scale_method': 'max'},
+                       {'n_bits': 4, 'channel_wise': False, 'scale_method': 'mse', 'leaf_param': True}).cuda().eval()
+    qnn.set_first_last_layer_to_8bit()
+    cali = torch.from_numpy(g["cali"])
+    qnn.set_quant_state(True, False)
+    with torch.no_grad():
+        qnn(cali[:32].cuda())
+    block = qnn.model.layer2[0]
+    for m in block.modules():
+        if isinstance(m, Q.QuantModule):
+            m.weight_quantizer = ChannelQuant(1.0, uaq=m.weight_quantizer, weight_tensor=m.org_weight.data,
+                                              shiftTarget=[float(s) for s in g["shifts"]], name=m.pathName)
+    block.cached_inp_features = [torch.from_numpy(g["A.inp"])]
+    block.cached_out_features = [torch.from_numpy(g["A.out"])]
+    block.set_quant_state(True, False)
+    mods = [(n, m) for n, m in block.named_modules() if isinstance(m, Q.QuantModule)]
+    return Q, qnn, block, mods, cali, g, int(g["iters"])
+
+
+def _close_params(ours, ref, what, atol=2e-3, lr=1e-3, steps=20):
+    """>= 99.9 % of the entries within atol; no entry further away than Adam can carry it (2 * lr * steps: an entry whose
+    tiny gradient changes sign between the cuDNN and the CPU convolution walks the other way for a few steps)"""
+    ours, ref = host(ours), np.asarray(ref)
+    assert ours.shape == ref.shape, what
+    err = np.abs(ours - ref)
+    frac = (err <= atol).mean()
+    assert frac >= 0.999, f"{what}: only {frac:.5f} of the entries within {atol}"
+    assert err.max() <= 2 * lr * steps, f"{what}: max abs diff {err.max():.3e}"
+
+
+@pytest.mark.parametrize("captured", [True, False])
+def test_shift_then_adaround_loops_match_reference(captured, monkeypatch):
+    from shiftedscalequantization_b200.quant import layer_recon_shiftedScale as LS
+    monkeypatch.setattr(LS, "USE_CAPTURED_LOOP", captured)
+    Q, qnn, block, mods, cali, g, iters = _golden_shift_setup()
+    torch.manual_seed(91)
+    soft, hard = LS.block_recon_shiftedScale(block, iters=iters, lmda=0.01, model=qnn)
+    assert_close(np.array([soft, hard]), g["A.shift.losses"], rtol=2e-3, what="shift [soft, hard] loss vs reference")
+    for n, m in mods:
+        _close_params(m.weight_quantizer.alpha, g[f"A.shift.{n}.alpha"], f"{n}.alpha after the shift loop")
+        agree = (host(m.weight_quantizer.alpha).argmax(-1) == g[f"A.shift.{n}.alpha"].argmax(-1)).mean()
+        assert agree > 0.99, (n, agree)
+    with torch.no_grad():
+        out = host(block(torch.from_numpy(g["A.inp"][:8]).cuda()))
+    assert np.abs(out - g["A.shift.hard_out"]).max() <= 2e-3 * np.abs(g["A.shift.hard_out"]).max()
+    torch.manual_seed(92)
+    soft, hard = LS.block_recon_shiftedScale(block, iters=iters, lmda=0.01, model=qnn, adaround=True)
+    assert_close(np.array([soft, hard]), g["A.ada.losses"], rtol=2e-3, what="adaround-on-shift [soft, hard] loss vs reference")
+    for n, m in mods:
+        assert_exact(host(m.weight_quantizer.delta), g[f"A.ada.{n}.delta"], f"{n}.delta after update_delta")
+        _close_params(m.weight_quantizer.beta, g[f"A.ada.{n}.beta"], f"{n}.beta after the AdaRound loop")
+        assert (np.sign(host(m.weight_quantizer.beta)) == np.sign(g[f"A.ada.{n}.beta"])).mean() > 0.9995
+
+
+@pytest.mark.parametrize("captured", [True, False])
+def test_fused_shift_loop_matches_reference(captured, monkeypatch):
+    from shiftedscalequantization_b200.quant import layer_recon_shiftedScale as LS
+    from shiftedscalequantization_b200.quant.layer_recon_fused_shiftedScale import block_recon_fused_shiftedScale
+    monkeypatch.setattr(LS, "USE_CAPTURED_LOOP", captured)
+    Q, qnn, block, mods, cali, g, iters = _golden_shift_setup()
+    torch.manual_seed(93)
+    soft, hard = block_recon_fused_shiftedScale(block, iters=iters, lmda=[0.01, 0.02], model=qnn)
+    assert_close(np.array([soft, hard]), g["B.fused.losses"], rtol=2e-3, what="fused [soft, hard] loss vs reference")
+    for n, m in mods:
+        _close_params(m.weight_quantizer.alpha, g[f"B.fused.{n}.alpha"], f"{n}.alpha after the fused loop")
+        assert_close(host(m.weight_quantizer.beta), g[f"B.fused.{n}.beta"], rtol=1e-5, what=f"{n}.beta (initialised, never stepped)")
+
+
+@pytest.mark.parametrize("captured", [True, False])
+def test_shift_act_loop_matches_reference(captured, monkeypatch):
+    """act=True: LSQ step sizes through the shifted loop; the module's own step size is listed twice upstream and
+    therefore Adam-stepped twice per iteration (layer_recon_shiftedScale.py:24-33) — reproduced"""
+    from shiftedscalequantization_b200.quant import layer_recon_shiftedScale as LS
+    monkeypatch.setattr(LS, "USE_CAPTURED_LOOP", captured)
+    Q, qnn, block, mods, cali, g, iters = _golden_shift_setup()
+    torch.manual_seed(94)
+    LS.block_recon_shiftedScale(block, iters=iters, lmda=0.01, model=qnn)
+    qnn.set_quant_state(True, True)
+    with torch.no_grad():
+        qnn(cali[:32].cuda())
+    block.set_quant_state(True, True)
+    deltas = lambda: np.array([float(block.act_quantizer.delta.detach())] +
+                              [float(m.act_quantizer.delta.detach()) for _n, m in mods
+                               if not m.act_quantizer.disable_act_quant and m.act_quantizer.delta is not None])
+    assert_close(deltas(), g["C.delta0"], rtol=2e-3, what="activation step sizes after init")
+    torch.manual_seed(95)
+    soft, hard = LS.block_recon_shiftedScale(block, iters=iters, lmda=0.01, model=qnn, act=True)
+    assert_close(np.array([soft, hard]), g["C.act.losses"], rtol=5e-3, what="act-phase [soft, hard] loss vs reference")
+    d1 = deltas()
+    assert_close(d1, g["C.delta1"], rtol=2e-3, what="activation step sizes after the loop")
+    moved_ref = g["C.delta1"] - g["C.delta0"]
+    assert_close(d1 - g["C.delta0"], moved_ref, rtol=0.05, what="step-size movement (double-stepped entry moves twice as far)")
