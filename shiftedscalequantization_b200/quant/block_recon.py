@@ -8,7 +8,7 @@ three fused kernels — reconstruction loss, rounding regulariser — under auto
 import torch
 
 from .. import ops
-from ..engine import ReconEngine, temperature
+from ..engine import AutogradReconEngine, ReconEngine, brecq_b_table, temperature
 from .adaptive_rounding import AdaRoundQuantizer
 from .data_utils import save_grad_data, save_inp_oup_data
 from .quant_block import BaseQuantBlock
@@ -20,8 +20,39 @@ def _quant_modules(unit):
     return [m for _n, m in unit.named_modules() if isinstance(m, QuantModule)]
 
 
+def _run_with_output_affine(unit, modules, cached_inps, cached_outs, *, iters, weight, b_range, warmup, p, batch_size, multi_gpu):
+    """README `--bias_cal`: the output-channel scale gamma^z (alpha_out) and offset varphi^z (beta_out) of every layer in
+    the unit are learned together with the AdaRound alphas (upstream's commented `opt_params +=` lines,
+    quant/layer_recon_fused_shiftedScale.py:67-68; forward at quant/quant_layer.py:258-259), same Adam (lr 1e-3), same loss.
+    The forward runs through the quantisers' autograd functions + the fused per-channel affine kernel (gradients of
+    gamma/varphi = per-channel reductions over N,H,W), captured as one graph per iteration."""
+    slots = []
+    for m in modules:
+        slots += [(m.weight_quantizer, 'alpha'), (m, 'alpha_out'), (m, 'beta_out')]
+        m.train_output_affine = True
+    quantizers = [m.weight_quantizer for m in modules]
+    reg_fn = lambda live: [sum(ops.RoundReg.apply(q.alpha, live[0], weight) for q in quantizers)]
+    eng = AutogradReconEngine(unit, slots, cached_inps, cached_outs, iters=iters, batch_size=batch_size, p=p,
+                              lr_table=torch.full((max(iters, 1),), 1e-3),
+                              b_tables=[brecq_b_table(iters, warmup, b_range, round_loss=True)], reg_fn=reg_fn,
+                              multi_gpu=multi_gpu)
+
+    def report(i):
+        count = i + 1
+        rec, rnd = float(eng.loss_dev), float(eng.reg_vals[0])
+        print('Total loss:\t{:.3f} (rec:{:.3f}, round:{:.3f})\tb={:.2f}\tcount={}'.format(rec + rnd, rec, rnd, float(eng.live[0]), count))
+
+    try:
+        eng.run(every=500, on_report=lambda i: report(i) if i > 0 else None)
+    finally:
+        eng.close()
+        for m in modules:
+            m.train_output_affine = False
+            m._affine_key = None            # the parameters were stepped through the flat buffer: re-derive "is identity"
+
+
 def reconstruct_unit(model, unit, cali_data, *, is_block, batch_size, iters, weight, opt_mode, asym, include_act_func,
-                     b_range, warmup, act_quant, lr, p, multi_gpu, eval):
+                     b_range, warmup, act_quant, lr, p, multi_gpu, eval, bias_cal=False):
     """shared body of block_reconstruction (block_recon.py:10-116) and layer_reconstruction (layer_recon.py:10-104)"""
     if eval:
         iters = 0          # structure-only call: swap the quantisers, learn nothing (block_recon.py:36-37)
@@ -46,13 +77,19 @@ def reconstruct_unit(model, unit, cali_data, *, is_block, batch_size, iters, wei
     if iters > 0:
         cached_inps, cached_outs = save_inp_oup_data(model, unit, cali_data, asym, act_quant, batch_size)
         cached_grads = save_grad_data(model, unit, cali_data, act_quant, batch_size=batch_size) if opt_mode != 'mse' else None
-        engine = ReconEngine(unit, modules, cached_inps, cached_outs, cached_grads, act_quant=act_quant, iters=iters,
-                             weight=weight, b_range=b_range, warmup=warmup, p=p, lr=lr, opt_mode=opt_mode,
-                             batch_size=batch_size, multi_gpu=multi_gpu, act_quantizers=act_quantizers)
-        try:
-            engine.run()
-        finally:
-            engine.close()
+        if bias_cal and not act_quant:
+            if opt_mode != 'mse':
+                raise NotImplementedError('bias_cal is defined for the mse reconstruction loss')
+            _run_with_output_affine(unit, modules, cached_inps, cached_outs, iters=iters, weight=weight, b_range=b_range,
+                                    warmup=warmup, p=p, batch_size=batch_size, multi_gpu=multi_gpu)
+        else:
+            engine = ReconEngine(unit, modules, cached_inps, cached_outs, cached_grads, act_quant=act_quant, iters=iters,
+                                 weight=weight, b_range=b_range, warmup=warmup, p=p, lr=lr, opt_mode=opt_mode,
+                                 batch_size=batch_size, multi_gpu=multi_gpu, act_quantizers=act_quantizers)
+            try:
+                engine.run()
+            finally:
+                engine.close()
         del cached_inps, cached_outs, cached_grads
         torch.cuda.empty_cache()
 
@@ -66,12 +103,13 @@ def block_reconstruction(model: QuantModel, block: BaseQuantBlock, cali_data: to
                          batch_size: int = 32, iters: int = 20000, weight: float = 0.01, opt_mode: str = 'mse',
                          asym: bool = False, include_act_func: bool = True, b_range: tuple = (20, 2),
                          warmup: float = 0.0, act_quant: bool = False, lr: float = 4e-5, p: float = 2.0,
-                         multi_gpu: bool = False, eval: bool = False):
+                         multi_gpu: bool = False, eval: bool = False, bias_cal: bool = False):
     """Optimise the rounding (or, with act_quant, the activation step sizes) of every layer in `block` so the
-    block output matches the FP block output on the calibration data. Arguments as upstream."""
+    block output matches the FP block output on the calibration data. Arguments as upstream; `bias_cal` (README flag,
+    keyword-only in practice) additionally learns every layer's output-channel scale/offset in the weight phase."""
     reconstruct_unit(model, block, cali_data, is_block=True, batch_size=batch_size, iters=iters, weight=weight,
                      opt_mode=opt_mode, asym=asym, include_act_func=include_act_func, b_range=b_range, warmup=warmup,
-                     act_quant=act_quant, lr=lr, p=p, multi_gpu=multi_gpu, eval=eval)
+                     act_quant=act_quant, lr=lr, p=p, multi_gpu=multi_gpu, eval=eval, bias_cal=bias_cal)
 
 
 class LossFunction:

@@ -143,10 +143,13 @@ class QuantBottleneck(BaseQuantBlock):
         self.stride = bottleneck.stride
 
     def forward(self, x):
+        self._cache_in(x)               # upstream caches block features in QuantBasicBlock only (quant_block.py:100,115)
         residual = x if self.downsample is None else self.downsample(x)
         out = self.conv3(self.conv2(self.conv1(x)))
         out += residual
-        return self._tail(out)
+        out = self._tail(out)
+        self._cache_out(out)
+        return out
 
 
 class QuantResBottleneckBlock(BaseQuantBlock):
@@ -162,10 +165,13 @@ class QuantResBottleneckBlock(BaseQuantBlock):
         self.downsample = _qm(bottleneck.proj, weight_quant_params, act_quant_params, last=True) if self.proj_block else None
 
     def forward(self, x):
+        self._cache_in(x)
         residual = self.downsample(x) if self.proj_block else x
         out = self.conv3(self.conv2(self.conv1(x)))
         out += residual
-        return self._tail(out)
+        out = self._tail(out)
+        self._cache_out(out)
+        return out
 
 
 class QuantInvertedResidual(BaseQuantBlock):
@@ -181,8 +187,11 @@ class QuantInvertedResidual(BaseQuantBlock):
         self.conv = nn.Sequential(*mods)
 
     def forward(self, x):
+        self._cache_in(x)
         out = x + self.conv(x) if self.use_res_connect else self.conv(x)
-        return self._tail(out)
+        out = self._tail(out)
+        self._cache_out(out)
+        return out
 
 
 specials = {

@@ -208,6 +208,7 @@ class QuantModule(nn.Module):
         self.beta_out = nn.Parameter(torch.zeros(affine_shape))     # README's varphi^z
         self._affine_key = None
         self._affine_identity = True
+        self.train_output_affine = False    # True while gamma^z / varphi^z are being learned: always apply the affine
         self._engine_weight = None      # set by ReconEngine: weight already produced by a multi-tensor launch
         self.selection = None
         self.selectionInited = False
@@ -235,7 +236,7 @@ class QuantModule(nn.Module):
         else:
             weight, bias = self.org_weight, self.org_bias
         out = self.fwd_func(input, weight, bias, **self.fwd_kwargs)
-        if quantized and not self._output_affine_is_identity():
+        if quantized and (self.train_output_affine or not self._output_affine_is_identity()):
             out = ops.ChanAffine.apply(out, self.alpha_out, self.beta_out)
         if self.se_module is not None:
             out = self.se_module(out)

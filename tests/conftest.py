@@ -15,6 +15,19 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+@pytest.fixture(autouse=True, scope="session")
+def _true_fp32_contractions():
+    """parity is stated against the reference's fp32 arithmetic (its CPU path is the pinned oracle): the convolutions
+    and matmuls the path does not own must not run in TF32 (torch's cuDNN default) while they are compared with it"""
+    try:
+        import torch
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+    except Exception:  # pragma: no cover
+        pass
+    yield
+
+
 def pytest_collection_modifyitems(config, items):
     try:
         import torch

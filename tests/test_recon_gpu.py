@@ -333,3 +333,75 @@ def test_act_phase_engine_vs_oracle_loop():
         ref, got = float(act_state[k][0]), float(q.delta)
         assert ref != d0[k], "reference step size did not move"
         assert abs(got - ref) <= 2e-3 * abs(ref - d0[k]) + 1e-5 * abs(ref), (k, d0[k], ref, got)
+
+
+def test_bias_cal_matches_reference_autograd():
+    """README --bias_cal: gamma^z / varphi^z (alpha_out / beta_out) learned with the AdaRound alphas. Golden = the real
+    reference's forward/autograd/LossFunction/Adam with those parameters added to the optimiser
+    (tests/golden/make_golden_bias_cal.py), on the reference's own cached features and index stream."""
+    from conftest import golden
+    from shiftedscalequantization_b200.engine import AutogradReconEngine, brecq_b_table
+    from shiftedscalequantization_b200.quant.adaptive_rounding import AdaRoundQuantizer
+    from shiftedscalequantization_b200 import ops
+    g = golden("bias_cal")
+    iters, bs = int(g["iters"]), int(g["bs"])
+    from shiftedscalequantization_b200 import quant as Q, zoo
+    torch.manual_seed(1005)
+    cnn = zoo.resnet18(num_classes=10).cuda().eval()
+    qnn = Q.QuantModel(cnn, {'n_bits': 2, 'channel_wise': True, 'scale_method': 'max'}, dict(AQ)).cuda().eval()
+    qnn.set_first_last_layer_to_8bit()
+    cali = torch.from_numpy(g["cali"])
+    qnn.set_quant_state(True, False)
+    with torch.no_grad():
+        qnn(cali.cuda())
+    block = qnn.model.layer2[0]
+    qnn.set_quant_state(False, False); block.set_quant_state(True, False)
+    mods = [(n, m) for n, m in block.named_modules() if isinstance(m, Q.QuantModule)]
+    slots = []
+    for _n, m in mods:
+        m.weight_quantizer = AdaRoundQuantizer(uaq=m.weight_quantizer, round_mode='learned_hard_sigmoid',
+                                               weight_tensor=m.org_weight.data)
+        m.weight_quantizer.soft_targets = True
+        m.train_output_affine = True
+        slots += [(m.weight_quantizer, 'alpha'), (m, 'alpha_out'), (m, 'beta_out')]
+    inps, outs = torch.from_numpy(g["inps"]).cuda(), torch.from_numpy(g["outs"]).cuda()
+    qs = [m.weight_quantizer for _n, m in mods]
+    eng = AutogradReconEngine(block, slots, inps, outs, iters=iters, batch_size=bs, p=2.0,
+                              lr_table=torch.full((iters,), 1e-3), b_tables=[brecq_b_table(iters, 0.2, (20, 2), True)],
+                              reg_fn=lambda live: [sum(ops.RoundReg.apply(q.alpha, live[0], 0.01) for q in qs)],
+                              idx_table=torch.from_numpy(g["idx"]), use_graph=True)
+    # first-iteration gradients of gamma / varphi against the reference's autograd (eager step, then roll back)
+    snap = [t.clone() for t in eng._state()]
+    eng._iteration()
+    off = 0
+    for (n, m), in zip(mods):
+        ga = eng.gviews[[id(p) for p in eng.params].index(id(m.alpha_out))]
+        gb = eng.gviews[[id(p) for p in eng.params].index(id(m.beta_out))]
+        assert_close(ga.cpu().numpy(), g[f"{n}.g_alpha_out0"], rtol=1e-4, what=f"{n} d/d alpha_out, iteration 0")
+        assert_close(gb.cpu().numpy(), g[f"{n}.g_beta_out0"], rtol=1e-4, what=f"{n} d/d beta_out, iteration 0")
+    for t, s0 in zip(eng._state(), snap):
+        t.copy_(s0)
+    losses = []
+    eng.capture()
+    for i in range(iters):
+        eng.step()
+        losses.append(float(eng.loss_dev) + float(eng.reg_vals[0]))
+    eng.close()
+    assert_close(np.array(losses), g["losses"], rtol=2e-3, what="total loss per iteration vs reference")
+    for n, m in mods:
+        for name, ours in (("alpha", m.weight_quantizer.alpha), ("alpha_out", m.alpha_out), ("beta_out", m.beta_out)):
+            err = np.abs(ours.detach().cpu().numpy() - g[f"{n}.{name}"])
+            assert (err <= 2e-3).mean() >= 0.999 and err.max() <= 2 * 1e-3 * iters, (n, name, err.max())
+        assert (np.sign(m.weight_quantizer.alpha.detach().cpu().numpy()) == np.sign(g[f"{n}.alpha"])).mean() > 0.9995
+        m.weight_quantizer.soft_targets = False
+    with torch.no_grad():
+        out = block(inps[:8]).cpu().numpy()
+    assert np.abs(out - g["hard_out"]).max() <= 5e-3 * np.abs(g["hard_out"]).max()
+    # the public entry point with the flag
+    Q2, qnn2, cali2 = build_qnn()
+    blk = qnn2.model.layer1[0]
+    Q2.block_reconstruction(qnn2, blk, cali_data=cali2, iters=24, weight=0.01, asym=True, b_range=(20, 2), warmup=0.2,
+                            act_quant=False, opt_mode='mse', batch_size=16, bias_cal=True)
+    assert not bool((blk.conv1.alpha_out.detach() == 1).all()) and blk.conv1.weight_quantizer.soft_targets is False
+    with torch.no_grad():
+        assert torch.isfinite(blk(torch.randn(2, 64, 8, 8, device='cuda'))).all()

@@ -258,13 +258,14 @@ def _golden_shift_setup(tag_feats="A"):
 
 
 def _close_params(ours, ref, what, atol=2e-3, lr=1e-3, steps=20):
-    """>= 99.9 % of the entries within atol; no entry further away than Adam can carry it (2 * lr * steps: an entry whose
+    """>= 99.9 % of the entries (or all but one group) within atol; no entry further away than Adam can carry it (2 * lr * steps: an entry whose
     tiny gradient changes sign between the cuDNN and the CPU convolution walks the other way for a few steps)"""
     ours, ref = host(ours), np.asarray(ref)
     assert ours.shape == ref.shape, what
     err = np.abs(ours - ref)
-    frac = (err <= atol).mean()
-    assert frac >= 0.999, f"{what}: only {frac:.5f} of the entries within {atol}"
+    bad = int((err > atol).sum())
+    allowed = max(int(np.ceil(1e-3 * err.size)), 3)           # 3 = one group of a small [IC,S] alpha
+    assert bad <= allowed, f"{what}: {bad} of {err.size} entries further than {atol} (allowed {allowed})"
     assert err.max() <= 2 * lr * steps, f"{what}: max abs diff {err.max():.3e}"
 
 
