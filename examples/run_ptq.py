@@ -15,6 +15,7 @@ import torch.nn as nn
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from shiftedscalequantization_b200 import quant as Q, zoo          # noqa: E402
+from shiftedscalequantization_b200.quant.quant_block import QuantBasicBlock  # noqa: E402
 from shiftedscalequantization_b200.quant import (BaseQuantBlock, QuantModel, QuantModule,  # noqa: E402
                                                    block_reconstruction, layer_reconstruction)
 
@@ -41,9 +42,16 @@ def main(argv=None):
     ap.add_argument('--p', default=2.4, type=float)
     ap.add_argument('--batch_size', default=32, type=int)
     ap.add_argument('--max_units', default=0, type=int, help='reconstruct only the first N units (0 = all)')
+    # the reference README's flags (README.md:20,33-34)
+    flag = lambda v: str(v).lower() in ('1', 'true', 'yes')
+    ap.add_argument('--device_gpu', default='cuda:0')
+    ap.add_argument('--bias_cal', default=False, type=flag, help='learn the output-channel scale gamma^z and offset varphi^z')
+    ap.add_argument('--bias_ch_quant', default=False, type=flag,
+                    help='learn the input-channel group R: shifted-scale ChannelQuant + fused shift/rounding loop on BasicBlock units')
     args = ap.parse_args(argv)
 
-    dev = torch.device('cuda')
+    dev = torch.device(args.device_gpu)
+    torch.cuda.set_device(dev)
     torch.manual_seed(args.seed)
     kw = {} if args.arch.startswith('regnet') else ({'n_class': args.num_classes} if args.arch == 'mobilenetv2' else {'num_classes': args.num_classes})
     cnn = zoo.build(args.arch, **kw).to(dev).eval()
@@ -62,6 +70,28 @@ def main(argv=None):
 
     done = [0]
 
+    def shifted_block(block, iters):
+        """--bias_ch_quant: ChannelQuant swap, 'if'/'of' feature caches, fused shift + rounding loop
+        (the flow of ShiftedScaleQuant.py:244-255,384-392 / myScaledMethods.py)"""
+        from shiftedscalequantization_b200.quant.channelQuant import ChannelQuant
+        from shiftedscalequantization_b200.quant.layer_recon_fused_shiftedScale import block_recon_fused_shiftedScale
+        for m in block.modules():
+            if isinstance(m, QuantModule):
+                m.weight_quantizer = ChannelQuant(1.0, uaq=m.weight_quantizer, weight_tensor=m.org_weight.data,
+                                                  shiftTarget=[0.96875, 1.03125, 1.0], name=m.pathName)
+        block.clear_cached_features()
+        for mode, wq_on in (('if', True), ('of', False)):
+            qnn.set_quant_state(wq_on, False)
+            block.cache_features = mode
+            with torch.no_grad():
+                for i in range(0, cali.shape[0], args.batch_size):
+                    qnn(cali[i:i + args.batch_size].to(dev))
+            block.cache_features = 'none'
+        qnn.set_quant_state(False, False)
+        block.set_quant_state(True, False)
+        block_recon_fused_shiftedScale(block, iters=iters, lmda=[args.weight, args.weight], model=qnn, bias_cal=args.bias_cal)
+        block.clear_cached_features()
+
     def recon_model(model: nn.Module, **kwargs):
         for name, module in model.named_children():
             if args.max_units and done[0] >= args.max_units:
@@ -74,14 +104,17 @@ def main(argv=None):
             elif isinstance(module, BaseQuantBlock):
                 if not module.ignore_reconstruction:
                     print(f'Reconstruction for block {name}')
-                    block_reconstruction(qnn, module, **kwargs)
+                    if args.bias_ch_quant and not kwargs.get('act_quant') and isinstance(module, QuantBasicBlock):
+                        shifted_block(module, kwargs['iters'])
+                    else:
+                        block_reconstruction(qnn, module, **kwargs)
                     done[0] += 1
             else:
                 recon_model(module, **kwargs)
 
     t0 = time.time()
     recon_model(qnn, cali_data=cali, iters=args.iters_w, weight=args.weight, asym=True, b_range=(args.b_start, args.b_end),
-                warmup=args.warmup, act_quant=False, opt_mode='mse', batch_size=args.batch_size)
+                warmup=args.warmup, act_quant=False, opt_mode='mse', batch_size=args.batch_size, bias_cal=args.bias_cal)
     torch.cuda.synchronize()
     print(f'weight reconstruction: {time.time() - t0:.2f}s for {done[0]} units x {args.iters_w} iterations')
     qnn.set_quant_state(weight_quant=True, act_quant=False)

@@ -91,7 +91,7 @@ class FusedScaleLossFunction(_LazyScalars):
             float(self.total_loss), float(self.rec_loss), self.round_loss_val, self.b)
 
 
-def _fused_captured(unit, loss_func, quantizers, lr, cached_inp, cached_out, iters, batch_size, describe):
+def _fused_captured(unit, loss_func, quantizers, lr, cached_inp, cached_out, iters, batch_size, describe, extra_slots=()):
     """captured-graph version of the loop at upstream :84-110: temperature b for h(beta), b2 (3/4-length schedule) for the
     group probabilities, both gated off during warm-up through their device tables"""
     lr_table = torch.full((max(iters, 1),), float(lr))
@@ -108,14 +108,16 @@ def _fused_captured(unit, loss_func, quantizers, lr, cached_inp, cached_out, ite
         if vals:
             loss_func._r, loss_func._s = vals[0].reshape(()), vals[1].reshape(())
 
-    slots = [(q, 'alpha') for q in quantizers]
+    slots = [(q, 'alpha') for q in quantizers] + list(extra_slots)
     start_loss, _eng = _run_captured(unit, loss_func, slots, lr_table, b_tables, reg_fn, cached_inp, cached_out, iters,
                                      batch_size, describe, on_regs)
     return start_loss
 
 
 def block_recon_fused_shiftedScale(block: BaseQuantBlock, iters: int = 20000, lmda: list = [1., 1.], model=None,
-                                   test_loader=None, act=False, adaround=False, useShiftedScale=True):
+                                   test_loader=None, act=False, adaround=False, useShiftedScale=True, bias_cal=False):
+    """bias_cal (README flag; upstream's commented `opt_params += [module.alpha_out] / [module.beta_out]`, :67-68): the
+    output-channel scale/offset of every layer joins the optimiser."""
     block.train()
     warmup, p, b_range, lr, batch_size = 0.2, 2.0, (20, 2), 0.001, 32
     device = next(model.parameters()).device
@@ -135,6 +137,12 @@ def block_recon_fused_shiftedScale(block: BaseQuantBlock, iters: int = 20000, lm
             opt_params.append(q.alpha)
             quantizers.append(q)
             q.opt_mode = 'adaShift'
+    extra_slots = []
+    if bias_cal and not act:
+        for m in modules:
+            m.train_output_affine = True
+            extra_slots += [(m, 'alpha_out'), (m, 'beta_out')]
+            opt_params += [m.alpha_out, m.beta_out]
     print("number of elements in opt_params: {}".format(sum(q.numel() for q in opt_params)))
     loss_func = FusedScaleLossFunction(block, quantizers, round_loss='none' if act else 'relaxation', lmda=lmda,
                                        max_count=iters, b_range=b_range, decay_start=0, warmup=warmup, p=p)
@@ -142,8 +150,9 @@ def block_recon_fused_shiftedScale(block: BaseQuantBlock, iters: int = 20000, lm
     cached_out = torch.cat(block.cached_out_features).to(device)
     describe = lambda s0, lf: f"{s0:.6f} -> {lf.rec_loss:.6f} {lf.round_loss_val} "
     if _ls.USE_CAPTURED_LOOP and iters >= 8 and opt_params:
-        start_loss = _fused_captured(block, loss_func, quantizers, lr, cached_inp, cached_out, iters, batch_size, describe)
-        optimizer = torch.optim.Adam([q.alpha for q in quantizers], lr=lr)
+        start_loss = _fused_captured(block, loss_func, quantizers, lr, cached_inp, cached_out, iters, batch_size, describe,
+                                     extra_slots)
+        optimizer = torch.optim.Adam([q.alpha for q in quantizers] + [getattr(o, a) for o, a in extra_slots], lr=lr)
     else:
         optimizer = torch.optim.Adam(opt_params, lr=lr)
         start_loss = _run_loop(block, loss_func, optimizer, None, cached_inp, cached_out, iters, batch_size, describe)
@@ -157,6 +166,10 @@ def block_recon_fused_shiftedScale(block: BaseQuantBlock, iters: int = 20000, lm
     out.append(_probe(block, loss_func, optimizer, cached_inp, cached_out, batch_size))
     print(f"Hard Round : {start_loss:.6f} -> {loss_func.rec_loss:.6f} {loss_func.round_loss_val}")
     print_ratio(quantizers)
+    for m in modules:
+        if getattr(m, 'train_output_affine', False):
+            m.train_output_affine = False
+            m._affine_key = None
     torch.cuda.empty_cache()
     model.eval()
     return out

@@ -187,6 +187,22 @@ def test_example_driver_cifar_config():
     assert any(k.endswith('weight_quantizer.alpha') for k in keys) and any(k.endswith('act_quantizer.delta') for k in keys)
 
 
+def test_example_driver_readme_flags():
+    """README usage line: --device_gpu / --bias_cal / --bias_ch_quant (parity unpinned upstream: the flags have no code
+    there; semantics defined in DESIGN.md) — the whole flow must run and leave learned gamma/varphi and group choices"""
+    sys.path.insert(0, os.path.join(ROOT, "examples"))
+    import run_ptq
+    from shiftedscalequantization_b200.quant.channelQuant import ChannelQuant
+    qnn = run_ptq.main(['--arch', 'resnet18', '--num_classes', '10', '--res', '32', '--n_bits_w', '2', '--n_bits_a', '4',
+                        '--num_samples', '64', '--iters_w', '24', '--iters_a', '16', '--max_units', '2', '--scale_method', 'max',
+                        '--device_gpu=cuda:0', '--bias_cal=True', '--bias_ch_quant=True'])
+    blk = qnn.model.layer1[0]
+    q = blk.conv1.weight_quantizer
+    assert isinstance(q, ChannelQuant) and q.opt_mode == 'adaShift' and q.hard_targets and q.hard_round
+    assert not bool((blk.conv1.alpha_out.detach() == 1).all()) and not bool((blk.conv2.beta_out.detach() == 0).all())
+    assert blk.conv1.train_output_affine is False
+
+
 def test_channel_shift_mse_flow_mobilenetv2_w3():
     """BASELINE configs[3] at small scale: MobileNetV2 W3 (depthwise-heavy) + ChannelQuantMSE input-scale search"""
     from shiftedscalequantization_b200 import scaled_methods as SM, zoo
