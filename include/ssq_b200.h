@@ -220,6 +220,25 @@ int ssq_recon_loss_bwd(const float* pred, const float* tgt, const float* fisher,
                        const float* gloss, float* dpred, int64_t batch, int64_t per_sample, double denom,
                        int mode, float p_norm, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- true-integer export --------------------------------------------------
+ * The reference never materialises integer weights; these entry points store the integer intermediate `x_quant` of
+ * its hard forwards bit-packed and read it back into the dequantised weight those forwards return:
+ *   alpha == NULL : q = clamp(rint(x/delta[c]) + zp[c], qmin, qmax)                 quant/quant_layer.py:92-96
+ *   alpha != NULL : q = clamp(floor(x/delta[c]) + (alpha >= 0) + zp[c], qmin, qmax)  quant/adaptive_rounding.py:50-58
+ *   in_scale != NULL (k elements): x is first divided by in_scale[j] and the dequantised value multiplied by it
+ *                   (quant/channelQuantMSE.py:134-143; pass zp = rint(raw_zp/delta))
+ *   import: w_q = ((u + qmin) - zp[c]) * delta[c] [* in_scale[j]]
+ * The tensor is [rows, k] with the usual channel layout (inner, nchan) over its rows*k elements. Each row occupies
+ * ssq_packed_row_bytes(k, n_bits) bytes; u = q - qmin is stored in sbits = smallest of {1,2,4,8} >= n_bits bits,
+ * element j at bit (j % (8/sbits))*sbits of byte j/(8/sbits); padding bits are zero. `packed` is DEVICE memory. */
+int64_t ssq_packed_row_bytes(int64_t k, int n_bits);
+int ssq_export_codes(const float* w, const float* alpha, const float* in_scale, const float* delta,
+                     const float* zero_point, uint8_t* packed, int64_t rows, int64_t k, int64_t inner,
+                     int64_t nchan, float qmin, float qmax, int n_bits, void* stream);
+int ssq_import_codes(const uint8_t* packed, const float* in_scale, const float* delta, const float* zero_point,
+                     float* w_q, int64_t rows, int64_t k, int64_t inner, int64_t nchan, float qmin,
+                     int n_bits, void* stream);
+
 /* ---- per-output-channel affine on activations, quant/quant_layer.py:258-259 -----------
  * y = x*a[c] + b[c] with two roundings (mul then add, as the reference) */
 int ssq_chan_affine_fwd(const float* x, const float* a, const float* b, float* y,

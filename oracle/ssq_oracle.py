@@ -406,3 +406,38 @@ def adam_step(p, g, m, v, step: int, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8):
     denom = np.sqrt(v) / F(bc2 ** 0.5) + F(eps)
     p = p - F(lr / bc1) * (m / denom)
     return p.astype(F), m.astype(F), v.astype(F)
+
+
+# ------------------------------------------------------------------------------------------------ integer export
+def storage_bits(n_bits: int) -> int:
+    return 1 if n_bits <= 1 else (2 if n_bits <= 2 else (4 if n_bits <= 4 else 8))
+
+
+def pack_rows(codes, qmin, n_bits: int):
+    """bit-packing of the integer intermediate `x_quant` the reference's hard forwards compute and discard
+    (quant/quant_layer.py:92-96, quant/adaptive_rounding.py:50-58): u = q - qmin, `storage_bits` bits per element,
+    little-endian within a byte, every row ([rows, k] view) starting on a byte boundary (include/ssq_b200.h)."""
+    q = np.asarray(codes)
+    rows = q.shape[0]
+    u = (q.reshape(rows, -1).astype(np.int64) - int(qmin)).astype(np.uint8)
+    sb = storage_bits(n_bits)
+    per = 8 // sb
+    k = u.shape[1]
+    row_bytes = (k * sb + 7) // 8
+    pad = np.zeros((rows, row_bytes * per), dtype=np.uint8)
+    pad[:, :k] = u
+    pad = pad.reshape(rows, row_bytes, per)
+    out = np.zeros((rows, row_bytes), dtype=np.uint8)
+    for e in range(per):
+        out |= (pad[:, :, e] << (e * sb)).astype(np.uint8)
+    return out
+
+
+def unpack_rows(packed, k: int, qmin, n_bits: int):
+    sb = storage_bits(n_bits)
+    per = 8 // sb
+    packed = np.asarray(packed, dtype=np.uint8)
+    rows = packed.shape[0]
+    parts = [(packed >> (e * sb)) & ((1 << sb) - 1) for e in range(per)]
+    u = np.stack(parts, axis=-1).reshape(rows, -1)[:, :k]
+    return (u.astype(F) + F(qmin)).astype(F)

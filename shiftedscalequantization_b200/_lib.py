@@ -65,6 +65,9 @@ PROTOTYPES = {
     "ssq_chan_affine_bwd": (_i32, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p, _sz, _p]),
     "ssq_adam_step": (_i32, [_p, _p, _p, _p, _i64, _p, _d, _d, _d, _p, _p]),
     "ssq_gather_rows": (_i32, [_p, _p, _p, _i64, _i64, _p]),
+    "ssq_packed_row_bytes": (_i64, [_i64, _i32]),
+    "ssq_export_codes": (_i32, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _f, _f, _i32, _p]),
+    "ssq_import_codes": (_i32, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _f, _i32, _p]),
     "ssq_stage_rows_h2d": (_i32, [_p, _p, _p, _i64, _i64, _p]),
     "ssq_pull_rows_host": (_i32, [_p, _p, _p, _i64, _i64, _p, _i64, _i64, _i32, _p]),
     "ssq_loop_advance": (_i32, [_p, _p, _p, _i32, _p, _p, _p, _p, _i64, _p]),

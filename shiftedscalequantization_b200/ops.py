@@ -519,6 +519,50 @@ class ReconLoss(torch.autograd.Function):
         return dpred.view_as(pred), None, None, None, None
 
 
+# --------------------------------------------------------------------------------------- integer export
+def packed_row_bytes(k: int, n_bits: int) -> int:
+    return int(_lib.load().ssq_packed_row_bytes(int(k), int(n_bits)))
+
+
+def export_codes(w, delta, zero_point, qmin: float, qmax: float, n_bits: int, alpha=None, in_scale=None):
+    """bit-packed integer codes [rows, packed_row_bytes] (uint8, device) of the hard forward of w; see include/ssq_b200.h"""
+    w = _req(w, "w"); delta = _req(delta, "delta"); zero_point = _req(match_param(zero_point, delta), "zero_point")
+    rows = w.shape[0]
+    k = w.numel() // max(rows, 1)
+    inner, nchan = channel_layout(w, delta)
+    if alpha is not None:
+        alpha = _req(alpha, "alpha")
+        if alpha.shape != w.shape:
+            raise _lib.SsqError("alpha must have the weight's shape")
+    if in_scale is not None:
+        in_scale = _req(in_scale, "in_scale")
+        if in_scale.numel() != k:
+            raise _lib.SsqError("in_scale must have IC*kh*kw elements")
+    packed = torch.zeros((rows, packed_row_bytes(k, n_bits)), dtype=torch.uint8, device=w.device)
+    _call("ssq_export_codes", w.data_ptr(), _ptr(alpha), _ptr(in_scale), delta.data_ptr(), zero_point.data_ptr(),
+          packed.data_ptr(), rows, k, inner, nchan, float(qmin), float(qmax), int(n_bits), _stream(w))
+    return packed
+
+
+def import_codes(packed, shape, delta, zero_point, qmin: float, n_bits: int, in_scale=None):
+    """dequantised fp32 weight of `shape` from codes packed by export_codes"""
+    delta = _req(delta, "delta"); zero_point = _req(match_param(zero_point, delta), "zero_point")
+    if not packed.is_cuda or packed.dtype != torch.uint8:
+        raise _lib.SsqError("packed must be a uint8 device tensor")
+    packed = packed.contiguous()
+    wq = torch.empty(tuple(shape), dtype=torch.float32, device=packed.device)
+    rows = wq.shape[0]
+    k = wq.numel() // max(rows, 1)
+    if tuple(packed.shape) != (rows, packed_row_bytes(k, n_bits)):
+        raise _lib.SsqError("packed tensor does not match shape / n_bits")
+    inner, nchan = channel_layout(wq, delta)
+    if in_scale is not None:
+        in_scale = _req(in_scale, "in_scale")
+    _call("ssq_import_codes", packed.data_ptr(), _ptr(in_scale), delta.data_ptr(), zero_point.data_ptr(), wq.data_ptr(),
+          rows, k, inner, nchan, float(qmin), int(n_bits), _stream(wq))
+    return wq
+
+
 # --------------------------------------------------------------------------------------- affine / adam / loop
 def chan_affine_fwd(x, a, b):
     x = _req(x, "x"); a = _req(a, "a"); b = _req(b, "b")

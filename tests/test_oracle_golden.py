@@ -130,3 +130,23 @@ def test_adam():
     for s in range(1, 6):
         p, m, v = O.adam_step(p, g[f"g{s}"], m, v, s)
         assert_close(p, g[f"p{s}"], rtol=2e-6, what=f"adam step {s}")
+
+
+@pytest.mark.parametrize("bits", [1, 2, 3, 4, 8])
+def test_pack_unpack_round_trip(bits):
+    """oracle bit-packing of the integer codes (layout of include/ssq_b200.h, export section): ragged rows, all widths"""
+    rng = np.random.default_rng(bits)
+    for rows, k in [(5, 9), (3, 27), (2, 147), (4, 64), (1, 1)]:
+        q = rng.integers(0, 2 ** bits, size=(rows, k)).astype(np.float32)
+        packed = O.pack_rows(q, 0, bits)
+        sb = O.storage_bits(bits)
+        assert packed.shape == (rows, (k * sb + 7) // 8) and packed.dtype == np.uint8
+        assert np.array_equal(O.unpack_rows(packed, k, 0, bits), q)
+    # known answer: 2-bit codes 1,2,3,0 -> 0b00_11_10_01; symmetric codes are stored offset by qmin
+    assert O.pack_rows(np.array([[1, 2, 3, 0]], np.float32), 0, 2)[0, 0] == 0b00111001
+    assert O.pack_rows(np.array([[-2, -1, 0, 1]], np.float32), -2, 2)[0, 0] == 0b11100100
+    # adaround codes of the reference (golden) survive the round trip
+    g = golden("adaround").case(golden("adaround").cases()[0])
+    codes = g["codes_hard"]
+    nb = int(np.ceil(np.log2(codes.max() + 1)))
+    assert np.array_equal(O.unpack_rows(O.pack_rows(codes, 0, nb), codes[0].size, 0, nb).reshape(codes.shape), codes)
