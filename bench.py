@@ -289,7 +289,10 @@ def kernel_microbench(dev, peak_gbs):
     m = torch.zeros_like(w); v = torch.zeros_like(w)
     step = torch.ones(1, dtype=torch.int64, device=dev); lr = ops.scalar_dev(1e-3, dev)
     res["adam_step"] = timeit(lambda: ops.adam_step(alpha, g, m, v, lr, step), 28 * n)
-    del w, alpha, g, ga, m, v
+    packed = ops.export_codes(w, d, z, 0.0, 3.0, 2, alpha=alpha)
+    res["export_codes(2-bit,+alpha)"] = timeit(lambda: ops.export_codes(w, d, z, 0.0, 3.0, 2, alpha=alpha), 8 * n + n // 4)
+    res["import_codes(2-bit)"] = timeit(lambda: ops.import_codes(packed, w.shape, d, z, 0.0, 2), 4 * n + n // 4)
+    del w, alpha, g, ga, m, v, packed
     torch.cuda.empty_cache()
     x = torch.relu(torch.randn(256, 256, 56, 56, device=dev))
     t = torch.relu(torch.randn(256, 256, 56, 56, device=dev))
@@ -327,6 +330,64 @@ def scale_search_bench(Q, qnn, dev):
             "weight_elems": int(sum(r.numel() for r, _ in rows)),
             "activation_tensor_ms": a_ms, "activation_elems": int(act.numel()),
             "note": "powf-bound (80 x |d|^2.4 per element), not HBM-bound; reference: Python loop, 48.5 s on 8 CPU cores (SURVEY probe)"}
+
+
+def shifted_loop_bench(dev, n_images=256):
+    """a17/a18: the shifted-scale loops through their public functions (block_recon_fused_shiftedScale,
+    block_recon_shiftedScale, layer_recon_shiftedScale), captured-graph iteration vs the eager autograd loop; device time
+    of the iteration loop only (ChannelQuant init, capture and read-outs excluded), real 224x224 unit shapes"""
+    import contextlib
+    import io
+    from shiftedscalequantization_b200 import quant as Q, zoo
+    from shiftedscalequantization_b200.quant import layer_recon_shiftedScale as LS
+    from shiftedscalequantization_b200.quant.channelQuant import ChannelQuant
+    from shiftedscalequantization_b200.quant.layer_recon_fused_shiftedScale import block_recon_fused_shiftedScale
+    out = {}
+    cases = [("resnet18", 2, "model.layer2.0", "fused"), ("resnet18", 2, "model.layer4.1", "shift"),
+             ("resnet50", 4, "model.layer3.2.conv2", "layer_shift")]
+    for arch, bits, path, kind in cases:
+        res = {}
+        for captured, iters in ((True, 600), (False, 100)):
+            torch.manual_seed(1005)
+            cnn = zoo.build(arch).to(dev).eval()
+            qnn = Q.QuantModel(cnn, {'n_bits': bits, 'channel_wise': True, 'scale_method': 'max'}, dict(AQ)).to(dev).eval()
+            qnn.set_first_last_layer_to_8bit()
+            cali = torch.randn(n_images, 3, 224, 224)
+            qnn.set_quant_state(True, False)
+            with torch.no_grad():
+                qnn(cali[:32].to(dev))
+            unit = qnn
+            for part in path.split('.'):
+                unit = unit[int(part)] if part.isdigit() else getattr(unit, part)
+            for m in ([unit] if isinstance(unit, Q.QuantModule) else [m for m in unit.modules() if isinstance(m, Q.QuantModule)]):
+                m.weight_quantizer = ChannelQuant(1.0, uaq=m.weight_quantizer, weight_tensor=m.org_weight.data,
+                                                  shiftTarget=[0.96875, 1.03125, 1.0], name=m.pathName)
+            for mode, wq_on in (('if', True), ('of', False)):
+                qnn.set_quant_state(wq_on, False)
+                unit.cache_features = mode
+                with torch.no_grad():
+                    for i in range(0, n_images, BATCH):
+                        qnn(cali[i:i + BATCH].to(dev))
+                unit.cache_features = 'none'
+            qnn.set_quant_state(False, False)
+            unit.set_quant_state(True, False)
+            LS.USE_CAPTURED_LOOP = captured
+            with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+                if kind == "fused":
+                    block_recon_fused_shiftedScale(unit, iters=iters, lmda=[0.01, 0.01], model=qnn)
+                elif kind == "shift":
+                    LS.block_recon_shiftedScale(unit, iters=iters, lmda=0.01, model=qnn)
+                else:
+                    LS.layer_recon_shiftedScale(unit, iters=iters, lmda=0.01, model=qnn)
+            st = dict(LS.LAST_LOOP_STATS)
+            res["captured" if captured else "eager"] = {"iters_per_s": st["iters"] / (st["loop_ms"] * 1e-3), "iters": st["iters"],
+                                                        "ssq_launches_per_iter": st["launches_per_iter"]}
+            del qnn, cnn, unit
+            torch.cuda.empty_cache()
+        LS.USE_CAPTURED_LOOP = True
+        res["speedup"] = res["captured"]["iters_per_s"] / res["eager"]["iters_per_s"]
+        out[f"{arch}:{path}:{kind}"] = res
+    return out
 
 
 ENTRY_TO_MICRO = {"ssq_recon_loss": "recon_loss(fwd+dpred)", "ssq_gather_rows": "gather_rows", "ssq_adam_step": "adam_step",
@@ -460,11 +521,13 @@ def run_ours(args):
     del feats
     del engines, qnn
     torch.cuda.empty_cache()
+    shifted = shifted_loop_bench(dev) if not args.skip_shift else None
 
     # ---- roofline: DRAM-resident microbench of every kernel + in-step shares
     if args.skip_micro:
         line = base_line(args, value, ms_step, world, clocks, launches_per_step, e2e, peak_src)
-        line["extra"] = {"first_quantised_forward_ms": scale_search_s * 1e3, "scale_search": search, "setup_s": setup_s, "act_phase": act}
+        line["extra"] = {"first_quantised_forward_ms": scale_search_s * 1e3, "scale_search": search, "setup_s": setup_s, "act_phase": act,
+                         "shifted_loops": shifted}
         print(json.dumps(line), flush=True)
         return
     micro = kernel_microbench(dev, peak_gbs)
@@ -496,7 +559,7 @@ def run_ours(args):
     fq = {k: round(v["gbs"], 1) for k, v in micro.items() if k.startswith("fq_")}
     line["extra"] = {"first_quantised_forward_ms": scale_search_s * 1e3, "scale_search": search, "setup_s": setup_s, "act_phase": act,
                      "fake_quant_hbm_gbs": fq, "fake_quant_hbm_frac_min": round(min(v["frac"] for k, v in micro.items() if k.startswith("fq_")), 3),
-                     "tf32": tf32_extra,
+                     "tf32": tf32_extra, "shifted_loops": shifted,
                      "projected_full_run_s": (9 * 20000) / value + ((9 * 5000) / act["iters_per_s"] if act else 0)}
     print(json.dumps(line), flush=True)
 
@@ -528,6 +591,7 @@ def main():
     ap.add_argument("--skip-act", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-tf32", action="store_true")
+    ap.add_argument("--skip-shift", action="store_true", help="no shifted-scale loop timing")
     ap.add_argument("--micro-only", action="store_true", help="only the DRAM-resident kernel microbench")
     ap.add_argument("--skip-micro", action="store_true", help="no roofline microbench (short profiler runs)")
     args = ap.parse_args()

@@ -10,7 +10,7 @@
 // bits, element j of a row at bit (j % (8/sbits)) * sbits of byte j / (8/sbits) (little-endian within the byte).
 //
 // HBM-bound: (4 [+4 with alpha] + sbits/8) B/elem out, the reverse in. Vector path (rows whose length is a multiple of
-// 32/sbits, 16-byte aligned): one thread = one 32-bit word of codes = 32/sbits elements read as float4s.
+// 32/sbits, channels a multiple of 4 long, 16-byte aligned): one thread = one float4, lanes cooperate on the code words.
 #include "ssq_common.cuh"
 
 namespace ssq {
@@ -38,42 +38,63 @@ __device__ __forceinline__ int64_t chan_of(int64_t i, int64_t inner, int64_t nch
     return (i / inner) % nchan;
 }
 
-// ---- vector path: one thread packs E = 32/SBITS consecutive elements of one row into one u32 ---------------------
+// ---- vector path ---------------------------------------------------------------------------------------------
+// One thread = one float4 of weights (4 codes = 4*SBITS bits), consecutive lanes = consecutive float4s, so every load
+// instruction of a warp is one contiguous 512-byte run. G = 8/SBITS neighbouring lanes hold the pieces of one 32-bit
+// word of codes: they are OR-ed together with a shuffle butterfly and lane 0 of the group stores the word.
+// Needs k % (32/SBITS) == 0 (rows are whole words) and inner % 4 == 0 (a float4 never straddles two channels);
+// the channel of a vector is tracked with adds/compares (ChanWalk), no division in the loop.
+template <int SBITS, bool HAS_ALPHA>
+__device__ __forceinline__ uint32_t pack4(const float4& x, const float4& al, float d, float zp, float qmin, float qmax) {
+    const Recip R = make_recip(d);
+    const float4 t = div4_exact(x, R);
+    float4 r;
+    if (HAS_ALPHA) {
+        r.x = floorf(t.x) + (al.x >= 0.f ? 1.f : 0.f); r.y = floorf(t.y) + (al.y >= 0.f ? 1.f : 0.f);
+        r.z = floorf(t.z) + (al.z >= 0.f ? 1.f : 0.f); r.w = floorf(t.w) + (al.w >= 0.f ? 1.f : 0.f);
+    } else {
+        r.x = rintf(t.x); r.y = rintf(t.y); r.z = rintf(t.z); r.w = rintf(t.w);
+    }
+    // q - qmin is a small non-negative integer held exactly in fp32
+    const uint32_t u0 = __float2uint_rn(fminf(fmaxf(r.x + zp, qmin), qmax) - qmin);
+    const uint32_t u1 = __float2uint_rn(fminf(fmaxf(r.y + zp, qmin), qmax) - qmin);
+    const uint32_t u2 = __float2uint_rn(fminf(fmaxf(r.z + zp, qmin), qmax) - qmin);
+    const uint32_t u3 = __float2uint_rn(fminf(fmaxf(r.w + zp, qmin), qmax) - qmin);
+    return u0 | (u1 << SBITS) | (u2 << (2 * SBITS)) | (u3 << (3 * SBITS));
+}
+
 template <int SBITS, bool HAS_ALPHA>
 __global__ void __launch_bounds__(SSQ_THREADS)
 export_vec_kernel(ExportArgs a) {
-    constexpr int E = 32 / SBITS;                // elements per thread: 32, 16, 8, 4
-    const int64_t words = a.rows * (a.k / E);    // k % E == 0 on this path => rows are contiguous words
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < words; t += stride) {
-        const int64_t i0 = t * E;                // flat element index (rows are dense: row_bytes*8 == k*SBITS)
-        int64_t c = chan_of(i0, a.inner, a.nchan);
-        int64_t col = i0 - (i0 / a.inner) * a.inner;     // position inside the channel's run of `inner` elements
-        Recip R = make_recip(__ldg(a.delta + c));
-        float zp = __ldg(a.zp + c);
-        uint32_t word = 0;
+    constexpr int G = 8 / SBITS;                 // lanes per output word: 8, 4, 2, 1
+    const int64_t total4 = (a.rows * a.k) >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int sh = (lane & (G - 1)) * 4 * SBITS;
+    uint32_t* __restrict__ out = reinterpret_cast<uint32_t*>(a.packed);
+    ChanWalk c0, c1;                             // two vectors in flight per thread: i and i + stride
+    c0.init(first, 2 * stride, a.inner >> 2, a.nchan);
+    c1.init(first + stride, 2 * stride, a.inner >> 2, a.nchan);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t i = first; i - lane < total4; i += 2 * stride) {    // warp-uniform trip count: shuffles need every lane
+        const int64_t j = i + stride;
+        const bool v0 = i < total4, v1 = j < total4;
+        float4 x0 = zero4, x1 = zero4, a0 = zero4, a1 = zero4;
+        if (v0) { x0 = ld_stream4(a.w + i * 4); if (HAS_ALPHA) a0 = ld_stream4(a.alpha + i * 4); }
+        if (v1) { x1 = ld_stream4(a.w + j * 4); if (HAS_ALPHA) a1 = ld_stream4(a.alpha + j * 4); }
+        uint32_t p0 = 0, p1 = 0;
+        if (v0) p0 = pack4<SBITS, HAS_ALPHA>(x0, a0, __ldg(a.delta + c0.c), __ldg(a.zp + c0.c), a.qmin, a.qmax) << sh;
+        if (v1) p1 = pack4<SBITS, HAS_ALPHA>(x1, a1, __ldg(a.delta + c1.c), __ldg(a.zp + c1.c), a.qmin, a.qmax) << sh;
 #pragma unroll
-        for (int v = 0; v < E / 4; ++v) {
-            float4 x = ld_stream4(a.w + i0 + v * 4);
-            float4 al = HAS_ALPHA ? ld_stream4(a.alpha + i0 + v * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (a.in_scale) {                    // ChannelQuantMSE: x / inp_scale first (its own IEEE division)
-                const int64_t j = (i0 + v * 4) % a.k;
-                x.x = __fdiv_rn(x.x, __ldg(a.in_scale + j)); x.y = __fdiv_rn(x.y, __ldg(a.in_scale + j + 1));
-                x.z = __fdiv_rn(x.z, __ldg(a.in_scale + j + 2)); x.w = __fdiv_rn(x.w, __ldg(a.in_scale + j + 3));
-            }
-            const float xs[4] = {x.x, x.y, x.z, x.w};
-            const float as[4] = {al.x, al.y, al.z, al.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                if (col >= a.inner) {            // crossed into the next channel (inner < E or unaligned runs)
-                    col -= a.inner; c = (c + 1 == a.nchan) ? 0 : c + 1;
-                    R = make_recip(__ldg(a.delta + c)); zp = __ldg(a.zp + c);
-                }
-                word |= code_of(xs[e], as[e], HAS_ALPHA, R, zp, a.qmin, a.qmax) << ((v * 4 + e) * SBITS);
-                ++col;
-            }
+        for (int o = 1; o < G; o <<= 1) {
+            p0 |= __shfl_xor_sync(0xffffffffu, p0, o);
+            p1 |= __shfl_xor_sync(0xffffffffu, p1, o);
         }
-        reinterpret_cast<uint32_t*>(a.packed)[t] = word;
+        if ((lane & (G - 1)) == 0) {
+            if (v0) out[i / G] = p0;
+            if (v1) out[j / G] = p1;
+        }
+        c0.next(); c1.next();
     }
 }
 
@@ -111,38 +132,27 @@ __device__ __forceinline__ float dequant_of(uint32_t u, float qmin, float zp, fl
     return __fmul_rn(__fsub_rn((float)u + qmin, zp), d);        // (x_quant - zero_point) * delta
 }
 
+// one thread = one float4 of dequantised weights; the G lanes of a word all load it (one broadcast sector)
 template <int SBITS>
 __global__ void __launch_bounds__(SSQ_THREADS)
 import_vec_kernel(ImportArgs a) {
-    constexpr int E = 32 / SBITS;
-    constexpr uint32_t MASK = (SBITS == 32) ? 0xffffffffu : ((1u << SBITS) - 1u);
-    const int64_t words = a.rows * (a.k / E);
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < words; t += stride) {
-        const uint32_t word = __ldg(reinterpret_cast<const uint32_t*>(a.packed) + t);
-        const int64_t i0 = t * E;
-        int64_t c = chan_of(i0, a.inner, a.nchan);
-        int64_t col = i0 - (i0 / a.inner) * a.inner;
-        float d = __ldg(a.delta + c), zp = __ldg(a.zp + c);
-#pragma unroll
-        for (int v = 0; v < E / 4; ++v) {
-            float ys[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                if (col >= a.inner) {
-                    col -= a.inner; c = (c + 1 == a.nchan) ? 0 : c + 1;
-                    d = __ldg(a.delta + c); zp = __ldg(a.zp + c);
-                }
-                ys[e] = dequant_of((word >> ((v * 4 + e) * SBITS)) & MASK, a.qmin, zp, d);
-                ++col;
-            }
-            if (a.in_scale) {
-                const int64_t j = (i0 + v * 4) % a.k;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) ys[e] = __fmul_rn(ys[e], __ldg(a.in_scale + j + e));
-            }
-            st_stream4(a.wq + i0 + v * 4, make_float4(ys[0], ys[1], ys[2], ys[3]));
-        }
+    constexpr int G = 8 / SBITS;
+    constexpr uint32_t MASK = (1u << SBITS) - 1u;
+    const int64_t total4 = (a.rows * a.k) >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t* __restrict__ in = reinterpret_cast<const uint32_t*>(a.packed);
+    ChanWalk cw;
+    cw.init(first, stride, a.inner >> 2, a.nchan);
+    for (int64_t i = first; i < total4; i += stride) {
+        const uint32_t bits = __ldg(in + i / G) >> ((uint32_t)(i & (G - 1)) * 4 * SBITS);
+        const float d = __ldg(a.delta + cw.c), zp = __ldg(a.zp + cw.c);
+        float4 y;
+        y.x = dequant_of(bits & MASK, a.qmin, zp, d);
+        y.y = dequant_of((bits >> SBITS) & MASK, a.qmin, zp, d);
+        y.z = dequant_of((bits >> (2 * SBITS)) & MASK, a.qmin, zp, d);
+        y.w = dequant_of((bits >> (3 * SBITS)) & MASK, a.qmin, zp, d);
+        st_stream4(a.wq + i * 4, y);
+        cw.next();
     }
 }
 
@@ -188,10 +198,11 @@ extern "C" int ssq_export_codes(const float* w, const float* alpha, const float*
     ExportArgs a{w, alpha, in_scale, delta, zero_point, packed, rows, k, inner, nchan, ssq_packed_row_bytes(k, n_bits), qmin, qmax};
     cudaStream_t st = (cudaStream_t)stream;
     const int E = 32 / sbits;
-    const bool vec = (k % E == 0) && aligned16(w) && (!alpha || aligned16(alpha)) && ((reinterpret_cast<uintptr_t>(packed) & 3u) == 0);
+    const bool vec = (k % E == 0) && (inner % 4 == 0) && !in_scale && aligned16(w) && (!alpha || aligned16(alpha)) &&
+                     ((reinterpret_cast<uintptr_t>(packed) & 3u) == 0);
     if (vec) {
-        const int64_t words = rows * (k / E);
-        const int grid = grid_for((words + SSQ_THREADS - 1) / SSQ_THREADS);
+        const int64_t total4 = (rows * k) >> 2;
+        const int grid = grid_for((total4 + SSQ_THREADS * 4 - 1) / (SSQ_THREADS * 4));
 #define SSQ_EXPORT(SB) (alpha ? export_vec_kernel<SB, true><<<grid, SSQ_THREADS, 0, st>>>(a) \
                               : export_vec_kernel<SB, false><<<grid, SSQ_THREADS, 0, st>>>(a))
         switch (sbits) { case 1: SSQ_EXPORT(1); break; case 2: SSQ_EXPORT(2); break; case 4: SSQ_EXPORT(4); break; default: SSQ_EXPORT(8); }
@@ -215,10 +226,10 @@ extern "C" int ssq_import_codes(const uint8_t* packed, const float* in_scale, co
     ImportArgs a{packed, in_scale, delta, zero_point, w_q, rows, k, inner, nchan, ssq_packed_row_bytes(k, n_bits), qmin};
     cudaStream_t st = (cudaStream_t)stream;
     const int E = 32 / sbits;
-    const bool vec = (k % E == 0) && aligned16(w_q) && ((reinterpret_cast<uintptr_t>(packed) & 3u) == 0);
+    const bool vec = (k % E == 0) && (inner % 4 == 0) && !in_scale && aligned16(w_q) && ((reinterpret_cast<uintptr_t>(packed) & 3u) == 0);
     if (vec) {
-        const int64_t words = rows * (k / E);
-        const int grid = grid_for((words + SSQ_THREADS - 1) / SSQ_THREADS);
+        const int64_t total4 = (rows * k) >> 2;
+        const int grid = grid_for((total4 + SSQ_THREADS * 2 - 1) / (SSQ_THREADS * 2));
         switch (sbits) {
             case 1: import_vec_kernel<1><<<grid, SSQ_THREADS, 0, st>>>(a); break;
             case 2: import_vec_kernel<2><<<grid, SSQ_THREADS, 0, st>>>(a); break;

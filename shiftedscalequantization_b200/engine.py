@@ -549,10 +549,18 @@ class AutogradReconEngine:
             return
         if self.use_graph and self.graph is None:
             self.capture()
+        self._t0, self._t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self._t0.record()
         for i in range(self.iters):
             self.step()
             if on_report is not None and i % every == 0:
                 on_report(i)
+        self._t1.record()
+
+    def loop_ms(self) -> float:
+        """device time of the last run()'s iteration loop (capture excluded); synchronises"""
+        self._t1.synchronize()
+        return self._t0.elapsed_time(self._t1)
 
     def close(self):
         for q, flag in self._frozen:

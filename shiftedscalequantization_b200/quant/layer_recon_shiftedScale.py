@@ -138,6 +138,7 @@ def _act_delta_params(unit):
 
 
 USE_CAPTURED_LOOP = True      # False: the eager autograd loop below (kept as the behavioural cross-check)
+LAST_LOOP_STATS = {}          # {'iters', 'loop_ms', 'captured', 'launches_per_iter'} of the most recent loop (bench.py reads it)
 
 
 def _run_captured(unit, loss_func, slots, lr_table, b_tables, reg_fn, cached_inp, cached_out, iters, batch_size, describe,
@@ -171,6 +172,8 @@ def _run_captured(unit, loss_func, slots, lr_table, b_tables, reg_fn, cached_inp
         sync_loss_object()
     loss_func.count += iters
     bar.close()
+    if iters > 0:
+        LAST_LOOP_STATS.update(iters=iters, loop_ms=eng.loop_ms(), captured=True, launches_per_iter=eng.launches_per_iter)
     eng.close()
     return state['start'], eng
 
@@ -178,6 +181,8 @@ def _run_captured(unit, loss_func, slots, lr_table, b_tables, reg_fn, cached_inp
 def _run_loop(unit, loss_func, optimizer, scheduler, cached_inp, cached_out, iters, batch_size, describe):
     start_loss = 0.0
     bar = tqdm(range(iters), desc='', dynamic_ncols=True)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
     for i in bar:
         perm = torch.randperm(cached_inp.size(0))[:batch_size]
         cur_inp, cur_out = cached_inp[perm], cached_out[perm]
@@ -190,6 +195,10 @@ def _run_loop(unit, loss_func, optimizer, scheduler, cached_inp, cached_out, ite
         if i % 500 == 0:
             start_loss = max(start_loss, loss_func.rec_loss)
             bar.set_description(describe(start_loss, loss_func))
+    t1.record()
+    if iters > 0:
+        t1.synchronize()
+        LAST_LOOP_STATS.update(iters=iters, loop_ms=t0.elapsed_time(t1), captured=False, launches_per_iter=None)
     return start_loss
 
 
