@@ -202,9 +202,9 @@ extern "C" int ssq_export_codes(const float* w, const float* alpha, const float*
                      ((reinterpret_cast<uintptr_t>(packed) & 3u) == 0);
     if (vec) {
         const int64_t total4 = (rows * k) >> 2;
-        const int grid = grid_for((total4 + SSQ_THREADS * 4 - 1) / (SSQ_THREADS * 4));
-#define SSQ_EXPORT(SB) (alpha ? export_vec_kernel<SB, true><<<grid, SSQ_THREADS, 0, st>>>(a) \
-                              : export_vec_kernel<SB, false><<<grid, SSQ_THREADS, 0, st>>>(a))
+        const int64_t want = (total4 + SSQ_THREADS * 4 - 1) / (SSQ_THREADS * 4);
+#define SSQ_EXPORT(SB) (alpha ? export_vec_kernel<SB, true><<<grid_for(want, ctas_per_sm(export_vec_kernel<SB, true>)), SSQ_THREADS, 0, st>>>(a) \
+                              : export_vec_kernel<SB, false><<<grid_for(want, ctas_per_sm(export_vec_kernel<SB, false>)), SSQ_THREADS, 0, st>>>(a))
         switch (sbits) { case 1: SSQ_EXPORT(1); break; case 2: SSQ_EXPORT(2); break; case 4: SSQ_EXPORT(4); break; default: SSQ_EXPORT(8); }
 #undef SSQ_EXPORT
     } else {

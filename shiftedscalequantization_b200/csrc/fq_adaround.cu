@@ -333,9 +333,8 @@ extern "C" int ssq_fq_adaround_fwd(const float* w, const float* alpha, const flo
     bool vec = aligned16(w) && aligned16(alpha) && aligned16(wq) && (!codes || aligned16(codes)) && (inner % 4 == 0) &&
                (n / 4 < (int64_t)0x7fffffff);
     int64_t per_cta = (int64_t)SSQ_THREADS * (vec ? 8 : 1);
-    int grid = grid_for((n + per_cta - 1) / per_cta);
     WsView v = ws_view(ws, 1);
-#define LAUNCH(S, R) ada_fwd_kernel<S, R><<<grid, SSQ_THREADS, 0, st>>>( \
+#define LAUNCH(S, R) ada_fwd_kernel<S, R><<<grid_for((n + per_cta - 1) / per_cta, ctas_per_sm(ada_fwd_kernel<S, R>)), SSQ_THREADS, 0, st>>>( \
         w, alpha, delta, zero_point, wq, codes, n, inner, nchan, qmin, qmax, vec, b_dev, lambda, reg_out, v)
     if (soft) { if (reg) LAUNCH(true, true); else LAUNCH(true, false); }
     else LAUNCH(false, false);
@@ -354,7 +353,7 @@ extern "C" int ssq_fq_adaround_bwd(const float* gwq, const float* w, const float
     bool vec = (!gwq || aligned16(gwq)) && aligned16(w) && aligned16(alpha) && aligned16(galpha) && (inner % 4 == 0) &&
                (n / 4 < (int64_t)0x7fffffff);
     int64_t per_cta = (int64_t)SSQ_THREADS * (vec ? 8 : 1);
-    int grid = grid_for((n + per_cta - 1) / per_cta);
+    int grid = grid_for((n + per_cta - 1) / per_cta, ctas_per_sm(ada_bwd_kernel));
     ada_bwd_kernel<<<grid, SSQ_THREADS, 0, (cudaStream_t)stream>>>(gwq, w, alpha, delta, zero_point, galpha, n, inner, nchan,
                                                                    qmin, qmax, vec, b_dev, lambda, greg, accumulate);
     return launch_status();
@@ -398,13 +397,12 @@ extern "C" int ssq_fq_adaround_fwd_mt(const ssq_adaround_desc* table, int count,
     if (count < 0 || count > SSQ_MT_MAX || total_tiles < 0) return SSQ_ERR_SIZE;
     if (reg_out && (!ws || ws_bytes < ssq_ws_bytes(1))) return SSQ_ERR_WORKSPACE;
     if (reg_out && !b_dev) return SSQ_ERR_MODE;
-    int grid = grid_for(total_tiles);
     WsView v = ws_view(ws, 1);
     cudaStream_t st = (cudaStream_t)stream;
     MtTable t;
     for (int i = 0; i < count; ++i) t.d[i] = table[i];
-    if (soft) ada_fwd_mt_kernel<true><<<grid, SSQ_THREADS, 0, st>>>(t, count, total_tiles, b_dev, lambda, reg_out, v);
-    else ada_fwd_mt_kernel<false><<<grid, SSQ_THREADS, 0, st>>>(t, count, total_tiles, b_dev, lambda, nullptr, v);
+    if (soft) ada_fwd_mt_kernel<true><<<grid_for(total_tiles, ctas_per_sm(ada_fwd_mt_kernel<true>)), SSQ_THREADS, 0, st>>>(t, count, total_tiles, b_dev, lambda, reg_out, v);
+    else ada_fwd_mt_kernel<false><<<grid_for(total_tiles, ctas_per_sm(ada_fwd_mt_kernel<false>)), SSQ_THREADS, 0, st>>>(t, count, total_tiles, b_dev, lambda, nullptr, v);
     return launch_status();
 }
 
@@ -413,7 +411,7 @@ extern "C" int ssq_fq_adaround_bwd_mt(const ssq_adaround_desc* table, int count,
     if (count == 0 || total_tiles == 0) return SSQ_OK;
     if (!table) return SSQ_ERR_NULL;
     if (count < 0 || count > SSQ_MT_MAX || total_tiles < 0) return SSQ_ERR_SIZE;
-    int grid = grid_for(total_tiles);
+    int grid = grid_for(total_tiles, ctas_per_sm(ada_bwd_mt_kernel));
     MtTable t;
     for (int i = 0; i < count; ++i) t.d[i] = table[i];
     ada_bwd_mt_kernel<<<grid, SSQ_THREADS, 0, (cudaStream_t)stream>>>(t, count, total_tiles, b_dev, lambda);

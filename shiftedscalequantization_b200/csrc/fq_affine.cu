@@ -245,9 +245,8 @@ extern "C" int ssq_fq_affine_fwd(const float* x, const float* delta, const float
     if (vec) {
         uint32_t n4 = (uint32_t)(n / 4), inner4 = (uint32_t)(inner / 4);
         int64_t ctas = ((int64_t)n4 + SSQ_THREADS * UNROLL - 1) / (SSQ_THREADS * UNROLL);
-        int grid = grid_for(ctas);
         bool per_tensor = (nchan == 1 && !in_scale);
-#define LAUNCH(CH, IS, CO) fq_affine_fwd_vec<CH, IS, CO><<<grid, SSQ_THREADS, 0, st>>>( \
+#define LAUNCH(CH, IS, CO) fq_affine_fwd_vec<CH, IS, CO><<<grid_for(ctas, ctas_per_sm(fq_affine_fwd_vec<CH, IS, CO>)), SSQ_THREADS, 0, st>>>( \
         x, delta, zero_point, in_scale, y, codes, n4, inner4, (uint32_t)nchan, qmin, qmax)
         if (per_tensor) { if (codes) LAUNCH(0, false, true); else LAUNCH(0, false, false); }
         else if (in_scale) { if (codes) LAUNCH(1, true, true); else LAUNCH(1, true, false); }

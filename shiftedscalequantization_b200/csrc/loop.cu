@@ -112,7 +112,7 @@ extern "C" int ssq_adam_step(float* param, const float* grad, float* exp_avg, fl
     if (n == 0) return SSQ_OK;
     if (!param || !grad || !exp_avg || !exp_avg_sq || !lr_dev || !step_dev) return SSQ_ERR_NULL;
     if (n < 0) return SSQ_ERR_SIZE;
-    int grid = grid_for((n + SSQ_THREADS * 4 - 1) / (SSQ_THREADS * 4));
+    int grid = grid_for((n + SSQ_THREADS * 4 - 1) / (SSQ_THREADS * 4), ctas_per_sm(adam_kernel));
     adam_kernel<<<grid, SSQ_THREADS, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr_dev, beta1, beta2, eps, step_dev);
     return launch_status();
 }

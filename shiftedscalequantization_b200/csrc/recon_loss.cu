@@ -35,7 +35,7 @@ recon_loss_kernel(LossArgs a, WsView ws) {
             term = d * d;
             if (GRAD) go = (inv * (2.0f * ad)) * sgnf(d);
         } else if (MODE == 2) {
-            const float l2 = log2_pos(ad);
+            const float l2 = log2_for_pow(ad);
             term = ex2_approx(p * l2);
             if (GRAD) go = (inv * (p * ex2_approx(pm1 * l2))) * sgnf(d);
         } else {
@@ -174,7 +174,7 @@ static int launch_loss(LossArgs a, int mode, bool fwd, void* ws, size_t ws_bytes
     int grid = grid_for((total + per_cta - 1) / per_cta);
     WsView v = ws_view(ws, 1);
     const bool grad = a.dpred != nullptr;
-#define L(M, V, G, F) recon_loss_kernel<M, V, G, F><<<grid, SSQ_THREADS, 0, st>>>(a, v)
+#define L(M, V, G, F) recon_loss_kernel<M, V, G, F><<<grid_for((total + per_cta - 1) / per_cta, ctas_per_sm(recon_loss_kernel<M, V, G, F>)), SSQ_THREADS, 0, st>>>(a, v)
 #define LM(M) do { if (vec) { if (fwd) { if (grad) L(M, true, true, true); else L(M, true, false, true); } \
                               else L(M, true, true, false); } \
                    else { if (fwd) { if (grad) L(M, false, true, true); else L(M, false, false, true); } \
@@ -212,7 +212,7 @@ extern "C" int ssq_gather_rows(const float* src, const int64_t* index, float* ds
     bool vec = (per_sample % 4 == 0) && aligned16(src) && aligned16(dst);
     int64_t total = batch * per_sample;
     int64_t per_cta = (int64_t)SSQ_THREADS * (vec ? 4 : 1) * 2;
-    int grid = grid_for((total + per_cta - 1) / per_cta);
+    int grid = grid_for((total + per_cta - 1) / per_cta, ctas_per_sm(gather_rows_kernel));
     gather_rows_kernel<<<grid, SSQ_THREADS, 0, (cudaStream_t)stream>>>(src, index, dst, batch, per_sample, vec);
     return launch_status();
 }
