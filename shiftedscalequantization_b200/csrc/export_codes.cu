@@ -43,7 +43,7 @@ __device__ __forceinline__ int64_t chan_of(int64_t i, int64_t inner, int64_t nch
 // instruction of a warp is one contiguous 512-byte run. G = 8/SBITS neighbouring lanes hold the pieces of one 32-bit
 // word of codes: they are OR-ed together with a shuffle butterfly and lane 0 of the group stores the word.
 // Needs k % (32/SBITS) == 0 (rows are whole words) and inner % 4 == 0 (a float4 never straddles two channels);
-// the channel of a vector is tracked with adds/compares (ChanWalk), no division in the loop.
+// tiles are address-ordered (ssq_common.cuh), the channel of a vector comes from TileWalk.
 template <int SBITS, bool HAS_ALPHA>
 __device__ __forceinline__ uint32_t pack4(const float4& x, const float4& al, float d, float zp, float qmin, float qmax) {
     const Recip R = make_recip(d);
@@ -67,34 +67,31 @@ template <int SBITS, bool HAS_ALPHA>
 __global__ void __launch_bounds__(SSQ_THREADS)
 export_vec_kernel(ExportArgs a) {
     constexpr int G = 8 / SBITS;                 // lanes per output word: 8, 4, 2, 1
-    const int64_t total4 = (a.rows * a.k) >> 2;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x, first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int U = 4;                         // float4s per thread; one address-ordered tile of 256*U per CTA
+    const int64_t total4 = (a.rows * a.k) >> 2;  // a multiple of G (rows are whole words), so a lane group is all-in or all-out
+    const int64_t i0 = (int64_t)blockIdx.x * (SSQ_THREADS * U) + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int sh = (lane & (G - 1)) * 4 * SBITS;
     uint32_t* __restrict__ out = reinterpret_cast<uint32_t*>(a.packed);
-    ChanWalk c0, c1;                             // two vectors in flight per thread: i and i + stride
-    c0.init(first, 2 * stride, a.inner >> 2, a.nchan);
-    c1.init(first + stride, 2 * stride, a.inner >> 2, a.nchan);
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t i = first; i - lane < total4; i += 2 * stride) {    // warp-uniform trip count: shuffles need every lane
-        const int64_t j = i + stride;
-        const bool v0 = i < total4, v1 = j < total4;
-        float4 x0 = zero4, x1 = zero4, a0 = zero4, a1 = zero4;
-        if (v0) { x0 = ld_stream4(a.w + i * 4); if (HAS_ALPHA) a0 = ld_stream4(a.alpha + i * 4); }
-        if (v1) { x1 = ld_stream4(a.w + j * 4); if (HAS_ALPHA) a1 = ld_stream4(a.alpha + j * 4); }
-        uint32_t p0 = 0, p1 = 0;
-        if (v0) p0 = pack4<SBITS, HAS_ALPHA>(x0, a0, __ldg(a.delta + c0.c), __ldg(a.zp + c0.c), a.qmin, a.qmax) << sh;
-        if (v1) p1 = pack4<SBITS, HAS_ALPHA>(x1, a1, __ldg(a.delta + c1.c), __ldg(a.zp + c1.c), a.qmin, a.qmax) << sh;
+    float4 x[U], al[U];
 #pragma unroll
-        for (int o = 1; o < G; o <<= 1) {
-            p0 |= __shfl_xor_sync(0xffffffffu, p0, o);
-            p1 |= __shfl_xor_sync(0xffffffffu, p1, o);
-        }
-        if ((lane & (G - 1)) == 0) {
-            if (v0) out[i / G] = p0;
-            if (v1) out[j / G] = p1;
-        }
-        c0.next(); c1.next();
+    for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + (int64_t)u * SSQ_THREADS;
+        x[u] = al[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < total4) { x[u] = ld_stream4(a.w + i * 4); if (HAS_ALPHA) al[u] = ld_stream4(a.alpha + i * 4); }
+    }
+    TileWalk tw;
+    tw.init((uint64_t)i0, (uint64_t)(a.inner >> 2), (uint64_t)a.nchan);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + (int64_t)u * SSQ_THREADS;
+        uint32_t piece = 0;
+        if (i < total4)
+            piece = pack4<SBITS, HAS_ALPHA>(x[u], al[u], __ldg(a.delta + tw.c), __ldg(a.zp + tw.c), a.qmin, a.qmax) << sh;
+#pragma unroll
+        for (int o = 1; o < G; o <<= 1) piece |= __shfl_xor_sync(0xffffffffu, piece, o);
+        if (i < total4 && (lane & (G - 1)) == 0) out[i / G] = piece;
+        tw.step(SSQ_THREADS);
     }
 }
 
@@ -137,22 +134,32 @@ template <int SBITS>
 __global__ void __launch_bounds__(SSQ_THREADS)
 import_vec_kernel(ImportArgs a) {
     constexpr int G = 8 / SBITS;
+    constexpr int U = 4;
     constexpr uint32_t MASK = (1u << SBITS) - 1u;
     const int64_t total4 = (a.rows * a.k) >> 2;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x, first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i0 = (int64_t)blockIdx.x * (SSQ_THREADS * U) + threadIdx.x;
     const uint32_t* __restrict__ in = reinterpret_cast<const uint32_t*>(a.packed);
-    ChanWalk cw;
-    cw.init(first, stride, a.inner >> 2, a.nchan);
-    for (int64_t i = first; i < total4; i += stride) {
-        const uint32_t bits = __ldg(in + i / G) >> ((uint32_t)(i & (G - 1)) * 4 * SBITS);
-        const float d = __ldg(a.delta + cw.c), zp = __ldg(a.zp + cw.c);
-        float4 y;
-        y.x = dequant_of(bits & MASK, a.qmin, zp, d);
-        y.y = dequant_of((bits >> SBITS) & MASK, a.qmin, zp, d);
-        y.z = dequant_of((bits >> (2 * SBITS)) & MASK, a.qmin, zp, d);
-        y.w = dequant_of((bits >> (3 * SBITS)) & MASK, a.qmin, zp, d);
-        st_stream4(a.wq + i * 4, y);
-        cw.next();
+    uint32_t bits[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + (int64_t)u * SSQ_THREADS;
+        bits[u] = (i < total4) ? __ldg(in + i / G) >> ((uint32_t)(i & (G - 1)) * 4 * SBITS) : 0u;
+    }
+    TileWalk tw;
+    tw.init((uint64_t)i0, (uint64_t)(a.inner >> 2), (uint64_t)a.nchan);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + (int64_t)u * SSQ_THREADS;
+        if (i < total4) {
+            const float d = __ldg(a.delta + tw.c), zp = __ldg(a.zp + tw.c);
+            float4 y;
+            y.x = dequant_of(bits[u] & MASK, a.qmin, zp, d);
+            y.y = dequant_of((bits[u] >> SBITS) & MASK, a.qmin, zp, d);
+            y.z = dequant_of((bits[u] >> (2 * SBITS)) & MASK, a.qmin, zp, d);
+            y.w = dequant_of((bits[u] >> (3 * SBITS)) & MASK, a.qmin, zp, d);
+            st_stream4(a.wq + i * 4, y);
+        }
+        tw.step(SSQ_THREADS);
     }
 }
 
@@ -202,9 +209,9 @@ extern "C" int ssq_export_codes(const float* w, const float* alpha, const float*
                      ((reinterpret_cast<uintptr_t>(packed) & 3u) == 0);
     if (vec) {
         const int64_t total4 = (rows * k) >> 2;
-        const int64_t want = (total4 + SSQ_THREADS * 4 - 1) / (SSQ_THREADS * 4);
-#define SSQ_EXPORT(SB) (alpha ? export_vec_kernel<SB, true><<<grid_for(want, ctas_per_sm(export_vec_kernel<SB, true>)), SSQ_THREADS, 0, st>>>(a) \
-                              : export_vec_kernel<SB, false><<<grid_for(want, ctas_per_sm(export_vec_kernel<SB, false>)), SSQ_THREADS, 0, st>>>(a))
+        const unsigned grid = tile_grid((total4 + SSQ_THREADS * 4 - 1) / (SSQ_THREADS * 4), false);
+#define SSQ_EXPORT(SB) (alpha ? export_vec_kernel<SB, true><<<grid, SSQ_THREADS, 0, st>>>(a) \
+                              : export_vec_kernel<SB, false><<<grid, SSQ_THREADS, 0, st>>>(a))
         switch (sbits) { case 1: SSQ_EXPORT(1); break; case 2: SSQ_EXPORT(2); break; case 4: SSQ_EXPORT(4); break; default: SSQ_EXPORT(8); }
 #undef SSQ_EXPORT
     } else {
@@ -229,7 +236,7 @@ extern "C" int ssq_import_codes(const uint8_t* packed, const float* in_scale, co
     const bool vec = (k % E == 0) && (inner % 4 == 0) && !in_scale && aligned16(w_q) && ((reinterpret_cast<uintptr_t>(packed) & 3u) == 0);
     if (vec) {
         const int64_t total4 = (rows * k) >> 2;
-        const int grid = grid_for((total4 + SSQ_THREADS * 2 - 1) / (SSQ_THREADS * 2));
+        const unsigned grid = tile_grid((total4 + SSQ_THREADS * 4 - 1) / (SSQ_THREADS * 4), false);
         switch (sbits) {
             case 1: import_vec_kernel<1><<<grid, SSQ_THREADS, 0, st>>>(a); break;
             case 2: import_vec_kernel<2><<<grid, SSQ_THREADS, 0, st>>>(a); break;

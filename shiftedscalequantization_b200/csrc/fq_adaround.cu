@@ -158,19 +158,25 @@ __device__ __forceinline__ void ada_bwd_span(const float* __restrict__ gwq, cons
 }
 
 // ---- single tensor ----------------------------------------------------------------------------------------
+#define SSQ_ST_TILE 8192      // elements per tile: 2048 float4s, 8 per thread, taken two at a time
 template <bool SOFT, bool REG>
 __global__ void __launch_bounds__(SSQ_THREADS, 4)
 ada_fwd_kernel(const float* __restrict__ w, const float* __restrict__ alpha, const float* __restrict__ delta,
                const float* __restrict__ zp, float* __restrict__ wq, float* __restrict__ codes,
                int64_t n, int64_t inner, int64_t nchan, float qmin, float qmax, bool vec,
-               const float* __restrict__ b_dev, float lambda, float* __restrict__ reg_out, WsView ws) {
+               const float* __restrict__ b_dev, float lambda, float* __restrict__ reg_out, WsView ws, int tiles_per_cta) {
     __shared__ double smem[32];
     const float b = REG ? __ldg(b_dev) : 0.f;
     const bool reg_on = REG && (b > 0.f);
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
-    double acc[1];
-    acc[0] = reg_on ? ada_fwd_span<SOFT, true>(w, alpha, delta, zp, wq, codes, 0, n, inner, nchan, qmin, qmax, b, tid, nthr, vec)
-                    : ada_fwd_span<SOFT, false>(w, alpha, delta, zp, wq, codes, 0, n, inner, nchan, qmin, qmax, b, tid, nthr, vec);
+    double acc[1] = {0.0};
+    const int64_t ntiles = (n + SSQ_ST_TILE - 1) / SSQ_ST_TILE;
+    const int64_t t0 = (int64_t)blockIdx.x * tiles_per_cta;                    // address-ordered tiles (ssq_common.cuh)
+    const int64_t t1 = t0 + tiles_per_cta < ntiles ? t0 + tiles_per_cta : ntiles;
+    for (int64_t tile = t0; tile < t1; ++tile) {
+        const int64_t e0 = tile * SSQ_ST_TILE, e1 = e0 + SSQ_ST_TILE < n ? e0 + SSQ_ST_TILE : n;
+        acc[0] += reg_on ? ada_fwd_span<SOFT, true>(w, alpha, delta, zp, wq, codes, e0, e1, inner, nchan, qmin, qmax, b, threadIdx.x, blockDim.x, vec)
+                         : ada_fwd_span<SOFT, false>(w, alpha, delta, zp, wq, codes, e0, e1, inner, nchan, qmin, qmax, b, threadIdx.x, blockDim.x, vec);
+    }
     if (!REG) return;
     block_sum<1>(acc, smem);
     if (grid_finish<1>(acc, ws, 0, blockIdx.x, gridDim.x, smem) && threadIdx.x == 0)
@@ -185,13 +191,17 @@ ada_bwd_kernel(const float* __restrict__ gwq, const float* __restrict__ w, const
     const float b = b_dev ? __ldg(b_dev) : 0.f;
     const bool reg_on = b_dev && (b > 0.f);
     const float lam_g = reg_on ? lambda * (greg ? __ldg(greg) : 1.f) : 0.f;
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
-    if (gwq) {
-        if (reg_on) ada_bwd_span<true, true>(gwq, w, alpha, delta, zp, galpha, 0, n, inner, nchan, qmin, qmax, b, lam_g, accumulate, tid, nthr, vec);
-        else ada_bwd_span<true, false>(gwq, w, alpha, delta, zp, galpha, 0, n, inner, nchan, qmin, qmax, b, lam_g, accumulate, tid, nthr, vec);
-    } else {
-        if (reg_on) ada_bwd_span<false, true>(gwq, w, alpha, delta, zp, galpha, 0, n, inner, nchan, qmin, qmax, b, lam_g, accumulate, tid, nthr, vec);
-        else ada_bwd_span<false, false>(gwq, w, alpha, delta, zp, galpha, 0, n, inner, nchan, qmin, qmax, b, lam_g, accumulate, tid, nthr, vec);
+    const int64_t ntiles = (n + SSQ_ST_TILE - 1) / SSQ_ST_TILE;
+    const int64_t tid = threadIdx.x, nthr = blockDim.x;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t e0 = tile * SSQ_ST_TILE, e1 = e0 + SSQ_ST_TILE < n ? e0 + SSQ_ST_TILE : n;
+        if (gwq) {
+            if (reg_on) ada_bwd_span<true, true>(gwq, w, alpha, delta, zp, galpha, e0, e1, inner, nchan, qmin, qmax, b, lam_g, accumulate, tid, nthr, vec);
+            else ada_bwd_span<true, false>(gwq, w, alpha, delta, zp, galpha, e0, e1, inner, nchan, qmin, qmax, b, lam_g, accumulate, tid, nthr, vec);
+        } else {
+            if (reg_on) ada_bwd_span<false, true>(gwq, w, alpha, delta, zp, galpha, e0, e1, inner, nchan, qmin, qmax, b, lam_g, accumulate, tid, nthr, vec);
+            else ada_bwd_span<false, false>(gwq, w, alpha, delta, zp, galpha, e0, e1, inner, nchan, qmin, qmax, b, lam_g, accumulate, tid, nthr, vec);
+        }
     }
 }
 
@@ -332,10 +342,12 @@ extern "C" int ssq_fq_adaround_fwd(const float* w, const float* alpha, const flo
     cudaStream_t st = (cudaStream_t)stream;
     bool vec = aligned16(w) && aligned16(alpha) && aligned16(wq) && (!codes || aligned16(codes)) && (inner % 4 == 0) &&
                (n / 4 < (int64_t)0x7fffffff);
-    int64_t per_cta = (int64_t)SSQ_THREADS * (vec ? 8 : 1);
+    const int64_t ntiles = (n + SSQ_ST_TILE - 1) / SSQ_ST_TILE;
     WsView v = ws_view(ws, 1);
-#define LAUNCH(S, R) ada_fwd_kernel<S, R><<<grid_for((n + per_cta - 1) / per_cta, ctas_per_sm(ada_fwd_kernel<S, R>)), SSQ_THREADS, 0, st>>>( \
-        w, alpha, delta, zero_point, wq, codes, n, inner, nchan, qmin, qmax, vec, b_dev, lambda, reg_out, v)
+    int per_cta = 1;
+    const unsigned grid = reg ? tile_grid_balanced(ntiles, per_cta) : tile_grid(ntiles, false);
+#define LAUNCH(S, R) ada_fwd_kernel<S, R><<<grid, SSQ_THREADS, 0, st>>>( \
+        w, alpha, delta, zero_point, wq, codes, n, inner, nchan, qmin, qmax, vec, b_dev, lambda, reg_out, v, per_cta)
     if (soft) { if (reg) LAUNCH(true, true); else LAUNCH(true, false); }
     else LAUNCH(false, false);
 #undef LAUNCH
@@ -352,8 +364,7 @@ extern "C" int ssq_fq_adaround_bwd(const float* gwq, const float* w, const float
     if (int e = check_layout(n, inner, nchan)) return e;
     bool vec = (!gwq || aligned16(gwq)) && aligned16(w) && aligned16(alpha) && aligned16(galpha) && (inner % 4 == 0) &&
                (n / 4 < (int64_t)0x7fffffff);
-    int64_t per_cta = (int64_t)SSQ_THREADS * (vec ? 8 : 1);
-    int grid = grid_for((n + per_cta - 1) / per_cta, ctas_per_sm(ada_bwd_kernel));
+    const unsigned grid = tile_grid((n + SSQ_ST_TILE - 1) / SSQ_ST_TILE, false);
     ada_bwd_kernel<<<grid, SSQ_THREADS, 0, (cudaStream_t)stream>>>(gwq, w, alpha, delta, zero_point, galpha, n, inner, nchan,
                                                                    qmin, qmax, vec, b_dev, lambda, greg, accumulate);
     return launch_status();
@@ -401,8 +412,8 @@ extern "C" int ssq_fq_adaround_fwd_mt(const ssq_adaround_desc* table, int count,
     cudaStream_t st = (cudaStream_t)stream;
     MtTable t;
     for (int i = 0; i < count; ++i) t.d[i] = table[i];
-    if (soft) ada_fwd_mt_kernel<true><<<grid_for(total_tiles, ctas_per_sm(ada_fwd_mt_kernel<true>)), SSQ_THREADS, 0, st>>>(t, count, total_tiles, b_dev, lambda, reg_out, v);
-    else ada_fwd_mt_kernel<false><<<grid_for(total_tiles, ctas_per_sm(ada_fwd_mt_kernel<false>)), SSQ_THREADS, 0, st>>>(t, count, total_tiles, b_dev, lambda, nullptr, v);
+    if (soft) ada_fwd_mt_kernel<true><<<tile_grid(total_tiles, reg_out != nullptr), SSQ_THREADS, 0, st>>>(t, count, total_tiles, b_dev, lambda, reg_out, v);
+    else ada_fwd_mt_kernel<false><<<tile_grid(total_tiles, false), SSQ_THREADS, 0, st>>>(t, count, total_tiles, b_dev, lambda, nullptr, v);
     return launch_status();
 }
 
@@ -411,7 +422,7 @@ extern "C" int ssq_fq_adaround_bwd_mt(const ssq_adaround_desc* table, int count,
     if (count == 0 || total_tiles == 0) return SSQ_OK;
     if (!table) return SSQ_ERR_NULL;
     if (count < 0 || count > SSQ_MT_MAX || total_tiles < 0) return SSQ_ERR_SIZE;
-    int grid = grid_for(total_tiles, ctas_per_sm(ada_bwd_mt_kernel));
+    const unsigned grid = tile_grid(total_tiles, false);
     MtTable t;
     for (int i = 0; i < count; ++i) t.d[i] = table[i];
     ada_bwd_mt_kernel<<<grid, SSQ_THREADS, 0, (cudaStream_t)stream>>>(t, count, total_tiles, b_dev, lambda);

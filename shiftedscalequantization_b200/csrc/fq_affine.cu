@@ -1,7 +1,7 @@
 // K1a — uniform affine fake-quant forward / STE backward, and the per-output-channel activation affine.
-// HBM-bound streaming kernels: 128-bit loads/stores, several vectors in flight per thread, persistent grid of
-// 148 SMs x 8 CTAs, channel index tracked incrementally (no integer division in the loop), reciprocal of delta
-// hoisted per vector.
+// HBM-bound streaming kernels: 128-bit loads/stores, several vectors in flight per thread, address-ordered tiles
+// (forward) / per-channel slabs (backward), no integer division in the element loop, reciprocal of delta hoisted
+// per vector.
 //   reference arithmetic: quant/quant_layer.py:92-97, quant/channelQuantMSE.py:134-143,
 //   quant/channelQuant.py:79-94, quant/quant_layer.py:258-259
 #include "ssq_common.cuh"
@@ -29,49 +29,55 @@ __device__ __forceinline__ float fq_one_inscale(float x, float s, const Recip& R
 
 constexpr int UNROLL = 4;
 
-// CHAN: 0 = per-tensor (nchan==1), 1 = per-channel with inner % 4 == 0
+// Vector path. One CTA = one contiguous run of 256*UNROLL float4s (16 KB); CTAs are dispatched in address order by the
+// hardware scheduler, so the set of DRAM pages being streamed stays compact and there is no persistent-grid drift or
+// ragged last wave (measured on B200: 6.75-6.8 TB/s against 5.3-6.4 TB/s for the same loop body under a persistent
+// 148 x k grid-stride grid, and 6.5 TB/s for torch's copy). The channel of a thread's first vector costs one 32-bit
+// division; its other vectors step by 256 with compares.
+// CHAN: 0 = per-tensor (nchan == 1), 1 = per-channel with inner % 4 == 0
 template <int CHAN, bool INSCALE, bool CODES>
 __global__ void __launch_bounds__(SSQ_THREADS)
 fq_affine_fwd_vec(const float* __restrict__ x, const float* __restrict__ delta, const float* __restrict__ zp,
                   const float* __restrict__ in_scale, float* __restrict__ y, float* __restrict__ codes,
                   uint32_t n4, uint32_t inner4, uint32_t nchan, float qmin, float qmax) {
-    const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t first = blockIdx.x * blockDim.x + threadIdx.x;
-    Recip R0; float z0 = 0.f;
-    if (CHAN == 0) { R0 = make_recip(__ldg(delta)); z0 = __ldg(zp); }
-    ChanWalk cw;
-    if (CHAN == 1) cw.init(first, stride, inner4, nchan);
-    for (uint32_t base = first; base < n4; base += stride * UNROLL) {
-        float4 v[UNROLL];
+    const uint32_t base = blockIdx.x * (SSQ_THREADS * UNROLL) + threadIdx.x;
+    float4 v[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            uint32_t i = base + u * stride;
-            if (i < n4) v[u] = ld_stream4(x + (size_t)i * 4);
+    for (int u = 0; u < UNROLL; ++u) {
+        const uint32_t i = base + u * SSQ_THREADS;
+        if (i < n4) v[u] = ld_stream4(x + (size_t)i * 4);
+    }
+    Recip R; float z;
+    uint32_t c = 0, col = 0;
+    if (CHAN == 0) { R = make_recip(__ldg(delta)); z = __ldg(zp); }
+    else { c = base / inner4; col = base - c * inner4; c %= nchan; }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+        const uint32_t i = base + u * SSQ_THREADS;
+        uint32_t mycol = 0;
+        if (CHAN == 1) {
+            while (col >= inner4) { col -= inner4; c = (c + 1 == nchan) ? 0 : c + 1; }
+            R = make_recip(__ldg(delta + c)); z = __ldg(zp + c);
+            mycol = col;
+            col += SSQ_THREADS;
         }
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            uint32_t i = base + u * stride;
-            if (i < n4) {
-                Recip R = R0; float z = z0;
-                float4 q, o;
-                if (CHAN == 1) { R = make_recip(__ldg(delta + cw.c)); z = __ldg(zp + cw.c); }
-                if (INSCALE) {
-                    const float4 s = __ldg(reinterpret_cast<const float4*>(in_scale) + cw.col);
-                    o.x = fq_one_inscale(v[u].x, s.x, R, z, qmin, qmax, q.x);
-                    o.y = fq_one_inscale(v[u].y, s.y, R, z, qmin, qmax, q.y);
-                    o.z = fq_one_inscale(v[u].z, s.z, R, z, qmin, qmax, q.z);
-                    o.w = fq_one_inscale(v[u].w, s.w, R, z, qmin, qmax, q.w);
-                } else {
-                    const float4 t = div4_exact(v[u], R);
-                    o.x = fq_post(t.x, R.d, z, qmin, qmax, q.x);
-                    o.y = fq_post(t.y, R.d, z, qmin, qmax, q.y);
-                    o.z = fq_post(t.z, R.d, z, qmin, qmax, q.z);
-                    o.w = fq_post(t.w, R.d, z, qmin, qmax, q.w);
-                }
-                st_stream4(y + (size_t)i * 4, o);
-                if (CODES) st_stream4(codes + (size_t)i * 4, q);
+        if (i < n4) {
+            float4 q, o;
+            if (INSCALE) {
+                const float4 s = __ldg(reinterpret_cast<const float4*>(in_scale) + mycol);
+                o.x = fq_one_inscale(v[u].x, s.x, R, z, qmin, qmax, q.x);
+                o.y = fq_one_inscale(v[u].y, s.y, R, z, qmin, qmax, q.y);
+                o.z = fq_one_inscale(v[u].z, s.z, R, z, qmin, qmax, q.z);
+                o.w = fq_one_inscale(v[u].w, s.w, R, z, qmin, qmax, q.w);
+            } else {
+                const float4 t = div4_exact(v[u], R);
+                o.x = fq_post(t.x, R.d, z, qmin, qmax, q.x);
+                o.y = fq_post(t.y, R.d, z, qmin, qmax, q.y);
+                o.z = fq_post(t.z, R.d, z, qmin, qmax, q.z);
+                o.w = fq_post(t.w, R.d, z, qmin, qmax, q.w);
             }
-            if (CHAN == 1) cw.next();
+            st_stream4(y + (size_t)i * 4, o);
+            if (CODES) st_stream4(codes + (size_t)i * 4, q);
         }
     }
 }
@@ -209,7 +215,7 @@ chan_affine_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x
 
 // split a channel's inner extent into CTAs so that nchan x nsplit CTAs fill the machine
 static inline void chan_split(int64_t inner, int64_t outer, int64_t nchan, int vec, int64_t& chunk, int& nsplit) {
-    const int64_t cap = (int64_t)SSQ_NUM_SMS * SSQ_CTAS_PER_SM;
+    const int64_t cap = SSQ_MAX_SLOTS;          // many small address-ordered slabs, bounded by the workspace's partial slots
     const int64_t want = (cap + nchan - 1) / nchan;
     const int64_t per_cta = (int64_t)SSQ_THREADS * 4 * (vec ? 2 : 1);
     const int64_t by_work = (inner * outer + per_cta * outer - 1) / (per_cta * outer);
@@ -227,7 +233,7 @@ using namespace ssq;
 
 extern "C" size_t ssq_ws_bytes(int64_t nchan) {
     if (nchan < 1) nchan = 1;
-    int64_t cap = (int64_t)SSQ_NUM_SMS * SSQ_CTAS_PER_SM;
+    int64_t cap = SSQ_MAX_SLOTS;
     return ws_ticket_bytes(nchan) + (size_t)(nchan + cap + 64) * 4 * sizeof(double);
 }
 
@@ -246,7 +252,7 @@ extern "C" int ssq_fq_affine_fwd(const float* x, const float* delta, const float
         uint32_t n4 = (uint32_t)(n / 4), inner4 = (uint32_t)(inner / 4);
         int64_t ctas = ((int64_t)n4 + SSQ_THREADS * UNROLL - 1) / (SSQ_THREADS * UNROLL);
         bool per_tensor = (nchan == 1 && !in_scale);
-#define LAUNCH(CH, IS, CO) fq_affine_fwd_vec<CH, IS, CO><<<grid_for(ctas, ctas_per_sm(fq_affine_fwd_vec<CH, IS, CO>)), SSQ_THREADS, 0, st>>>( \
+#define LAUNCH(CH, IS, CO) fq_affine_fwd_vec<CH, IS, CO><<<(unsigned)ctas, SSQ_THREADS, 0, st>>>( \
         x, delta, zero_point, in_scale, y, codes, n4, inner4, (uint32_t)nchan, qmin, qmax)
         if (per_tensor) { if (codes) LAUNCH(0, false, true); else LAUNCH(0, false, false); }
         else if (in_scale) { if (codes) LAUNCH(1, true, true); else LAUNCH(1, true, false); }

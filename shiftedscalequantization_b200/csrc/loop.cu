@@ -12,36 +12,57 @@ __global__ void __launch_bounds__(SSQ_THREADS)
 adam_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,
             int64_t n, const float* __restrict__ lr_dev, double beta1d, double beta2d, double epsd,
             const int64_t* __restrict__ step_dev) {
-    // host-side doubles of torch/optim/adam.py (_single_tensor_adam), evaluated per thread
-    const double t = (double)(*step_dev);
-    const double bc1 = 1.0 - pow(beta1d, t);
-    const double bc2 = 1.0 - pow(beta2d, t);
-    const float step_size = (float)((double)__ldg(lr_dev) / bc1);
-    const float bc2_sqrt = (float)sqrt(bc2);
     // Python-double scalars, cast to fp32 by ATen when they meet an fp32 tensor
     const float w1 = (float)(1.0 - beta1d);   // lerp weight (< 0.5 => m + w*(g-m))
     const float w2 = (float)(1.0 - beta2d);
     const float beta2 = (float)beta2d, eps = (float)epsd;
     const bool vec = aligned16(param) && aligned16(grad) && aligned16(m) && aligned16(v);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    // address-ordered tiles of SSQ_THREADS*U float4s, one per CTA (ssq_common.cuh): 8 loads in flight per thread
+    constexpr int U = 2;
+    const int64_t n4 = vec ? (n >> 2) : 0;
+    const int64_t i0 = (int64_t)blockIdx.x * (SSQ_THREADS * U) + threadIdx.x;
+    float4 p4[U], g4[U], m4[U], v4[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + (int64_t)u * SSQ_THREADS;
+        if (i < n4) {
+            p4[u] = *reinterpret_cast<float4*>(param + i * 4);
+            g4[u] = ld_stream4(grad + i * 4);
+            m4[u] = *reinterpret_cast<float4*>(m + i * 4);
+            v4[u] = *reinterpret_cast<float4*>(v + i * 4);
+        }
+    }
+    // host-side doubles of torch/optim/adam.py (_single_tensor_adam): bias corrections from the device step count,
+    // evaluated by one thread per CTA while the tile's loads are in flight
+    __shared__ float s_step_size, s_bc2_sqrt;
+    if (threadIdx.x == 0) {
+        const double t = (double)(*step_dev);
+        const double bc1 = 1.0 - pow(beta1d, t);
+        const double bc2 = 1.0 - pow(beta2d, t);
+        s_step_size = (float)((double)__ldg(lr_dev) / bc1);
+        s_bc2_sqrt = (float)sqrt(bc2);
+    }
+    __syncthreads();
+    const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
     auto one = [&](float& p, float g, float& mm, float& vv) {
         mm = mm + w1 * (g - mm);
         vv = vv * beta2 + w2 * g * g;
         float denom = sqrtf(vv) / bc2_sqrt + eps;
         p = p - step_size * (mm / denom);
     };
-    const int64_t n4 = vec ? (n >> 2) : 0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-        float4 p4 = *reinterpret_cast<float4*>(param + i * 4);
-        float4 g4 = ld_stream4(grad + i * 4);
-        float4 m4 = *reinterpret_cast<float4*>(m + i * 4);
-        float4 v4 = *reinterpret_cast<float4*>(v + i * 4);
-        one(p4.x, g4.x, m4.x, v4.x); one(p4.y, g4.y, m4.y, v4.y);
-        one(p4.z, g4.z, m4.z, v4.z); one(p4.w, g4.w, m4.w, v4.w);
-        *reinterpret_cast<float4*>(param + i * 4) = p4;
-        *reinterpret_cast<float4*>(m + i * 4) = m4;
-        *reinterpret_cast<float4*>(v + i * 4) = v4;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + (int64_t)u * SSQ_THREADS;
+        if (i < n4) {
+            one(p4[u].x, g4[u].x, m4[u].x, v4[u].x); one(p4[u].y, g4[u].y, m4[u].y, v4[u].y);
+            one(p4[u].z, g4[u].z, m4[u].z, v4[u].z); one(p4[u].w, g4[u].w, m4[u].w, v4[u].w);
+            *reinterpret_cast<float4*>(param + i * 4) = p4[u];
+            *reinterpret_cast<float4*>(m + i * 4) = m4[u];
+            *reinterpret_cast<float4*>(v + i * 4) = v4[u];
+        }
     }
+    // tail (n % 4 elements, or everything when a pointer is not 16-byte aligned): grid-stride, scalar
     for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
         one(param[i], grad[i], m[i], v[i]);
 }
@@ -112,7 +133,9 @@ extern "C" int ssq_adam_step(float* param, const float* grad, float* exp_avg, fl
     if (n == 0) return SSQ_OK;
     if (!param || !grad || !exp_avg || !exp_avg_sq || !lr_dev || !step_dev) return SSQ_ERR_NULL;
     if (n < 0) return SSQ_ERR_SIZE;
-    int grid = grid_for((n + SSQ_THREADS * 4 - 1) / (SSQ_THREADS * 4), ctas_per_sm(adam_kernel));
+    const bool vec = aligned16(param) && aligned16(grad) && aligned16(exp_avg) && aligned16(exp_avg_sq);
+    const unsigned grid = vec ? tile_grid(((n >> 2) + SSQ_THREADS * 2 - 1) / (SSQ_THREADS * 2), false)
+                              : (unsigned)grid_for((n + SSQ_THREADS - 1) / SSQ_THREADS);
     adam_kernel<<<grid, SSQ_THREADS, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr_dev, beta1, beta2, eps, step_dev);
     return launch_status();
 }

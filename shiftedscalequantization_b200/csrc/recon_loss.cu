@@ -19,7 +19,7 @@ struct LossArgs {
 // |d|^p and |d|^(p-1) share one log2 (2 MUFU.EX2). One persistent grid; fixed-order reduction.
 template <int MODE, bool VEC, bool GRAD, bool FWD>
 __global__ void __launch_bounds__(SSQ_THREADS)
-recon_loss_kernel(LossArgs a, WsView ws) {
+recon_loss_kernel(LossArgs a, WsView ws, int tiles_per_cta) {
     __shared__ double smem[32];
     const float g0 = a.gscale ? __ldg(a.gscale) : 1.f;
     const float inv = __fdiv_rn(g0, (float)a.denom);   // mean backward: grad / (numel/C)
@@ -45,31 +45,58 @@ recon_loss_kernel(LossArgs a, WsView ws) {
         }
         return term;
     };
-    const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    ChanWalk cw;      // c = sample, col = offset inside the sample (only needed to follow tgt_index)
+    // address-ordered tiles of SSQ_THREADS*U vectors (ssq_common.cuh); TileWalk: c = sample, col = offset inside the
+    // sample (only needed to follow tgt_index)
+    constexpr int U = 4;
+    TileWalk tw;
     if (VEC) {
-        const int64_t ps4 = a.per_sample >> 2, total4 = total >> 2;
-        if (a.tgt_index) cw.init(first, stride, ps4, a.batch);
-        for (int64_t i = first; i < total4; i += stride) {
-            int64_t toff = i;
-            if (a.tgt_index) { toff = __ldg(a.tgt_index + cw.c) * ps4 + cw.col; cw.next(); }
-            float4 pr = ld_stream4(a.pred + i * 4), tg = ld_stream4(a.tgt + toff * 4);
-            float4 fi = make_float4(0.f, 0.f, 0.f, 0.f), go;
-            if (MODE == 1) fi = ld_stream4(a.fisher + toff * 4);
-            float s = one(pr.x, tg.x, fi.x, go.x) + one(pr.y, tg.y, fi.y, go.y)
-                    + one(pr.z, tg.z, fi.z, go.z) + one(pr.w, tg.w, fi.w, go.w);
-            if (GRAD) st_stream4(a.dpred + i * 4, go);
-            acc[0] += (double)s;
+        const int64_t ps4 = a.per_sample >> 2, total4 = total >> 2, tile_v = (int64_t)SSQ_THREADS * U;
+        const int64_t ntiles = (total4 + tile_v - 1) / tile_v;
+        const int64_t t0 = (int64_t)blockIdx.x * tiles_per_cta, t1 = t0 + tiles_per_cta < ntiles ? t0 + tiles_per_cta : ntiles;
+        for (int64_t tile = t0; tile < t1; ++tile) {
+            const int64_t i0 = tile * tile_v + threadIdx.x;
+            if (a.tgt_index) tw.init((uint64_t)i0, (uint64_t)ps4, (uint64_t)a.batch);
+            float4 pr[U], tg[U], fi[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t i = i0 + (int64_t)u * SSQ_THREADS;
+                if (i < total4) {
+                    const int64_t toff = a.tgt_index ? __ldg(a.tgt_index + tw.c) * ps4 + tw.col : i;
+                    pr[u] = ld_stream4(a.pred + i * 4); tg[u] = ld_stream4(a.tgt + toff * 4);
+                    if (MODE == 1) fi[u] = ld_stream4(a.fisher + toff * 4);
+                }
+                if (a.tgt_index) tw.step(SSQ_THREADS);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t i = i0 + (int64_t)u * SSQ_THREADS;
+                if (i < total4) {
+                    float4 go;
+                    const float4 f = (MODE == 1) ? fi[u] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float s = one(pr[u].x, tg[u].x, f.x, go.x) + one(pr[u].y, tg[u].y, f.y, go.y)
+                                  + one(pr[u].z, tg[u].z, f.z, go.z) + one(pr[u].w, tg[u].w, f.w, go.w);
+                    if (GRAD) st_stream4(a.dpred + i * 4, go);
+                    acc[0] += (double)s;
+                }
+            }
         }
     } else {
-        if (a.tgt_index) cw.init(first, stride, a.per_sample, a.batch);
-        for (int64_t i = first; i < total; i += stride) {
-            int64_t toff = i;
-            if (a.tgt_index) { toff = __ldg(a.tgt_index + cw.c) * a.per_sample + cw.col; cw.next(); }
-            float go = 0.f;
-            float s = one(a.pred[i], a.tgt[toff], MODE == 1 ? a.fisher[toff] : 0.f, go);
-            if (GRAD) a.dpred[i] = go;
-            acc[0] += (double)s;
+        const int64_t tile_e = (int64_t)SSQ_THREADS * U, ntiles = (total + tile_e - 1) / tile_e;
+        const int64_t t0 = (int64_t)blockIdx.x * tiles_per_cta, t1 = t0 + tiles_per_cta < ntiles ? t0 + tiles_per_cta : ntiles;
+        for (int64_t tile = t0; tile < t1; ++tile) {
+            const int64_t i0 = tile * tile_e + threadIdx.x;
+            if (a.tgt_index) tw.init((uint64_t)i0, (uint64_t)a.per_sample, (uint64_t)a.batch);
+            for (int u = 0; u < U; ++u) {
+                const int64_t i = i0 + (int64_t)u * SSQ_THREADS;
+                if (i < total) {
+                    const int64_t toff = a.tgt_index ? __ldg(a.tgt_index + tw.c) * a.per_sample + tw.col : i;
+                    float go = 0.f;
+                    const float s = one(a.pred[i], a.tgt[toff], MODE == 1 ? a.fisher[toff] : 0.f, go);
+                    if (GRAD) a.dpred[i] = go;
+                    acc[0] += (double)s;
+                }
+                if (a.tgt_index) tw.step(SSQ_THREADS);
+            }
         }
     }
     if (!FWD) return;
@@ -122,21 +149,32 @@ fisher_full_grad_kernel(LossArgs a, const double* dots) {
 __global__ void __launch_bounds__(SSQ_THREADS)
 gather_rows_kernel(const float* __restrict__ src, const int64_t* __restrict__ index, float* __restrict__ dst,
                    int64_t batch, int64_t per_sample, bool vec) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x, first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    ChanWalk cw;
+    constexpr int U = 4;
+    TileWalk tw;                      // c = output row, col = offset inside the row
     if (vec) {
         const int64_t ps4 = per_sample >> 2, total4 = batch * ps4;
-        cw.init(first, stride, ps4, batch);
-        for (int64_t i = first; i < total4; i += stride) {
-            st_stream4(dst + i * 4, ld_stream4(src + (__ldg(index + cw.c) * ps4 + cw.col) * 4));
-            cw.next();
+        const int64_t i0 = (int64_t)blockIdx.x * (SSQ_THREADS * U) + threadIdx.x;       // one address-ordered tile per CTA
+        tw.init((uint64_t)i0, (uint64_t)ps4, (uint64_t)batch);
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + (int64_t)u * SSQ_THREADS;
+            if (i < total4) v[u] = ld_stream4(src + (__ldg(index + tw.c) * ps4 + tw.col) * 4);
+            tw.step(SSQ_THREADS);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + (int64_t)u * SSQ_THREADS;
+            if (i < total4) st_stream4(dst + i * 4, v[u]);
         }
     } else {
         const int64_t total = batch * per_sample;
-        cw.init(first, stride, per_sample, batch);
-        for (int64_t i = first; i < total; i += stride) {
-            dst[i] = src[__ldg(index + cw.c) * per_sample + cw.col];
-            cw.next();
+        const int64_t i0 = (int64_t)blockIdx.x * (SSQ_THREADS * U) + threadIdx.x;
+        tw.init((uint64_t)i0, (uint64_t)per_sample, (uint64_t)batch);
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + (int64_t)u * SSQ_THREADS;
+            if (i < total) dst[i] = src[__ldg(index + tw.c) * per_sample + tw.col];
+            tw.step(SSQ_THREADS);
         }
     }
 }
@@ -153,7 +191,7 @@ static int launch_loss(LossArgs a, int mode, bool fwd, void* ws, size_t ws_bytes
     if (mode == 2) {
         if (a.batch > 65535) return SSQ_ERR_SIZE;
         if (!ws || ws_bytes < ssq_ws_bytes(a.batch)) return SSQ_ERR_WORKSPACE;
-        int64_t cap = (int64_t)SSQ_NUM_SMS * SSQ_CTAS_PER_SM;
+        int64_t cap = SSQ_MAX_SLOTS;
         int64_t want = (cap + a.batch - 1) / a.batch;
         int64_t by_work = (a.per_sample + SSQ_THREADS * 4 - 1) / (SSQ_THREADS * 4);
         int64_t s = want < by_work ? want : by_work; if (s < 1) s = 1;
@@ -170,11 +208,13 @@ static int launch_loss(LossArgs a, int mode, bool fwd, void* ws, size_t ws_bytes
     if (fwd && (!ws || ws_bytes < ssq_ws_bytes(1))) return SSQ_ERR_WORKSPACE;
     bool vec = (a.per_sample % 4 == 0) && aligned16(a.pred) && aligned16(a.tgt) &&
                (!a.dpred || aligned16(a.dpred)) && (!a.fisher || aligned16(a.fisher));
-    int64_t per_cta = (int64_t)SSQ_THREADS * (vec ? 4 : 1) * 2;
-    int grid = grid_for((total + per_cta - 1) / per_cta);
+    const int64_t per_tile = (int64_t)SSQ_THREADS * 4 * (vec ? 4 : 1);
+    const int64_t ntiles = (total + per_tile - 1) / per_tile;
     WsView v = ws_view(ws, 1);
     const bool grad = a.dpred != nullptr;
-#define L(M, V, G, F) recon_loss_kernel<M, V, G, F><<<grid_for((total + per_cta - 1) / per_cta, ctas_per_sm(recon_loss_kernel<M, V, G, F>)), SSQ_THREADS, 0, st>>>(a, v)
+    int per_cta = 1;
+    const unsigned grid = fwd ? tile_grid_balanced(ntiles, per_cta) : tile_grid(ntiles, false);
+#define L(M, V, G, F) recon_loss_kernel<M, V, G, F><<<grid, SSQ_THREADS, 0, st>>>(a, v, per_cta)
 #define LM(M) do { if (vec) { if (fwd) { if (grad) L(M, true, true, true); else L(M, true, false, true); } \
                               else L(M, true, true, false); } \
                    else { if (fwd) { if (grad) L(M, false, true, true); else L(M, false, false, true); } \
@@ -211,8 +251,8 @@ extern "C" int ssq_gather_rows(const float* src, const int64_t* index, float* ds
     if (batch < 0 || per_sample < 0) return SSQ_ERR_SIZE;
     bool vec = (per_sample % 4 == 0) && aligned16(src) && aligned16(dst);
     int64_t total = batch * per_sample;
-    int64_t per_cta = (int64_t)SSQ_THREADS * (vec ? 4 : 1) * 2;
-    int grid = grid_for((total + per_cta - 1) / per_cta, ctas_per_sm(gather_rows_kernel));
+    const int64_t per_tile = (int64_t)SSQ_THREADS * 4 * (vec ? 4 : 1);
+    const unsigned grid = tile_grid((total + per_tile - 1) / per_tile, false);
     gather_rows_kernel<<<grid, SSQ_THREADS, 0, (cudaStream_t)stream>>>(src, index, dst, batch, per_sample, vec);
     return launch_status();
 }
