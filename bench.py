@@ -539,7 +539,9 @@ def run_ours(args):
     try:    # dram__bytes_read+write of one launch at this microbench shape, from the committed ncu --set full capture
         prof = json.load(open(os.path.join(ROOT, "profiles", "r01_kernels_ncu_full.json")))
         key = {"fq_adaround_fwd(+reg)": "ada_fwd_kernel", "fq_adaround_bwd(+reg grad)": "ada_bwd_kernel", "adam_step": "adam_kernel",
-               "recon_loss(fwd+dpred)": "recon_loss_kernel"}.get(mk)    # captures taken at exactly these shapes
+               "recon_loss(fwd+dpred)": "recon_loss_kernel", "gather_rows": "gather_rows_kernel",
+               "fq_affine_fwd(weights,per-channel)": "fq_affine_fwd_vec",
+               "fq_affine_bwd(weights,per-channel)": "fq_affine_bwd_kernel"}.get(mk)    # captures taken at exactly these shapes
         if key in prof:
             traffic = prof[key]["traffic_MB"] * 1e6
     except Exception:
