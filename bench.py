@@ -162,7 +162,7 @@ def recon_units(Q, qnn):
     return units
 
 
-def make_engines(Q, qnn, cali, dev, act_quant, multi_gpu, host_resident=False, feats=None):
+def make_engines(Q, qnn, cali, dev, act_quant, multi_gpu, host_resident=False, feats=None, scaling='weak'):
     """replicates the setup half of block_reconstruction/layer_reconstruction for every unit, keeping the engines"""
     from shiftedscalequantization_b200.engine import ReconEngine
     from shiftedscalequantization_b200.quant.adaptive_rounding import AdaRoundQuantizer
@@ -194,7 +194,7 @@ def make_engines(Q, qnn, cali, dev, act_quant, multi_gpu, host_resident=False, f
             kw.update(p=2.4)
         eng = ReconEngine(unit, mods, inps, outs, None, act_quant=act_quant, iters=SCHED_ITERS, lr=4e-4, opt_mode='mse',
                           batch_size=BATCH, multi_gpu=multi_gpu, act_quantizers=aqs, use_graph=True, verbose=False,
-                          host_resident=host_resident, device=dev, **kw)
+                          host_resident=host_resident, device=dev, scaling=scaling, **kw)
         # time a representative point of the 20k schedule: past warm-up, so the regulariser path is live
         eng.step_dev.fill_(int(SCHED_ITERS * 0.5)); eng.host_step = int(SCHED_ITERS * 0.5)
         eng.capture()
@@ -444,7 +444,9 @@ def run_ours(args):
     lo, hi = D.shard_range(n_total, rank, world)
     t_setup = time.perf_counter()
     Q, qnn, cali = build_model(dev, n_total)
-    cali = cali[lo:hi]
+    strong = world > 1 and args.scaling == "strong"
+    if not strong:
+        cali = cali[lo:hi]            # weak: each rank owns a shard; strong: every rank holds the whole cache
     # weight-scale init: the first quantised forward runs the MSE search of all 21 layers (K2a)
     qnn.set_quant_state(True, False)
     torch.cuda.synchronize(dev); t0 = time.perf_counter()
@@ -453,7 +455,7 @@ def run_ours(args):
     torch.cuda.synchronize(dev); scale_search_s = time.perf_counter() - t0
     log(f"[rank {rank}] weight scale search (5800 channels x 80 candidates): {scale_search_s * 1e3:.1f} ms")
     search = scale_search_bench(Q, qnn, dev) if world == 1 else None
-    engines, feats = make_engines(Q, qnn, cali, dev, act_quant=False, multi_gpu=world > 1)
+    engines, feats = make_engines(Q, qnn, cali, dev, act_quant=False, multi_gpu=world > 1, scaling=args.scaling)
     setup_s = time.perf_counter() - t_setup
     launches_per_step = sum(e.launches_per_iter for e in engines)
     log(f"[rank {rank}] setup {setup_s:.1f}s, {len(engines)} units, {launches_per_step} ssq launches per step")
@@ -464,7 +466,8 @@ def run_ours(args):
     ms_step = timed_steps(engines, args.steps, args.warmup, dev, world)
     clocks = sampler.stop() if rank == 0 else None
     n_units = len(engines)
-    value = world * n_units / (ms_step * 1e-3)
+    work = 1 if strong else world      # strong: the ranks split ONE batch-32 iteration; weak: each rank completes its own
+    value = work * n_units / (ms_step * 1e-3)
 
     extra = {}
     if world == 1:
@@ -473,9 +476,10 @@ def run_ours(args):
     e2e = None
     # ---- end to end: features in pinned host memory, per-step H2D of the mini-batch, D2H of the loss
     if not args.skip_e2e:
-        eng_h, _ = make_engines(Q, qnn, cali, dev, act_quant=False, multi_gpu=world > 1, host_resident=True, feats=feats)
+        eng_h, _ = make_engines(Q, qnn, cali, dev, act_quant=False, multi_gpu=world > 1, host_resident=True, feats=feats,
+                                scaling=args.scaling)
         ms_e2e = timed_steps(eng_h, max(args.steps // 2, 3), max(args.warmup // 2, 3), dev, world, read_loss=True)
-        e2e = {"value": world * n_units / (ms_e2e * 1e-3), "unit": "iters/s", "ms_per_step": ms_e2e,
+        e2e = {"value": work * n_units / (ms_e2e * 1e-3), "unit": "iters/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": sum(e.h2d_bytes_per_step() for e in eng_h), "d2h_bytes_per_step": 4 * n_units,
                "path": "ReconEngine(host_resident=True, host_stage='pull'): pinned host feature cache; inside each captured iteration a 16-CTA "
                        "kernel (ssq_pull_rows_host) reads the NEXT mini-batch's input and target rows out of mapped host memory over PCIe "
@@ -568,15 +572,21 @@ def run_ours(args):
 
 def base_line(args, value, ms_step, world, clocks, launches_per_step, e2e, peak_src):
     return {"metric": "recon iters/s (ResNet-18 W2A4, 1024 calib imgs)", "value": value, "unit": "iters/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": args.scaling if world > 1 else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "ResNet-18 W2A4 block reconstruction (configs[1]): 9 units (8 blocks + fc), weight-rounding phase, "
                                    "mini-batch 32, randn 224x224 calibration images, random-init weights",
-                       "calib_images": args.images, "per_rank_batch": BATCH, "global_batch": BATCH * world,
+                       "calib_images": args.images, "per_rank_batch": BATCH // world if (world > 1 and args.scaling == "strong") else BATCH,
+                       "global_batch": BATCH if (world > 1 and args.scaling == "strong") else BATCH * world,
                        "step": "one iteration on each of the 9 units (CUDA-graph replay per unit)",
                        "conv_math": "tf32" if args.tf32 else "fp32", "cudnn_benchmark": bool(args.cudnn_benchmark),
                        "l2": "per-unit working sets are re-read every step; the roofline kernels are timed on inputs larger than L2",
-                       "multi_gpu": "calibration images sharded by rank; SUM all-reduce of the flat alpha gradient every iteration" if world > 1 else "single GPU"},
+                       "multi_gpu": ("single GPU" if world == 1 else
+                                     "strong: every rank holds the cache, the ranks split one global mini-batch of 32, SUM all-reduce of the flat "
+                                     "alpha gradient (= the 1-GPU gradient) every iteration" if args.scaling == "strong" else
+                                     "weak: calibration images sharded by rank, each rank draws its own mini-batch of 32, SUM all-reduce of the "
+                                     "flat alpha gradient every iteration")},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * (args.steps + args.warmup)}
 
 
@@ -587,6 +597,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images", type=int, default=1024)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="multi-GPU partitioning (DESIGN.md §7)")
     ap.add_argument("--tf32", type=int, default=0)
     ap.add_argument("--cudnn-benchmark", type=int, default=1)
     ap.add_argument("--skip-e2e", action="store_true")

@@ -87,14 +87,23 @@ class ReconEngine:
                  lr: float = 4e-5, opt_mode: str = 'mse', batch_size: int = 32, multi_gpu: bool = False,
                  act_quantizers: Sequence[nn.Module] = (), use_graph: Optional[bool] = None,
                  idx_table: Optional[torch.Tensor] = None, verbose: bool = True,
-                 host_resident: bool = False, device: Optional[torch.device] = None, host_stage: str = 'pull'):
+                 host_resident: bool = False, device: Optional[torch.device] = None, host_stage: str = 'pull',
+                 scaling: str = 'weak'):
         """host_resident=True keeps the cached features in (pinned) host memory, as the reference does with
         keep_gpu=False (quant/data_utils.py:34-36, `cached_inps[idx].to(device)` at block_recon.py:91-92): every
         step moves its mini-batch rows host->device. host_stage='pull' (default): a kernel inside the captured
         iteration reads the NEXT mini-batch's rows out of the mapped pinned cache while the current iteration
         computes (no host work per step); 'dma': one cudaMemcpyAsync per row on a copy stream, issued by the host."""
+        """scaling (multi_gpu only): 'weak' = every rank draws its own mini-batch of `batch_size` from its shard and the
+        gradients are SUMMED (the reference's link.allreduce semantics, block_recon.py:100-102; global batch = R x batch);
+        'strong' = the ranks split ONE global mini-batch of `batch_size` (every rank holds the whole cache and the same
+        index table, rank r takes columns [r*b, (r+1)*b)); the loss gradient is scaled by 1/R and the regulariser counted
+        once, so the summed gradient equals the single-GPU gradient up to summation order and the trajectory is the
+        1-GPU trajectory."""
         self.unit, self.modules = unit, list(modules)
         self.host_resident = bool(host_resident)
+        if scaling not in ('weak', 'strong'):
+            raise ValueError('scaling must be "weak" or "strong"')
         if host_stage not in ('pull', 'dma'):
             raise ValueError('host_stage must be "pull" or "dma"')
         self.host_pull = self.host_resident and host_stage == 'pull'
@@ -112,6 +121,7 @@ class ReconEngine:
         self.act_quant, self.iters, self.weight, self.p, self.opt_mode = act_quant, int(iters), float(weight), float(p), opt_mode
         self.batch = min(int(batch_size), self.cached_inps.shape[0])
         self.multi_gpu = bool(multi_gpu) and ssq_dist.world_size() > 1
+        self.strong = self.multi_gpu and scaling == 'strong'
         self.use_graph = (self.iters >= 8) if use_graph is None else bool(use_graph)
         self.verbose = verbose
         self.launches_per_iter = 0
@@ -119,6 +129,16 @@ class ReconEngine:
         n = self.cached_inps.shape[0]
         # ---- device-side schedules -------------------------------------------------------------------
         tab = idx_table if idx_table is not None else index_table(n, self.batch, self.iters)
+        self.grad_scale, self.reg_share = None, 1.0
+        if self.strong:
+            world, rk = ssq_dist.world_size(), ssq_dist.rank()
+            if self.batch % world:
+                raise ValueError(f'strong scaling needs batch_size ({self.batch}) divisible by the world size ({world})')
+            b = self.batch // world
+            tab = tab[:, rk * b:(rk + 1) * b].contiguous()          # this rank's slice of the global mini-batch
+            self.batch = b
+            self.reg_share = 1.0 / world
+            self.grad_scale = torch.full((1,), 1.0 / world, device=self.dev)
         self.idx_table = tab.to(self.dev)
         self.idx_table_host = tab.cpu()
         self.host_step = 0
@@ -210,10 +230,11 @@ class ReconEngine:
         with torch.enable_grad():
             out = self.unit(self.cur_inp)
         if self.host_resident:
-            loss, dpred = ops.recon_loss(out.detach(), self.cur_out, self.p, self.opt_mode, fisher=self.cur_grad)
+            loss, dpred = ops.recon_loss(out.detach(), self.cur_out, self.p, self.opt_mode, fisher=self.cur_grad,
+                                         gscale=self.grad_scale)
         else:
             loss, dpred = ops.recon_loss(out.detach(), self.cached_outs, self.p, self.opt_mode, fisher=self.cached_grads,
-                                         tgt_index=self.idx_live)
+                                         tgt_index=self.idx_live, gscale=self.grad_scale)
         self.loss_dev = loss
         if self.act_quant:
             # a unit whose output does not depend on any step size (e.g. the head after
@@ -225,7 +246,7 @@ class ReconEngine:
                 self.gflat[:packed.numel()].copy_(packed)
         else:
             gwqs = torch.autograd.grad([out], self.wq_leaves, [dpred.view_as(out)])
-            self.table.backward(gwqs, self.b_live, self.weight)
+            self.table.backward(gwqs, self.b_live, self.weight * self.reg_share)
         if self.multi_gpu:
             ssq_dist.all_reduce_sum_(self.gflat)                     # SUM, as link.allreduce at block_recon.py:100-102
         ops.adam_step(self.flat, self.gflat, self.exp_avg, self.exp_avg_sq, self.lr_live, self.step_dev)

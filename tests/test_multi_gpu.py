@@ -1,0 +1,76 @@
+"""Multi-GPU reconstruction on real devices: 2 ranks, NCCL. Needs >= 2 GPUs (skipped on the 1-GPU box;
+run with `gpurun --gpus 2 -- python -m pytest tests/test_multi_gpu.py -m gpu`). The CPU-side plumbing (sharding,
+all-reduce, all-gather) is covered by the gloo test in test_host_cpu.py."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+_WORKER = r'''
+import os, sys
+import numpy as np
+import torch
+import torch.distributed as td
+sys.path.insert(0, os.environ["SSQ_ROOT"]); sys.path.insert(0, os.path.join(os.environ["SSQ_ROOT"], "tests"))
+from shiftedscalequantization_b200 import dist as D
+from shiftedscalequantization_b200.engine import ReconEngine, index_table
+from shiftedscalequantization_b200.quant.adaptive_rounding import AdaRoundQuantizer
+from shiftedscalequantization_b200.quant.data_utils import save_inp_oup_data
+from test_recon_gpu import build_qnn
+rk, local, world = D.init_from_env()
+torch.cuda.set_device(local)
+torch.backends.cudnn.allow_tf32 = False
+iters, bs = 20, 16
+
+def run(mode):
+    Q, qnn, cali = build_qnn()                       # same seed on every rank => identical replicas
+    block = qnn.model.layer2[0]
+    qnn.set_quant_state(False, False); block.set_quant_state(True, False)
+    mods = [m for m in block.modules() if isinstance(m, Q.QuantModule)]
+    for m in mods:
+        m.weight_quantizer = AdaRoundQuantizer(uaq=m.weight_quantizer, round_mode='learned_hard_sigmoid', weight_tensor=m.org_weight.data)
+        m.weight_quantizer.soft_targets = True
+    data = D.shard_calibration(cali) if mode == 'weak' else cali
+    inps, outs = save_inp_oup_data(qnn, block, data, True, False, bs)
+    torch.manual_seed(7)
+    tab = index_table(inps.shape[0], bs, iters)
+    eng = ReconEngine(block, mods, inps, outs, None, act_quant=False, iters=iters, weight=0.01, b_range=(20, 2), warmup=0.2,
+                      p=2.0, batch_size=bs, use_graph=True, idx_table=tab, verbose=False, multi_gpu=(mode != 'single'),
+                      scaling='strong' if mode == 'strong' else 'weak')
+    eng.run(); eng.close()
+    return torch.cat([m.weight_quantizer.alpha.detach().reshape(-1) for m in mods])
+
+single = run('single')
+for mode in ('strong', 'weak'):
+    a = run(mode)
+    both = [torch.empty_like(a) for _ in range(world)]
+    td.all_gather(both, a)
+    assert torch.equal(both[0], both[1]), f"{mode}: replicas diverged"          # same reduced gradient, same Adam => bit-identical
+    if mode == 'strong':
+        err = (a - single).abs()
+        frac = float((err <= 2e-3).float().mean())
+        assert frac >= 0.999 and float(err.max()) <= 2 * 1e-3 * iters, (frac, float(err.max()))
+        assert float((torch.sign(a) == torch.sign(single)).float().mean()) > 0.9995
+    else:
+        assert not torch.equal(a, single)                                       # other mini-batches: a different trajectory
+td.barrier()
+sys.stdout.write(f"rank {rk} ok\n"); sys.stdout.flush()
+td.destroy_process_group()
+'''
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_gpu_strong_matches_single_and_replicas_identical(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, SSQ_ROOT=ROOT)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29621", str(script)]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout
