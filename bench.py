@@ -289,6 +289,15 @@ def kernel_microbench(dev, peak_gbs):
     m = torch.zeros_like(w); v = torch.zeros_like(w)
     step = torch.ones(1, dtype=torch.int64, device=dev); lr = ops.scalar_dev(1e-3, dev)
     res["adam_step"] = timeit(lambda: ops.adam_step(alpha, g, m, v, lr, step), 28 * n)
+    # K1c: shifted-scale mixture, S = 3 shifts, one group per input channel (alpha [IC,3]); candidates recomputed from w
+    shifts = [0.96875, 1.03125, 1.0]
+    sd = torch.stack([(d * st).reshape(-1) for st in shifts]).contiguous()
+    pr = ops.shift_probs_fwd(torch.randn(4096, 3, device=dev))
+    dflat, zflat = d.reshape(-1).contiguous(), z.reshape(-1).contiguous()
+    res["fq_shift_fwd(adaShift,soft)"] = timeit(lambda: ops.fq_shift_fwd(w, sd, dflat, zflat, pr, alpha, ops.SHIFT_ADASHIFT, False, False, 0.0, 3.0, False), 12 * n)
+    res["fq_shift_bwd(adaShift,soft)"] = timeit(lambda: ops.fq_shift_bwd(g, w, sd, dflat, zflat, pr, alpha, ops.SHIFT_ADASHIFT, False, 0.0, 3.0, False, True), 16 * n)
+    res["fq_shift_fwd(dequant mix)"] = timeit(lambda: ops.fq_shift_fwd(w, sd, dflat, zflat, pr, None, ops.SHIFT_DEQUANT, False, False, 0.0, 3.0, False), 8 * n)
+    res["fq_shift_bwd(dequant mix)"] = timeit(lambda: ops.fq_shift_bwd(g, w, sd, dflat, zflat, pr, None, ops.SHIFT_DEQUANT, False, 0.0, 3.0, False, False), 8 * n)
     packed = ops.export_codes(w, d, z, 0.0, 3.0, 2, alpha=alpha)
     res["export_codes(2-bit,+alpha)"] = timeit(lambda: ops.export_codes(w, d, z, 0.0, 3.0, 2, alpha=alpha), 8 * n + n // 4)
     res["import_codes(2-bit)"] = timeit(lambda: ops.import_codes(packed, w.shape, d, z, 0.0, 2), 4 * n + n // 4)
@@ -470,7 +479,25 @@ def run_ours(args):
     value = work * n_units / (ms_step * 1e-3)
 
     extra = {}
+    per_unit = None
     if world == 1:
+        # SURVEY §8d protocol: per-unit iterations/s (each unit replayed on its own, CUDA events) + harmonic mean
+        per_unit = {}
+        for ui, e in enumerate(engines):
+            for _ in range(5):
+                e.step()
+            torch.cuda.synchronize(dev)
+            t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(max(args.steps, 20)):
+                e.step()
+            t1.record(); torch.cuda.synchronize(dev)
+            us = 1e3 * t0.elapsed_time(t1) / max(args.steps, 20)
+            name = getattr(e.unit, "pathName", "") or f"unit{ui}"
+            per_unit[name] = {"us_per_iter": round(us, 1), "iters_per_s": round(1e6 / us, 1),
+                              "alpha_elems": int(e.flat.numel()), "ssq_launches": e.launches_per_iter}
+        hm = len(per_unit) / sum(1.0 / v["iters_per_s"] for v in per_unit.values())
+        per_unit["harmonic_mean_iters_per_s"] = round(hm, 1)
         prof, eager_ms = in_step_profile(engines, dev)
     release(engines)
     e2e = None
@@ -531,7 +558,7 @@ def run_ours(args):
     if args.skip_micro:
         line = base_line(args, value, ms_step, world, clocks, launches_per_step, e2e, peak_src)
         line["extra"] = {"first_quantised_forward_ms": scale_search_s * 1e3, "scale_search": search, "setup_s": setup_s, "act_phase": act,
-                         "shifted_loops": shifted}
+                         "shifted_loops": shifted, "per_unit": per_unit}
         print(json.dumps(line), flush=True)
         return
     micro = kernel_microbench(dev, peak_gbs)
@@ -565,7 +592,7 @@ def run_ours(args):
     fq = {k: round(v["gbs"], 1) for k, v in micro.items() if k.startswith("fq_")}
     line["extra"] = {"first_quantised_forward_ms": scale_search_s * 1e3, "scale_search": search, "setup_s": setup_s, "act_phase": act,
                      "fake_quant_hbm_gbs": fq, "fake_quant_hbm_frac_min": round(min(v["frac"] for k, v in micro.items() if k.startswith("fq_")), 3),
-                     "tf32": tf32_extra, "shifted_loops": shifted,
+                     "tf32": tf32_extra, "shifted_loops": shifted, "per_unit": per_unit,
                      "projected_full_run_s": (9 * 20000) / value + ((9 * 5000) / act["iters_per_s"] if act else 0)}
     print(json.dumps(line), flush=True)
 

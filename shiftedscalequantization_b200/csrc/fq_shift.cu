@@ -184,6 +184,177 @@ fq_shift_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ w, c
         _Pragma("unroll") for (int i = 0; i < MS; ++i) if (i < S) partial[((int64_t)blockIdx.y * K + col) * S + i] = acc[i];
 }
 
+// ---- vector kernels (conv layers: K % 4 == 0, 16-byte aligned, one group per input channel) ---------------------------
+// Same arithmetic as shift_one on quotients that were divided four at a time against a reciprocal hoisted per (row, shift).
+template <int MODE, int S>
+__device__ __forceinline__ float shift_eval(const float (&u)[S], const float (&ds)[S], float d, float z, const float (&p)[S],
+                                            float beta, int hard_targets, int hard_round, float qmin, float qmax,
+                                            float (&t)[S], bool& inside, float& dh) {
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+        if (MODE == SSQ_SHIFT_DEQUANT) {
+            const float q = clampk(__fadd_rn(rintf(u[i]), z), qmin, qmax);
+            t[i] = __fmul_rn(__fsub_rn(q, z), ds[i]);
+        } else {
+            t[i] = floorf(u[i]);
+        }
+    }
+    float mix;
+    if (hard_targets) {
+        float pbest = p[0];                       // torch.argmax: first maximum wins
+        mix = t[0];
+#pragma unroll
+        for (int i = 1; i < S; ++i) if (p[i] > pbest) { pbest = p[i]; mix = t[i]; }
+    } else {
+        mix = __fmul_rn(t[0], p[0]);
+#pragma unroll
+        for (int i = 1; i < S; ++i) mix = __fadd_rn(mix, __fmul_rn(t[i], p[i]));
+    }
+    inside = true; dh = 0.f;
+    if (MODE == SSQ_SHIFT_DEQUANT) return mix;
+    float r;
+    if (hard_round) r = (beta >= 0.f) ? 1.f : 0.f;
+    else { float h; dh = rect_sigmoid_grad(beta, h); r = h; }
+    const float xi = __fadd_rn(__fadd_rn(mix, r), z);
+    inside = (xi >= qmin) && (xi <= qmax);
+    return __fmul_rn(__fsub_rn(clampk(xi, qmin, qmax), z), d);
+}
+
+// forward: address-ordered tiles of 256*U float4s (ssq_common.cuh); row = output channel, group = (k / kk)
+template <int MODE, int S>
+__global__ void __launch_bounds__(SSQ_THREADS)
+fq_shift_fwd_vec(const float* __restrict__ w, const float* __restrict__ shift_delta, const float* __restrict__ delta,
+                 const float* __restrict__ zp, const float* __restrict__ p, const float* __restrict__ beta,
+                 float* __restrict__ y, int64_t oc, uint32_t K4, uint32_t kk, int hard_targets, int hard_round,
+                 float qmin, float qmax) {
+    constexpr int U = 2;
+    const int64_t total4 = oc * (int64_t)K4;
+    const int64_t i0 = (int64_t)blockIdx.x * (SSQ_THREADS * U) + threadIdx.x;
+    float4 wv[U], bv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + (int64_t)u * SSQ_THREADS;
+        wv[u] = bv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < total4) { wv[u] = ld_stream4(w + i * 4); if (MODE == SSQ_SHIFT_ADASHIFT) bv[u] = ld_stream4(beta + i * 4); }
+    }
+    TileWalk tw;                                   // c = row (output channel), col = float4 column inside the row
+    tw.init((uint64_t)i0, K4, (uint64_t)oc);
+    float ds[S], d = 0.f, z = 0.f;
+    Recip R[S];
+    uint32_t r_have = 0xffffffffu;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + (int64_t)u * SSQ_THREADS;
+        if (i < total4) {
+            const uint32_t r = tw.c, k0 = tw.col * 4;
+            if (r != r_have) {                     // row parameters: reused by the thread's next vector when it is in the same row
+#pragma unroll
+                for (int sft = 0; sft < S; ++sft) { ds[sft] = __ldg(shift_delta + (int64_t)sft * oc + r); R[sft] = make_recip(ds[sft]); }
+                d = __ldg(delta + r); z = __ldg(zp + r);
+                r_have = r;
+            }
+            float qa[S][4];
+            const bool small = small4(wv[u]);
+#pragma unroll
+            for (int sft = 0; sft < S; ++sft) {
+                const float4 q = div4_exact(wv[u], R[sft], small);
+                qa[sft][0] = q.x; qa[sft][1] = q.y; qa[sft][2] = q.z; qa[sft][3] = q.w;
+            }
+            uint32_t g = k0 / kk, rem = k0 - g * kk;
+            float pv[S];
+#pragma unroll
+            for (int sft = 0; sft < S; ++sft) pv[sft] = __ldg(p + g * S + sft);
+            const float be[4] = {bv[u].x, bv[u].y, bv[u].z, bv[u].w};
+            float out[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (rem == kk) {                   // next input channel: its own group probabilities
+                    rem = 0; ++g;
+#pragma unroll
+                    for (int sft = 0; sft < S; ++sft) pv[sft] = __ldg(p + g * S + sft);
+                }
+                float uu[S], t[S]; bool inside; float dh;
+#pragma unroll
+                for (int sft = 0; sft < S; ++sft) uu[sft] = qa[sft][e];
+                out[e] = shift_eval<MODE, S>(uu, ds, d, z, pv, be[e], hard_targets, hard_round, qmin, qmax, t, inside, dh);
+                ++rem;
+            }
+            st_stream4(y + i * 4, make_float4(out[0], out[1], out[2], out[3]));
+        }
+        tw.step(SSQ_THREADS);
+    }
+}
+
+// backward: a thread owns 4 adjacent columns and walks the rows of its slab, two rows in flight; per-column sums of
+// d y / d p[g, i] in registers -> partial[slab][K][S] (the finish kernel adds slabs and the kk columns of a group in fp64)
+template <int MODE, int S>
+__global__ void __launch_bounds__(SSQ_THREADS)
+fq_shift_bwd_vec(const float* __restrict__ gy, const float* __restrict__ w, const float* __restrict__ shift_delta,
+                 const float* __restrict__ delta, const float* __restrict__ zp, const float* __restrict__ p,
+                 const float* __restrict__ beta, float* __restrict__ gbeta, float* __restrict__ partial,
+                 int64_t oc, uint32_t K4, uint32_t kk, int hard_round, float qmin, float qmax, int64_t rows_per_slab) {
+    const uint32_t col4 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col4 >= K4) return;
+    const int64_t K = (int64_t)K4 * 4;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_slab;
+    const int64_t r1 = r0 + rows_per_slab < oc ? r0 + rows_per_slab : oc;
+    float pe[4][S], acc[4][S];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const uint32_t g = (col4 * 4 + e) / kk;
+#pragma unroll
+        for (int sft = 0; sft < S; ++sft) { pe[e][sft] = __ldg(p + g * S + sft); acc[e][sft] = 0.f; }
+    }
+    auto row = [&](int64_t r, const float4& g4, const float4& w4, const float4& b4) {
+        float ds[S], qa[S][4];
+        const bool small = small4(w4);
+#pragma unroll
+        for (int sft = 0; sft < S; ++sft) {
+            ds[sft] = __ldg(shift_delta + (int64_t)sft * oc + r);
+            const float4 q = div4_exact(w4, make_recip(ds[sft]), small);
+            qa[sft][0] = q.x; qa[sft][1] = q.y; qa[sft][2] = q.z; qa[sft][3] = q.w;
+        }
+        const float d = __ldg(delta + r), z = __ldg(zp + r);
+        const float ge[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
+        float gb[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float uu[S], t[S]; bool inside; float dh;
+#pragma unroll
+            for (int sft = 0; sft < S; ++sft) uu[sft] = qa[sft][e];
+            (void)shift_eval<MODE, S>(uu, ds, d, z, pe[e], be[e], 0, hard_round, qmin, qmax, t, inside, dh);
+            float gm = ge[e];                       // gradient wrt the mixture
+            gb[e] = 0.f;
+            if (MODE == SSQ_SHIFT_ADASHIFT) {
+                gm = inside ? ge[e] * d : 0.f;
+                gb[e] = hard_round ? 0.f : gm * dh;
+            }
+#pragma unroll
+            for (int sft = 0; sft < S; ++sft) acc[e][sft] += gm * t[sft];
+        }
+        if (MODE == SSQ_SHIFT_ADASHIFT && gbeta) st_stream4(gbeta + r * K + (int64_t)col4 * 4, make_float4(gb[0], gb[1], gb[2], gb[3]));
+    };
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    int64_t r = r0;
+    for (; r + 1 < r1; r += 2) {
+        const int64_t ea = r * K + (int64_t)col4 * 4, eb = ea + K;
+        const float4 ga = ld_stream4(gy + ea), wa = ld_stream4(w + ea), gbv = ld_stream4(gy + eb), wb = ld_stream4(w + eb);
+        const float4 ba = (MODE == SSQ_SHIFT_ADASHIFT) ? ld_stream4(beta + ea) : zero4;
+        const float4 bb = (MODE == SSQ_SHIFT_ADASHIFT) ? ld_stream4(beta + eb) : zero4;
+        row(r, ga, wa, ba);
+        row(r + 1, gbv, wb, bb);
+    }
+    if (r < r1) {
+        const int64_t ea = r * K + (int64_t)col4 * 4;
+        row(r, ld_stream4(gy + ea), ld_stream4(w + ea), (MODE == SSQ_SHIFT_ADASHIFT) ? ld_stream4(beta + ea) : zero4);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int sft = 0; sft < S; ++sft)
+            partial[((int64_t)blockIdx.y * K + (int64_t)col4 * 4 + e) * S + sft] = acc[e][sft];
+}
+
 __global__ void __launch_bounds__(SSQ_THREADS)
 fq_shift_bwd_finish_kernel(const float* __restrict__ partial, float* __restrict__ gp, int64_t ic, int64_t K, int64_t kk,
                            int S, int nslab) {
@@ -196,9 +367,11 @@ fq_shift_bwd_finish_kernel(const float* __restrict__ partial, float* __restrict_
     gp[t] = (float)s;
 }
 
-static inline void slab_plan(int64_t oc, int64_t K, int& nslab, int64_t& rows_per_slab) {
-    int64_t colblocks = (K + SSQ_THREADS - 1) / SSQ_THREADS;
-    int64_t want = ((int64_t)SSQ_NUM_SMS * SSQ_CTAS_PER_SM + colblocks - 1) / colblocks;
+static inline void slab_plan(int64_t oc, int64_t K, int& nslab, int64_t& rows_per_slab, bool vec = false) {
+    int64_t colblocks = ((vec ? K / 4 : K) + SSQ_THREADS - 1) / SSQ_THREADS;
+    // vec: ~3 resident CTAs per SM (about 80 registers), slabs of at least 4 rows so the partials stay small
+    int64_t want = ((int64_t)SSQ_NUM_SMS * (vec ? 3 : SSQ_CTAS_PER_SM) + colblocks - 1) / colblocks;
+    if (vec && want > (oc + 3) / 4) want = (oc + 3) / 4;
     if (want > oc) want = oc;
     if (want < 1) want = 1;
     rows_per_slab = (oc + want - 1) / want;
@@ -246,6 +419,19 @@ extern "C" int ssq_fq_shift_fwd(const float* w, const float* shift_delta, const 
     const int64_t K = ic * kk, n = oc * K;
     int grid = grid_for((n + SSQ_THREADS - 1) / SSQ_THREADS);
     cudaStream_t st = (cudaStream_t)stream;
+    if (mode != SSQ_SHIFT_DEQUANT && mode != SSQ_SHIFT_ADASHIFT) return SSQ_ERR_MODE;
+    const bool vec = !per_element && (K % 4 == 0) && K / 4 < 0x7fffffff && kk < 0x7fffffff && aligned16(w) && aligned16(y) &&
+                     (!beta || aligned16(beta));
+    if (vec) {
+        const unsigned vgrid = tile_grid((n / 4 + SSQ_THREADS * 2 - 1) / (SSQ_THREADS * 2), false);
+#define FWDV(M, SS) fq_shift_fwd_vec<M, SS><<<vgrid, SSQ_THREADS, 0, st>>>(w, shift_delta, delta, zero_point, p, beta, y, oc, \
+        (uint32_t)(K / 4), (uint32_t)kk, hard_targets, hard_round, qmin, qmax)
+#define FWDS(M) switch (nshift) { case 1: FWDV(M, 1); break; case 2: FWDV(M, 2); break; case 3: FWDV(M, 3); break; default: FWDV(M, 4); }
+        if (mode == SSQ_SHIFT_DEQUANT) { FWDS(SSQ_SHIFT_DEQUANT) } else { FWDS(SSQ_SHIFT_ADASHIFT) }
+#undef FWDS
+#undef FWDV
+        return launch_status();
+    }
     if (mode == SSQ_SHIFT_DEQUANT)
         fq_shift_fwd_kernel<SSQ_SHIFT_DEQUANT><<<grid, SSQ_THREADS, 0, st>>>(w, shift_delta, delta, zero_point, p, beta, y, oc, K, kk, nshift, per_element, hard_targets, hard_round, qmin, qmax);
     else if (mode == SSQ_SHIFT_ADASHIFT)
@@ -256,8 +442,10 @@ extern "C" int ssq_fq_shift_fwd(const float* w, const float* shift_delta, const 
 
 extern "C" size_t ssq_shift_bwd_ws_bytes(int64_t oc, int64_t ic, int64_t kk, int nshift, int per_element) {
     if (per_element || oc <= 0 || ic <= 0 || kk <= 0) return 16;
-    int nslab; int64_t rps;
+    int nslab, nslab_v = 0; int64_t rps;
     slab_plan(oc, ic * kk, nslab, rps);
+    if ((ic * kk) % 4 == 0) slab_plan(oc, ic * kk, nslab_v, rps, true);
+    if (nslab_v > nslab) nslab = nslab_v;
     return (size_t)nslab * (size_t)(ic * kk) * (size_t)nshift * sizeof(float) + 16;
 }
 
@@ -273,12 +461,28 @@ extern "C" int ssq_fq_shift_bwd(const float* gy, const float* w, const float* sh
     if (mode == SSQ_SHIFT_ADASHIFT && !beta) return SSQ_ERR_NULL;
     if (!per_element && (!ws || ws_bytes < ssq_shift_bwd_ws_bytes(oc, ic, kk, nshift, per_element))) return SSQ_ERR_WORKSPACE;
     const int64_t K = ic * kk;
+    if (mode != SSQ_SHIFT_DEQUANT && mode != SSQ_SHIFT_ADASHIFT) return SSQ_ERR_MODE;
+    const bool vec = !per_element && (K % 4 == 0) && K / 4 < 0x7fffffff && kk < 0x7fffffff && aligned16(gy) && aligned16(w) &&
+                     (!beta || aligned16(beta)) && (!gbeta || aligned16(gbeta));
     int nslab; int64_t rps;
-    slab_plan(oc, K, nslab, rps);
+    slab_plan(oc, K, nslab, rps, vec);
     if (nslab > 65535) return SSQ_ERR_SIZE;
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid((unsigned)((K + SSQ_THREADS - 1) / SSQ_THREADS), (unsigned)nslab);
     float* partial = reinterpret_cast<float*>(ws);
+    if (vec) {
+        dim3 vgrid((unsigned)((K / 4 + SSQ_THREADS - 1) / SSQ_THREADS), (unsigned)nslab);
+#define BWDV(M, SS) fq_shift_bwd_vec<M, SS><<<vgrid, SSQ_THREADS, 0, st>>>(gy, w, shift_delta, delta, zero_point, p, beta, gbeta, partial, \
+        oc, (uint32_t)(K / 4), (uint32_t)kk, hard_round, qmin, qmax, rps)
+#define BWDS(M) switch (nshift) { case 1: BWDV(M, 1); break; case 2: BWDV(M, 2); break; case 3: BWDV(M, 3); break; default: BWDV(M, 4); }
+        if (mode == SSQ_SHIFT_DEQUANT) { BWDS(SSQ_SHIFT_DEQUANT) } else { BWDS(SSQ_SHIFT_ADASHIFT) }
+#undef BWDS
+#undef BWDV
+        int ev = launch_status();
+        if (ev) return ev;
+        fq_shift_bwd_finish_kernel<<<(unsigned)((ic * nshift + SSQ_THREADS - 1) / SSQ_THREADS), SSQ_THREADS, 0, st>>>(partial, gp, ic, K, kk, nshift, nslab);
+        return launch_status();
+    }
+    dim3 grid((unsigned)((K + SSQ_THREADS - 1) / SSQ_THREADS), (unsigned)nslab);
     if (mode == SSQ_SHIFT_DEQUANT)
         fq_shift_bwd_kernel<SSQ_SHIFT_DEQUANT><<<grid, SSQ_THREADS, 0, st>>>(gy, w, shift_delta, delta, zero_point, p, beta, gp, gbeta, partial, oc, K, kk, nshift, per_element, hard_round, qmin, qmax, rps);
     else if (mode == SSQ_SHIFT_ADASHIFT)
