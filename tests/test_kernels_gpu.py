@@ -428,3 +428,80 @@ def test_workspace_reuse_across_channel_counts(ops):
         _, gd1, _ = ops.fq_affine_bwd(gy, x, d[:1].reshape(()), z[:1].reshape(()), 0.0, 15.0)
         _, gd1_ref, _ = O.uaq_backward(host(gy), host(x), host(d[:1].reshape(())), host(z[:1].reshape(())), 0, 15)
         assert_close(host(gd1), gd1_ref, what="per-tensor gdelta")
+
+
+def test_no_writes_outside_the_outputs(ops):
+    """guard bands (compute-sanitizer is not available on the GPU pool): every output lives in the middle of a canary-filled
+    arena; after running each streaming kernel on shapes whose last tile is partial, the canaries must be untouched"""
+    CANARY = 12345.678
+    arena = torch.full((1 << 22,), CANARY, device='cuda')
+    cursor = [1024]
+
+    def out_like(shape, misalign=0):
+        n = int(np.prod(shape))
+        start = (cursor[0] + 255) // 256 * 256 + misalign        # 1 KiB-aligned (+ optional 4-byte misalignment)
+        cursor[0] = start + n + 1024
+        return arena[start:start + n].view(shape), (start, n)
+
+    spans = []
+
+    def intact():
+        mask = torch.ones_like(arena, dtype=torch.bool)
+        for s, n in spans:
+            mask[s:s + n] = False
+        return bool((arena[mask] == CANARY).all())
+
+    g = torch.Generator(device='cuda').manual_seed(3)
+    for shape in [(37, 5, 3, 3), (64, 33, 3, 3), (10, 1000), (3, 4100)]:       # 1665 / 19008 / 10000 / 12300 elements
+        for mis in (0, 1):
+            w = torch.randn(shape, device='cuda', generator=g) * 0.05
+            ps = (shape[0],) + (1,) * (len(shape) - 1)
+            d = (w.abs().reshape(shape[0], -1).amax(1) / 2 + 1e-6).view(ps).contiguous()
+            z = torch.full_like(d, 2.0)
+            alpha = ops.adaround_init_alpha(w, d)
+            gy = torch.randn(shape, device='cuda', generator=g)
+            n = w.numel()
+            lib = ops._lib.load()
+            st = torch.cuda.current_stream().cuda_stream
+            inner, nchan = ops.channel_layout(w, d)
+            # K1a fwd (y + codes), K1b fwd / bwd, straight through the C ABI into arena views
+            y, sp = out_like(shape, mis); spans.append(sp)
+            c, sp = out_like(shape, mis); spans.append(sp)
+            ops._lib.check(lib.ssq_fq_affine_fwd(w.data_ptr(), d.data_ptr(), z.data_ptr(), None, y.data_ptr(), c.data_ptr(), n, inner, nchan, 0.0, 3.0, st), "fwd")
+            y2, sp = out_like(shape, mis); spans.append(sp)
+            ops._lib.check(lib.ssq_fq_adaround_fwd(w.data_ptr(), alpha.data_ptr(), d.data_ptr(), z.data_ptr(), y2.data_ptr(), None, n, inner, nchan,
+                                                   0.0, 3.0, 1, None, 0.0, None, None, 0, st), "ada fwd")
+            ga, sp = out_like(shape, mis); spans.append(sp)
+            ops.adaround_bwd(gy, w, alpha, d, z, 0.0, 3.0, out=ga)
+            # K3 dpred, gather, Adam, import
+            dp, sp = out_like(shape, mis); spans.append(sp)
+            ws = ops._ws(w, 1, "loss"); loss = torch.empty(1, device='cuda')
+            b, per = shape[0], n // shape[0]
+            ops._lib.check(lib.ssq_recon_loss(w.data_ptr(), gy.data_ptr(), None, None, loss.data_ptr(), dp.data_ptr(), b, per, float(n / max(shape[1], 1)),
+                                              0, 2.0, None, ws.data_ptr(), ws.numel(), st), "loss")
+            go, sp = out_like(shape, mis); spans.append(sp)
+            idx = torch.randperm(shape[0], device='cuda')
+            ops.gather_rows(w, idx, out=go)
+            pa, sp = out_like(shape, mis); spans.append(sp)
+            m_, sp2 = out_like(shape, mis); spans.append(sp2)
+            v_, sp3 = out_like(shape, mis); spans.append(sp3)
+            pa.copy_(w); m_.zero_(); v_.zero_()
+            ops.adam_step(pa.view(-1), gy.view(-1), m_.view(-1), v_.view(-1), ops.scalar_dev(1e-3, 'cuda'), torch.ones(1, dtype=torch.int64, device='cuda'))
+            packed = ops.export_codes(w, d, z, 0.0, 3.0, 2, alpha=alpha)
+            wi, sp = out_like(shape, mis); spans.append(sp)
+            k = n // shape[0]
+            ops._lib.check(lib.ssq_import_codes(packed.data_ptr(), None, d.data_ptr(), z.data_ptr(), wi.data_ptr(), shape[0], k, inner, nchan, 0.0, 2, st), "import")
+            torch.cuda.synchronize()
+            assert intact(), (shape, mis)
+            assert torch.equal(wi, ops.adaround_fwd(w, alpha, d, z, 0.0, 3.0, soft=False)) and torch.equal(go, w[idx])
+    # packed export buffer: bytes after the last row must stay zero-initialised canary (uint8 arena)
+    barena = torch.full((1 << 16,), 0xAB, dtype=torch.uint8, device='cuda')
+    w = torch.randn(7, 3, 3, 3, device='cuda', generator=g) * 0.05          # rows of 27 -> 7 bytes per row at 2 bits
+    d = (w.abs().reshape(7, -1).amax(1) / 2).view(7, 1, 1, 1).contiguous(); z = torch.full_like(d, 2.0)
+    rb = ops.packed_row_bytes(27, 2)
+    view = barena[4096:4096 + 7 * rb]
+    ops._lib.check(ops._lib.load().ssq_export_codes(w.data_ptr(), None, None, d.data_ptr(), z.data_ptr(), view.data_ptr(), 7, 27, 27, 7, 0.0, 3.0, 2,
+                                                    torch.cuda.current_stream().cuda_stream), "export")
+    torch.cuda.synchronize()
+    assert bool((barena[:4096] == 0xAB).all()) and bool((barena[4096 + 7 * rb:] == 0xAB).all())
+    assert_exact(host(view.view(7, rb)), O.pack_rows(O.uaq_forward(host(w), host(d), host(z), 0, 3)[1], 0, 2), "packed rows of 27")

@@ -150,3 +150,13 @@ def test_pack_unpack_round_trip(bits):
     codes = g["codes_hard"]
     nb = int(np.ceil(np.log2(codes.max() + 1)))
     assert np.array_equal(O.unpack_rows(O.pack_rows(codes, 0, nb), codes[0].size, 0, nb).reshape(codes.shape), codes)
+
+
+def test_mse_search_vs_reference_numpy_restatement():
+    """the reference ships its own NumPy version of the clip search (myQuant.py:6-45, 4 bits); its outputs on a seeded
+    weight (tests/golden/make_golden_myquant.py) must agree with the oracle that the kernels are held to: same candidate
+    per channel (so the same zero point) and the same step size to fp32 rounding"""
+    g = golden("myquant")
+    d, z, raw, idx = O.mse_search(g["w"], 4)
+    assert_exact(z.astype(np.float64), g["zero_point"], "zero point vs myQuant")
+    assert_close(d.astype(np.float64), g["delta"], rtol=2e-7, what="delta vs myQuant")
