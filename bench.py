@@ -33,6 +33,8 @@ AQ = {'n_bits': 4, 'channel_wise': False, 'scale_method': 'mse', 'leaf_param': T
 RECON = dict(weight=0.01, b_range=(20, 2), warmup=0.2, p=2.0)          # Brecq/main_imagenet.py:201-202
 SCHED_ITERS = 20000
 BATCH = 32
+WORKLOAD = ("ResNet-18 W2A4 block reconstruction (configs[1]): 9 units (8 blocks + fc), weight-rounding phase, "
+            "mini-batch 32, randn 224x224 calibration images, random-init weights")
 
 
 def log(*a):
@@ -129,8 +131,11 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "recon iters/s (ResNet-18 W2A4, 1024 calib imgs)", "value": r["iters_per_s"],
             "unit": "iters/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "ResNet-18 W2A4 block reconstruction, 9 units x batch 32, weight-rounding phase",
-                       "arm": "reference CPU path (oracle port of quant/block_recon.py loop) on host cores"},
+            "config": {"workload": WORKLOAD, "calib_images": args.images, "per_rank_batch": BATCH, "global_batch": BATCH,
+                       "step": "one iteration on each of the 9 units",
+                       "arm": "reference CPU path (oracle/ref_loop_torch.py: the ATen-CPU op chain of quant/block_recon.py:89-105, pinned to the "
+                              "real reference loops by tests/golden/recon_loop.npz) on all host cores; rank 0 only",
+                       "conv_math": "fp32"},
             "cpu_baseline": {"value": r["iters_per_s"], "unit": "iters/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["iters_per_s"], "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -602,8 +607,7 @@ def base_line(args, value, ms_step, world, clocks, launches_per_step, e2e, peak_
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": args.scaling if world > 1 else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "ResNet-18 W2A4 block reconstruction (configs[1]): 9 units (8 blocks + fc), weight-rounding phase, "
-                                   "mini-batch 32, randn 224x224 calibration images, random-init weights",
+            "config": {"workload": WORKLOAD,
                        "calib_images": args.images, "per_rank_batch": BATCH // world if (world > 1 and args.scaling == "strong") else BATCH,
                        "global_batch": BATCH if (world > 1 and args.scaling == "strong") else BATCH * world,
                        "step": "one iteration on each of the 9 units (CUDA-graph replay per unit)",
