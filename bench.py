@@ -167,6 +167,9 @@ def recon_units(Q, qnn):
     return units
 
 
+CAPTURE_S = []      # seconds spent in save_inp_oup_data per unit (feature capture, reported beside the loop numbers)
+
+
 def make_engines(Q, qnn, cali, dev, act_quant, multi_gpu, host_resident=False, feats=None, scaling='weak'):
     """replicates the setup half of block_reconstruction/layer_reconstruction for every unit, keeping the engines"""
     from shiftedscalequantization_b200.engine import ReconEngine
@@ -190,7 +193,9 @@ def make_engines(Q, qnn, cali, dev, act_quant, multi_gpu, host_resident=False, f
                 aqs.append(unit.act_quantizer)
             aqs += [m.act_quantizer for m in mods if m.act_quantizer.delta is not None]
         if feats is None:
+            torch.cuda.synchronize(dev); t_c = time.perf_counter()
             inps, outs = save_inp_oup_data(qnn, unit, cali, True, act_quant, BATCH)
+            torch.cuda.synchronize(dev); CAPTURE_S.append(time.perf_counter() - t_c)
         else:
             inps, outs = feats[ui]
         feats_out.append((inps, outs))
@@ -472,6 +477,8 @@ def run_ours(args):
     engines, feats = make_engines(Q, qnn, cali, dev, act_quant=False, multi_gpu=world > 1, scaling=args.scaling)
     setup_s = time.perf_counter() - t_setup
     launches_per_step = sum(e.launches_per_iter for e in engines)
+    capture_s = list(CAPTURE_S)
+    log(f"[rank {rank}] feature capture per unit (s): {[round(c, 2) for c in capture_s]}")
     log(f"[rank {rank}] setup {setup_s:.1f}s, {len(engines)} units, {launches_per_step} ssq launches per step")
 
     sampler = ClockSampler(local)
@@ -598,6 +605,8 @@ def run_ours(args):
     line["extra"] = {"first_quantised_forward_ms": scale_search_s * 1e3, "scale_search": search, "setup_s": setup_s, "act_phase": act,
                      "fake_quant_hbm_gbs": fq, "fake_quant_hbm_frac_min": round(min(v["frac"] for k, v in micro.items() if k.startswith("fq_")), 3),
                      "tf32": tf32_extra, "shifted_loops": shifted, "per_unit": per_unit,
+                     "feature_capture_s": {"per_unit": [round(c, 3) for c in capture_s], "total": round(sum(capture_s), 3),
+                                           "note": "save_inp_oup_data (quant/data_utils.py:8-37), 1024 images, batch 32, asym=True: excluded from iters/s"},
                      "projected_full_run_s": (9 * 20000) / value + ((9 * 5000) / act["iters_per_s"] if act else 0)}
     print(json.dumps(line), flush=True)
 

@@ -25,7 +25,6 @@ recon_loss_kernel(LossArgs a, WsView ws, int tiles_per_cta) {
     const float inv = __fdiv_rn(g0, (float)a.denom);   // mean backward: grad / (numel/C)
     const float p = a.p, pm1 = a.p - 1.0f;
     const int64_t total = a.batch * a.per_sample;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     double acc[1] = {0.0};
     auto one = [&](float pr, float tg, float fi, float& go) -> float {
         float d = pr - tg;
