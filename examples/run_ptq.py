@@ -42,6 +42,8 @@ def main(argv=None):
     ap.add_argument('--p', default=2.4, type=float)
     ap.add_argument('--batch_size', default=32, type=int)
     ap.add_argument('--max_units', default=0, type=int, help='reconstruct only the first N units (0 = all)')
+    ap.add_argument('--tf32', default=0, type=int, help='1: let cuDNN/cuBLAS use TF32 (torch default); 0: true fp32 like the CPU reference')
+    ap.add_argument('--cudnn_benchmark', default=1, type=int)
     # the reference README's flags (README.md:20,33-34)
     flag = lambda v: str(v).lower() in ('1', 'true', 'yes')
     ap.add_argument('--device_gpu', default='cuda:0')
@@ -52,6 +54,9 @@ def main(argv=None):
 
     dev = torch.device(args.device_gpu)
     torch.cuda.set_device(dev)
+    torch.backends.cudnn.allow_tf32 = bool(args.tf32)
+    torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
+    torch.backends.cudnn.benchmark = bool(args.cudnn_benchmark)
     torch.manual_seed(args.seed)
     kw = {} if args.arch.startswith('regnet') else ({'n_class': args.num_classes} if args.arch == 'mobilenetv2' else {'num_classes': args.num_classes})
     cnn = zoo.build(args.arch, **kw).to(dev).eval()
