@@ -621,7 +621,9 @@ def base_line(args, value, ms_step, world, clocks, launches_per_step, e2e, peak_
                        "global_batch": BATCH if (world > 1 and args.scaling == "strong") else BATCH * world,
                        "step": "one iteration on each of the 9 units (CUDA-graph replay per unit)",
                        "conv_math": "tf32" if args.tf32 else "fp32", "cudnn_benchmark": bool(args.cudnn_benchmark),
-                       "l2": "per-unit working sets are re-read every step; the roofline kernels are timed on inputs larger than L2",
+                       "l2": "inputs larger than L2: one step streams ~215 MB of mini-batch features (random rows of the 6.4 GB cache) plus the "
+                             "weights / alpha / Adam state of all 9 units (~230 MB), so nothing a unit touches survives in the 126 MB L2 until its "
+                             "next iteration; the roofline kernels are timed on 0.6-0.8 GB tensors",
                        "multi_gpu": ("single GPU" if world == 1 else
                                      "strong: every rank holds the cache, the ranks split one global mini-batch of 32, SUM all-reduce of the flat "
                                      "alpha gradient (= the 1-GPU gradient) every iteration" if args.scaling == "strong" else
