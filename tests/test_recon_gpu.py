@@ -405,3 +405,40 @@ def test_bias_cal_matches_reference_autograd():
     assert not bool((blk.conv1.alpha_out.detach() == 1).all()) and blk.conv1.weight_quantizer.soft_targets is False
     with torch.no_grad():
         assert torch.isfinite(blk(torch.randn(2, 64, 8, 8, device='cuda'))).all()
+
+
+def test_checkpoint_round_trip_through_eval_rebuild():
+    """upstream's checkpoint protocol (main_cifar10.py:86,106; myProject.py:43,69-73): torch.save(qnn.state_dict()), later
+    rebuild the module structure with `eval=True` reconstruction calls (AdaRound quantisers swapped in, nothing learned,
+    block_recon.py:36-37) and load_state_dict — the restored model must reproduce the calibrated one bit for bit"""
+    import io
+    Q, qnn, cali = build_qnn()
+    kw = dict(cali_data=cali, iters=24, weight=0.01, asym=True, b_range=(20, 2), warmup=0.2, act_quant=False, opt_mode='mse', batch_size=16)
+    units = [("block", qnn.model.layer1[0]), ("block", qnn.model.layer2[0]), ("layer", qnn.model.fc)]
+    for kind, u in units:
+        (Q.block_reconstruction if kind == "block" else Q.layer_reconstruction)(qnn, u, **kw)
+    qnn.set_quant_state(True, False)
+    x = cali[:8].cuda()
+    with torch.no_grad():
+        ref = qnn(x)
+    buf = io.BytesIO()
+    torch.save(qnn.state_dict(), buf)
+    buf.seek(0)
+    # a fresh process would do exactly this
+    Q2, qnn2, _ = build_qnn(seed=4242)                      # different weights: everything must come from the checkpoint
+    for kind, u in [("block", qnn2.model.layer1[0]), ("block", qnn2.model.layer2[0]), ("layer", qnn2.model.fc)]:
+        (Q2.block_reconstruction if kind == "block" else Q2.layer_reconstruction)(qnn2, u, cali_data=cali, eval=True, **{k: v for k, v in kw.items() if k != 'cali_data'})
+    sd = torch.load(buf)
+    missing, unexpected = qnn2.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert all('org_' not in k for k in missing), missing
+    for m2, m1 in zip([m for m in qnn2.modules() if isinstance(m, Q2.QuantModule)], [m for m in qnn.modules() if isinstance(m, Q.QuantModule)]):
+        m2.org_weight.copy_(m1.org_weight)                  # plain attributes upstream too (not in the state_dict, quant_layer.py:209-212)
+        if m1.org_bias is not None:
+            m2.org_bias.copy_(m1.org_bias)
+    qnn2.set_quant_state(True, False)
+    with torch.no_grad():
+        out = qnn2(x)
+    assert torch.equal(out, ref)
+    a1, a2 = qnn.model.layer2[0].conv2.weight_quantizer.alpha, qnn2.model.layer2[0].conv2.weight_quantizer.alpha
+    assert torch.equal(a1, a2) and a2.requires_grad
