@@ -37,6 +37,18 @@ WORKLOAD = ("ResNet-18 W2A4 block reconstruction (configs[1]): 9 units (8 blocks
             "mini-batch 32, randn 224x224 calibration images, random-init weights")
 
 
+# The contract is ONE JSON line on stdout. Libraries write to fd 1 behind Python's back (NCCL prints its version banner
+# there at communicator creation), so fd 1 is pointed at stderr for the whole run and the result line goes to a
+# private duplicate of the original stdout.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(text: str):
+    _REAL_STDOUT.write(text + "\n")
+    _REAL_STDOUT.flush()
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -139,7 +151,7 @@ def run_reference(args):
             "cpu_baseline": {"value": r["iters_per_s"], "unit": "iters/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["iters_per_s"], "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------- our arm
@@ -457,7 +469,7 @@ def run_ours(args):
     if args.micro_only:
         micro = kernel_microbench(dev, peak_gbs)
         for k, v in micro.items():
-            print(f"{k:40s} {v['ms']:8.4f} ms  {v['gbs']:8.1f} GB/s  {v['frac']:.3f} of {peak_gbs:.0f}")
+            emit(f"{k:40s} {v['ms']:8.4f} ms  {v['gbs']:8.1f} GB/s  {v['frac']:.3f} of {peak_gbs:.0f}")
         return
     n_total = args.images
     lo, hi = D.shard_range(n_total, rank, world)
@@ -530,7 +542,7 @@ def run_ours(args):
     if world > 1:
         if rank == 0:
             line = base_line(args, value, ms_step, world, clocks, launches_per_step, e2e, peak_src)
-            print(json.dumps(line), flush=True)
+            emit(json.dumps(line))
         import torch.distributed as td
         td.barrier()
         td.destroy_process_group()
@@ -571,7 +583,7 @@ def run_ours(args):
         line = base_line(args, value, ms_step, world, clocks, launches_per_step, e2e, peak_src)
         line["extra"] = {"first_quantised_forward_ms": scale_search_s * 1e3, "scale_search": search, "setup_s": setup_s, "act_phase": act,
                          "shifted_loops": shifted, "per_unit": per_unit}
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
         return
     micro = kernel_microbench(dev, peak_gbs)
     ours_ms = sum(ms for _n, ms in prof.values())
@@ -608,7 +620,7 @@ def run_ours(args):
                      "feature_capture_s": {"per_unit": [round(c, 3) for c in capture_s], "total": round(sum(capture_s), 3),
                                            "note": "save_inp_oup_data (quant/data_utils.py:8-37), 1024 images, batch 32, asym=True: excluded from iters/s"},
                      "projected_full_run_s": (9 * 20000) / value + ((9 * 5000) / act["iters_per_s"] if act else 0)}
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 def base_line(args, value, ms_step, world, clocks, launches_per_step, e2e, peak_src):
