@@ -453,6 +453,8 @@ def run_ours(args):
     from shiftedscalequantization_b200 import dist as D
     from shiftedscalequantization_b200 import ops
     rank, local, world = D.init_from_env()
+    if world > 1:
+        log(f"[rank {int(os.environ.get('RANK', 0))}] bound to {D.bind_to_gpu_cpus(local)} GPU-local cores (0 = unchanged)")
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     torch.backends.cudnn.benchmark = bool(args.cudnn_benchmark)   # pass 0 under a profiler: autotuning mis-times there
