@@ -220,14 +220,19 @@ __device__ __forceinline__ float shift_eval(const float (&u)[S], const float (&d
     return __fmul_rn(__fsub_rn(clampk(xi, qmin, qmax), z), d);
 }
 
-// forward: address-ordered tiles of 256*U float4s (ssq_common.cuh); row = output channel, group = (k / kk)
-template <int MODE, int S>
+// forward: address-ordered tiles of 256*U float4s (ssq_common.cuh); row = output channel, group = (k / kk).
+// SOFT: soft targets and soft round known at compile time (the training loops) — the per-element mode branches vanish.
+// WIDE: kk >= 4, so a float4 touches at most two groups: both probability rows are loaded up front and selected per element
+// (kk < 4, i.e. 1x1 kernels, reloads at every group change).
+template <int MODE, int S, bool SOFT, bool WIDE>
 __global__ void __launch_bounds__(SSQ_THREADS)
 fq_shift_fwd_vec(const float* __restrict__ w, const float* __restrict__ shift_delta, const float* __restrict__ delta,
                  const float* __restrict__ zp, const float* __restrict__ p, const float* __restrict__ beta,
-                 float* __restrict__ y, int64_t oc, uint32_t K4, uint32_t kk, int hard_targets, int hard_round,
+                 float* __restrict__ y, int64_t oc, uint32_t K4, uint32_t kk, int hard_targets_rt, int hard_round_rt,
                  float qmin, float qmax) {
     constexpr int U = 2;
+    const int hard_targets = SOFT ? 0 : hard_targets_rt, hard_round = SOFT ? 0 : hard_round_rt;
+    const uint32_t last_group = (K4 * 4) / kk - 1;
     const int64_t total4 = oc * (int64_t)K4;
     const int64_t i0 = (int64_t)blockIdx.x * (SSQ_THREADS * U) + threadIdx.x;
     float4 wv[U], bv[U];
@@ -261,14 +266,25 @@ fq_shift_fwd_vec(const float* __restrict__ w, const float* __restrict__ shift_de
                 qa[sft][0] = q.x; qa[sft][1] = q.y; qa[sft][2] = q.z; qa[sft][3] = q.w;
             }
             uint32_t g = k0 / kk, rem = k0 - g * kk;
-            float pv[S];
+            float pv[S], p1[S];
 #pragma unroll
             for (int sft = 0; sft < S; ++sft) pv[sft] = __ldg(p + g * S + sft);
+            const uint32_t n0 = kk - rem;          // elements of this vector that still belong to group g
+            if (WIDE) {
+                const uint32_t g1 = g < last_group ? g + 1 : g;
+#pragma unroll
+                for (int sft = 0; sft < S; ++sft) p1[sft] = __ldg(p + g1 * S + sft);
+            }
             const float be[4] = {bv[u].x, bv[u].y, bv[u].z, bv[u].w};
             float out[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                if (rem == kk) {                   // next input channel: its own group probabilities
+                if (WIDE) {
+                    if (e > 0 && (uint32_t)e == n0) {
+#pragma unroll
+                        for (int sft = 0; sft < S; ++sft) pv[sft] = p1[sft];
+                    }
+                } else if (rem == kk) {            // next input channel: its own group probabilities
                     rem = 0; ++g;
 #pragma unroll
                     for (int sft = 0; sft < S; ++sft) pv[sft] = __ldg(p + g * S + sft);
@@ -287,14 +303,15 @@ fq_shift_fwd_vec(const float* __restrict__ w, const float* __restrict__ shift_de
 
 // backward: a thread owns 4 adjacent columns and walks the rows of its slab, two rows in flight; per-column sums of
 // d y / d p[g, i] in registers -> partial[slab][K][S] (the finish kernel adds slabs and the kk columns of a group in fp64)
-template <int MODE, int S>
+template <int MODE, int S, bool SOFT>
 __global__ void __launch_bounds__(SSQ_THREADS)
 fq_shift_bwd_vec(const float* __restrict__ gy, const float* __restrict__ w, const float* __restrict__ shift_delta,
                  const float* __restrict__ delta, const float* __restrict__ zp, const float* __restrict__ p,
                  const float* __restrict__ beta, float* __restrict__ gbeta, float* __restrict__ partial,
-                 int64_t oc, uint32_t K4, uint32_t kk, int hard_round, float qmin, float qmax, int64_t rows_per_slab) {
+                 int64_t oc, uint32_t K4, uint32_t kk, int hard_round_rt, float qmin, float qmax, int64_t rows_per_slab) {
     const uint32_t col4 = blockIdx.x * blockDim.x + threadIdx.x;
     if (col4 >= K4) return;
+    const int hard_round = SOFT ? 0 : hard_round_rt;
     const int64_t K = (int64_t)K4 * 4;
     const int64_t r0 = (int64_t)blockIdx.y * rows_per_slab;
     const int64_t r1 = r0 + rows_per_slab < oc ? r0 + rows_per_slab : oc;
@@ -424,12 +441,16 @@ extern "C" int ssq_fq_shift_fwd(const float* w, const float* shift_delta, const 
                      (!beta || aligned16(beta));
     if (vec) {
         const unsigned vgrid = tile_grid((n / 4 + SSQ_THREADS * 2 - 1) / (SSQ_THREADS * 2), false);
-#define FWDV(M, SS) fq_shift_fwd_vec<M, SS><<<vgrid, SSQ_THREADS, 0, st>>>(w, shift_delta, delta, zero_point, p, beta, y, oc, \
+        const bool soft = !hard_targets && !hard_round, wide = kk >= 4;
+#define FWDK(M, SS, SO, WI) fq_shift_fwd_vec<M, SS, SO, WI><<<vgrid, SSQ_THREADS, 0, st>>>(w, shift_delta, delta, zero_point, p, beta, y, oc, \
         (uint32_t)(K / 4), (uint32_t)kk, hard_targets, hard_round, qmin, qmax)
+#define FWDV(M, SS) do { if (soft) { if (wide) FWDK(M, SS, true, true); else FWDK(M, SS, true, false); } \
+                         else { if (wide) FWDK(M, SS, false, true); else FWDK(M, SS, false, false); } } while (0)
 #define FWDS(M) switch (nshift) { case 1: FWDV(M, 1); break; case 2: FWDV(M, 2); break; case 3: FWDV(M, 3); break; default: FWDV(M, 4); }
         if (mode == SSQ_SHIFT_DEQUANT) { FWDS(SSQ_SHIFT_DEQUANT) } else { FWDS(SSQ_SHIFT_ADASHIFT) }
 #undef FWDS
 #undef FWDV
+#undef FWDK
         return launch_status();
     }
     if (mode == SSQ_SHIFT_DEQUANT)
@@ -471,12 +492,14 @@ extern "C" int ssq_fq_shift_bwd(const float* gy, const float* w, const float* sh
     float* partial = reinterpret_cast<float*>(ws);
     if (vec) {
         dim3 vgrid((unsigned)((K / 4 + SSQ_THREADS - 1) / SSQ_THREADS), (unsigned)nslab);
-#define BWDV(M, SS) fq_shift_bwd_vec<M, SS><<<vgrid, SSQ_THREADS, 0, st>>>(gy, w, shift_delta, delta, zero_point, p, beta, gbeta, partial, \
+#define BWDK(M, SS, SO) fq_shift_bwd_vec<M, SS, SO><<<vgrid, SSQ_THREADS, 0, st>>>(gy, w, shift_delta, delta, zero_point, p, beta, gbeta, partial, \
         oc, (uint32_t)(K / 4), (uint32_t)kk, hard_round, qmin, qmax, rps)
+#define BWDV(M, SS) do { if (!hard_round) BWDK(M, SS, true); else BWDK(M, SS, false); } while (0)
 #define BWDS(M) switch (nshift) { case 1: BWDV(M, 1); break; case 2: BWDV(M, 2); break; case 3: BWDV(M, 3); break; default: BWDV(M, 4); }
         if (mode == SSQ_SHIFT_DEQUANT) { BWDS(SSQ_SHIFT_DEQUANT) } else { BWDS(SSQ_SHIFT_ADASHIFT) }
 #undef BWDS
 #undef BWDV
+#undef BWDK
         int ev = launch_status();
         if (ev) return ev;
         fq_shift_bwd_finish_kernel<<<(unsigned)((ic * nshift + SSQ_THREADS - 1) / SSQ_THREADS), SSQ_THREADS, 0, st>>>(partial, gp, ic, K, kk, nshift, nslab);
