@@ -29,6 +29,8 @@ KERNELS = OrderedDict([
     ("fq_affine_fwd_vec", ("K1a fwd per-channel weights (ssq_fq_affine_fwd)", 8, W)),
     ("fq_affine_bwd_kernel", ("K1a bwd per-channel weights (ssq_fq_affine_bwd)", 12, W)),
     ("gather_rows_kernel", ("mini-batch gather (ssq_gather_rows), activations [256,256,56,56]", 8, A)),
+    ("fq_shift_fwd_vec", ("K1c fwd, adaShift soft, S = 3 (ssq_fq_shift_fwd)", 12, W)),
+    ("fq_shift_bwd_vec", ("K1c bwd, adaShift soft, S = 3 (ssq_fq_shift_bwd)", 16, W)),
     ("export_vec_kernel", ("integer export, 2-bit + alpha (ssq_export_codes)", 8.25, W)),
     ("import_vec_kernel", ("integer import, 2-bit (ssq_import_codes)", 4.25, W)),
 ])

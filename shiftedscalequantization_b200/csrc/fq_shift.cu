@@ -225,7 +225,7 @@ __device__ __forceinline__ float shift_eval(const float (&u)[S], const float (&d
 // WIDE: kk >= 4, so a float4 touches at most two groups: both probability rows are loaded up front and selected per element
 // (kk < 4, i.e. 1x1 kernels, reloads at every group change).
 template <int MODE, int S, bool SOFT, bool WIDE>
-__global__ void __launch_bounds__(SSQ_THREADS)
+__global__ void __launch_bounds__(SSQ_THREADS, 5)
 fq_shift_fwd_vec(const float* __restrict__ w, const float* __restrict__ shift_delta, const float* __restrict__ delta,
                  const float* __restrict__ zp, const float* __restrict__ p, const float* __restrict__ beta,
                  float* __restrict__ y, int64_t oc, uint32_t K4, uint32_t kk, int hard_targets_rt, int hard_round_rt,
@@ -304,7 +304,7 @@ fq_shift_fwd_vec(const float* __restrict__ w, const float* __restrict__ shift_de
 // backward: a thread owns 4 adjacent columns and walks the rows of its slab, two rows in flight; per-column sums of
 // d y / d p[g, i] in registers -> partial[slab][K][S] (the finish kernel adds slabs and the kk columns of a group in fp64)
 template <int MODE, int S, bool SOFT>
-__global__ void __launch_bounds__(SSQ_THREADS)
+__global__ void __launch_bounds__(SSQ_THREADS, 4)
 fq_shift_bwd_vec(const float* __restrict__ gy, const float* __restrict__ w, const float* __restrict__ shift_delta,
                  const float* __restrict__ delta, const float* __restrict__ zp, const float* __restrict__ p,
                  const float* __restrict__ beta, float* __restrict__ gbeta, float* __restrict__ partial,
@@ -387,7 +387,7 @@ fq_shift_bwd_finish_kernel(const float* __restrict__ partial, float* __restrict_
 static inline void slab_plan(int64_t oc, int64_t K, int& nslab, int64_t& rows_per_slab, bool vec = false) {
     int64_t colblocks = ((vec ? K / 4 : K) + SSQ_THREADS - 1) / SSQ_THREADS;
     // vec: ~3 resident CTAs per SM (about 80 registers), slabs of at least 4 rows so the partials stay small
-    int64_t want = ((int64_t)SSQ_NUM_SMS * (vec ? 3 : SSQ_CTAS_PER_SM) + colblocks - 1) / colblocks;
+    int64_t want = ((int64_t)SSQ_NUM_SMS * (vec ? 4 : SSQ_CTAS_PER_SM) + colblocks - 1) / colblocks;
     if (vec && want > (oc + 3) / 4) want = (oc + 3) / 4;
     if (want > oc) want = oc;
     if (want < 1) want = 1;
