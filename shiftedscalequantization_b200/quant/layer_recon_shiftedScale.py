@@ -138,6 +138,7 @@ def _act_delta_params(unit):
 
 
 USE_CAPTURED_LOOP = True      # False: the eager autograd loop below (kept as the behavioural cross-check)
+MULTI_GPU = False             # True under torchrun: SUM all-reduce of the flat gradient per iteration (upstream's loops are single-GPU)
 LAST_LOOP_STATS = {}          # {'iters', 'loop_ms', 'captured', 'launches_per_iter'} of the most recent loop (bench.py reads it)
 
 
@@ -149,7 +150,7 @@ def _run_captured(unit, loss_func, slots, lr_table, b_tables, reg_fn, cached_inp
     from ..engine import AutogradReconEngine
     from .. import dist as ssq_dist
     eng = AutogradReconEngine(unit, slots, cached_inp, cached_out, iters=iters, batch_size=batch_size, p=loss_func.p,
-                              lr_table=lr_table, b_tables=b_tables, reg_fn=reg_fn, multi_gpu=ssq_dist.world_size() > 1)
+                              lr_table=lr_table, b_tables=b_tables, reg_fn=reg_fn, multi_gpu=MULTI_GPU and ssq_dist.world_size() > 1)
     state = {'start': 0.0}
     bar = tqdm(total=iters, desc='', dynamic_ncols=True)
 
