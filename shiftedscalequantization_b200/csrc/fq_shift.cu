@@ -185,214 +185,378 @@ fq_shift_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ w, c
 }
 
 // ---- vector kernels (conv layers: K % 4 == 0, 16-byte aligned, one group per input channel) ---------------------------
-// Same arithmetic as shift_one on quotients that were divided four at a time against a reciprocal hoisted per (row, shift).
-template <int MODE, int S>
-__device__ __forceinline__ float shift_eval(const float (&u)[S], const float (&ds)[S], float d, float z, const float (&p)[S],
-                                            float beta, int hard_targets, int hard_round, float qmin, float qmax,
-                                            float (&t)[S], bool& inside, float& dh) {
-#pragma unroll
-    for (int i = 0; i < S; ++i) {
-        if (MODE == SSQ_SHIFT_DEQUANT) {
-            const float q = clampk(__fadd_rn(rintf(u[i]), z), qmin, qmax);
-            t[i] = __fmul_rn(__fsub_rn(q, z), ds[i]);
-        } else {
-            t[i] = floorf(u[i]);
-        }
+// Same arithmetic as shift_one, organised so that the per-thread fixed cost is small against 16 elements of work:
+//  * row / group indices come from host-computed multiply-shift constants (FastDiv) instead of emulated 32-bit divisions;
+//  * a row's S reciprocals (MUFU.RCP + Newton) and clamp bounds are computed once per row change (forward) or once per CTA
+//    row chunk into shared memory (backward);
+//  * ONE range test per float4 decides between the fast path (hoisted-reciprocal exact quotients, FMNMX clamps — every value
+//    is finite there) and shift_*_slow, an out-of-line restatement with div.rn and NaN-preserving clamps;
+//  * dequantised candidates use clamp(rint(u) + z, qmin, qmax) - z == clamp(rint(u), qmin - z, qmax - z), exact whenever z, qmin,
+//    qmax are integers below 2^22 (checked per row; anything else takes the slow path). fma(k, ds, +0) keeps the reference's +0
+//    where rint(u) is -0.
+struct FastDiv { uint32_t mul, sh; };            // n / d for n < 2^31, d >= 2: umulhi(n, mul) >> sh
+static inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    uint32_t s = 0;
+    while ((1ull << s) < (uint64_t)d) ++s;         // ceil(log2 d) >= 1
+    f.mul = (uint32_t)(((1ull << (31 + s)) / d) + 1ull);   // < 2^32 because d > 2^(s-1); error term n * (mul * d - 2^(31+s)) < 2^(31+s)
+    f.sh = s - 1;
+    return f;
+}
+__device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv& f) { return __umulhi(n, f.mul) >> f.sh; }
+
+struct ShiftArgs {
+    const float *w, *shift_delta, *delta, *zp, *p, *beta, *gy;
+    float *y, *gbeta, *partial;
+    int64_t oc, rows_per_slab;
+    uint32_t K4, kk, total4, last_group;
+    FastDiv dK4, dkk;
+    int S, hard_targets, hard_round, q_int;        // q_int: qmin, qmax are integers of magnitude <= 2^22
+    float qmin, qmax;
+};
+
+// out-of-line slow paths: one float4 of the forward / one float4 of one row of the backward, scalar reference arithmetic
+template <int MODE>
+__device__ __noinline__ void shift_fwd_slow(const ShiftArgs& a, uint32_t i) {
+    const int64_t K = (int64_t)a.K4 * 4;
+    const int64_t r = i / a.K4;
+    ShiftCtx c;
+    for (int s = 0; s < MS; ++s) if (s < a.S) c.ds[s] = __ldg(a.shift_delta + (int64_t)s * a.oc + r);
+    c.d = __ldg(a.delta + r); c.z = __ldg(a.zp + r);
+    for (int e = 0; e < 4; ++e) {
+        const int64_t idx = (int64_t)i * 4 + e, k = idx - r * K, g = k / a.kk;
+        float pv[MS];
+        for (int s = 0; s < MS; ++s) if (s < a.S) pv[s] = __ldg(a.p + g * a.S + s);
+        bool inside; float dh;
+        const float bv = (MODE == SSQ_SHIFT_ADASHIFT) ? a.beta[idx] : 0.f;
+        a.y[idx] = shift_one<MODE>(a.w[idx], c, pv, bv, a.S, a.hard_targets, a.hard_round, a.qmin, a.qmax, nullptr, inside, dh);
     }
+}
+struct SlowTerms { float gm_t[4][MS]; };            // gm * t_i of the four columns
+template <int MODE>
+__device__ __noinline__ SlowTerms shift_bwd_slow(const ShiftArgs& a, int64_t r, uint32_t col4) {
+    SlowTerms o;
+    const int64_t K = (int64_t)a.K4 * 4;
+    ShiftCtx c;
+    for (int s = 0; s < MS; ++s) if (s < a.S) c.ds[s] = __ldg(a.shift_delta + (int64_t)s * a.oc + r);
+    c.d = __ldg(a.delta + r); c.z = __ldg(a.zp + r);
+    for (int e = 0; e < 4; ++e) {
+        const int64_t k = (int64_t)col4 * 4 + e, idx = r * K + k, g = k / a.kk;
+        float pv[MS], terms[MS];
+        for (int s = 0; s < MS; ++s) { pv[s] = (s < a.S) ? __ldg(a.p + g * a.S + s) : 0.f; terms[s] = 0.f; }
+        bool inside; float dh;
+        const float bv = (MODE == SSQ_SHIFT_ADASHIFT) ? a.beta[idx] : 0.f;
+        (void)shift_one<MODE>(a.w[idx], c, pv, bv, a.S, 0, a.hard_round, a.qmin, a.qmax, terms, inside, dh);
+        float gm = a.gy[idx];
+        if (MODE == SSQ_SHIFT_ADASHIFT) {
+            gm = inside ? gm * c.d : 0.f;
+            if (a.gbeta) a.gbeta[idx] = a.hard_round ? 0.f : gm * dh;
+        }
+        for (int s = 0; s < MS; ++s) o.gm_t[e][s] = gm * terms[s];
+    }
+    return o;
+}
+
+// per-row constants of the fast path
+template <int S> struct RowP { float ds[S], r[S], c0, c1; bool ok; };   // (c0, c1) = (qmin - z, qmax - z) dequant | (d, z) adaShift
+template <int MODE, int S>
+__device__ __forceinline__ void row_params(RowP<S>& R, const ShiftArgs& a, int64_t row) {
+    bool ok = true;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const float ds = __ldg(a.shift_delta + (int64_t)s * a.oc + row);
+        const float r0 = rcp_approx(ds);
+        R.ds[s] = ds;
+        R.r[s] = fmaf(r0, fmaf(-ds, r0, 1.0f), r0);
+        ok = ok && (ds >= 0x1p-60f) && (ds <= 0x1p60f);
+    }
+    const float d = __ldg(a.delta + row), z = __ldg(a.zp + row);
+    if (MODE == SSQ_SHIFT_DEQUANT) {
+        R.c0 = __fsub_rn(a.qmin, z); R.c1 = __fsub_rn(a.qmax, z);
+        ok = ok && a.q_int && (fabsf(z) <= 0x1p22f) && (rintf(z) == z);
+    } else {
+        R.c0 = d; R.c1 = z;
+        ok = ok && (fabsf(z) <= 0x1p60f) && (fabsf(d) <= 0x1p60f);
+    }
+    R.ok = ok;
+}
+__device__ __forceinline__ float quot_fast(float x, float ds, float r) {
+    const float q0 = __fmul_rn(x, r);
+    return fmaf(r, fmaf(-ds, q0, x), q0);
+}
+// fast-path candidates of one element: dequantised (q - z) * ds, or the integer floors
+template <int MODE, int S>
+__device__ __forceinline__ void candidates(float x, const RowP<S>& R, float (&t)[S]) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const float u = quot_fast(x, R.ds[s], R.r[s]);
+        if (MODE == SSQ_SHIFT_DEQUANT) t[s] = fmaf(fminf(fmaxf(rintf(u), R.c0), R.c1), R.ds[s], 0.0f);
+        else t[s] = floorf(u);
+    }
+}
+template <int S>
+__device__ __forceinline__ float mixture(const float (&t)[S], const float (&p)[S], int hard_targets) {
     float mix;
     if (hard_targets) {
         float pbest = p[0];                       // torch.argmax: first maximum wins
         mix = t[0];
 #pragma unroll
-        for (int i = 1; i < S; ++i) if (p[i] > pbest) { pbest = p[i]; mix = t[i]; }
+        for (int s = 1; s < S; ++s) if (p[s] > pbest) { pbest = p[s]; mix = t[s]; }
     } else {
         mix = __fmul_rn(t[0], p[0]);
 #pragma unroll
-        for (int i = 1; i < S; ++i) mix = __fadd_rn(mix, __fmul_rn(t[i], p[i]));
+        for (int s = 1; s < S; ++s) mix = __fadd_rn(mix, __fmul_rn(t[s], p[s]));
     }
-    inside = true; dh = 0.f;
-    if (MODE == SSQ_SHIFT_DEQUANT) return mix;
-    float r;
-    if (hard_round) r = (beta >= 0.f) ? 1.f : 0.f;
-    else { float h; dh = rect_sigmoid_grad(beta, h); r = h; }
-    const float xi = __fadd_rn(__fadd_rn(mix, r), z);
-    inside = (xi >= qmin) && (xi <= qmax);
-    return __fmul_rn(__fsub_rn(clampk(xi, qmin, qmax), z), d);
+    return mix;
 }
 
-// forward: address-ordered tiles of 256*U float4s (ssq_common.cuh); row = output channel, group = (k / kk).
+// group probabilities of the four elements of a float4 starting at in-row offset k0
+//   GK 1: kk >= 4 — at most two groups per float4, both rows loaded up front, selected per element
+//   GK 2: kk == 1 — the 4*S probabilities are contiguous: S float4 loads
+//   GK 0: anything else — per-element lookup
+template <int S, int GK>
+__device__ __forceinline__ void group_probs(const ShiftArgs& a, uint32_t k0, float (&pe)[4][S]) {
+    if (GK == 1) {
+        const uint32_t g = fastdiv(k0, a.dkk), n0 = a.kk - (k0 - g * a.kk);   // n0 elements still belong to group g
+        const uint32_t g1 = g < a.last_group ? g + 1 : g;
+        float p0[S], p1[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) { p0[s] = __ldg(a.p + (size_t)g * S + s); p1[s] = __ldg(a.p + (size_t)g1 * S + s); }
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int s = 0; s < S; ++s) pe[e][s] = (e == 0 || (uint32_t)e < n0) ? p0[s] : p1[s];
+    } else if (GK == 2) {
+        float flat[4 * S];
+        const float4* src = reinterpret_cast<const float4*>(a.p + (size_t)k0 * S);
+#pragma unroll
+        for (int j = 0; j < S; ++j) { const float4 v = __ldg(src + j); flat[4 * j] = v.x; flat[4 * j + 1] = v.y; flat[4 * j + 2] = v.z; flat[4 * j + 3] = v.w; }
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int s = 0; s < S; ++s) pe[e][s] = flat[e * S + s];
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const uint32_t g = a.kk == 1 ? k0 + e : fastdiv(k0 + e, a.dkk);
+#pragma unroll
+            for (int s = 0; s < S; ++s) pe[e][s] = __ldg(a.p + (size_t)g * S + s);
+        }
+    }
+}
+
+// forward: address-ordered tiles of 256*U float4s (ssq_common.cuh); row = output channel, group = k / kk.
 // SOFT: soft targets and soft round known at compile time (the training loops) — the per-element mode branches vanish.
-// WIDE: kk >= 4, so a float4 touches at most two groups: both probability rows are loaded up front and selected per element
-// (kk < 4, i.e. 1x1 kernels, reloads at every group change).
-template <int MODE, int S, bool SOFT, bool WIDE>
-__global__ void __launch_bounds__(SSQ_THREADS, 5)
-fq_shift_fwd_vec(const float* __restrict__ w, const float* __restrict__ shift_delta, const float* __restrict__ delta,
-                 const float* __restrict__ zp, const float* __restrict__ p, const float* __restrict__ beta,
-                 float* __restrict__ y, int64_t oc, uint32_t K4, uint32_t kk, int hard_targets_rt, int hard_round_rt,
-                 float qmin, float qmax) {
-    constexpr int U = 2;
-    const int hard_targets = SOFT ? 0 : hard_targets_rt, hard_round = SOFT ? 0 : hard_round_rt;
-    const uint32_t last_group = (K4 * 4) / kk - 1;
-    const int64_t total4 = oc * (int64_t)K4;
-    const int64_t i0 = (int64_t)blockIdx.x * (SSQ_THREADS * U) + threadIdx.x;
+#ifndef SSQ_K1C_FWD_U
+#define SSQ_K1C_FWD_U 4
+#endif
+#ifndef SSQ_K1C_FWD_CTAS
+#define SSQ_K1C_FWD_CTAS 4
+#endif
+
+template <int MODE, int S, bool SOFT, int GK>
+__global__ void __launch_bounds__(SSQ_THREADS, SSQ_K1C_FWD_CTAS)
+fq_shift_fwd_vec(const __grid_constant__ ShiftArgs a) {
+    constexpr int U = SSQ_K1C_FWD_U;
+    const int hard_targets = SOFT ? 0 : a.hard_targets, hard_round = SOFT ? 0 : a.hard_round;
+    const uint32_t i0 = blockIdx.x * (uint32_t)(SSQ_THREADS * U) + threadIdx.x;
     float4 wv[U], bv[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        const int64_t i = i0 + (int64_t)u * SSQ_THREADS;
+        const uint32_t i = i0 + u * SSQ_THREADS;
         wv[u] = bv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < total4) { wv[u] = ld_stream4(w + i * 4); if (MODE == SSQ_SHIFT_ADASHIFT) bv[u] = ld_stream4(beta + i * 4); }
+        if (i < a.total4) {
+            wv[u] = ld_stream4(a.w + (size_t)i * 4);
+            if (MODE == SSQ_SHIFT_ADASHIFT) bv[u] = ld_stream4(a.beta + (size_t)i * 4);
+        }
     }
-    TileWalk tw;                                   // c = row (output channel), col = float4 column inside the row
-    tw.init((uint64_t)i0, K4, (uint64_t)oc);
-    float ds[S], d = 0.f, z = 0.f;
-    Recip R[S];
+    RowP<S> R;
     uint32_t r_have = 0xffffffffu;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        const int64_t i = i0 + (int64_t)u * SSQ_THREADS;
-        if (i < total4) {
-            const uint32_t r = tw.c, k0 = tw.col * 4;
-            if (r != r_have) {                     // row parameters: reused by the thread's next vector when it is in the same row
+        const uint32_t i = i0 + u * SSQ_THREADS;
+        if (i >= a.total4) break;
+        const uint32_t row = fastdiv(i, a.dK4), k0 = (i - row * a.K4) * 4;
+        if (row != r_have) { row_params<MODE, S>(R, a, row); r_have = row; }
+        if (!(R.ok && small4(wv[u]))) { shift_fwd_slow<MODE>(a, i); continue; }
+        float pe[4][S];
+        group_probs<S, GK>(a, k0, pe);
+        const float xe[4] = {wv[u].x, wv[u].y, wv[u].z, wv[u].w}, be[4] = {bv[u].x, bv[u].y, bv[u].z, bv[u].w};
+        float out[4];
 #pragma unroll
-                for (int sft = 0; sft < S; ++sft) { ds[sft] = __ldg(shift_delta + (int64_t)sft * oc + r); R[sft] = make_recip(ds[sft]); }
-                d = __ldg(delta + r); z = __ldg(zp + r);
-                r_have = r;
+        for (int e = 0; e < 4; ++e) {
+            float t[S];
+            candidates<MODE, S>(xe[e], R, t);
+            const float mix = mixture<S>(t, pe[e], hard_targets);
+            if (MODE == SSQ_SHIFT_DEQUANT) out[e] = mix;
+            else {
+                const float rr = hard_round ? ((be[e] >= 0.f) ? 1.f : 0.f) : rect_sigmoid(be[e]);
+                const float xi = __fadd_rn(__fadd_rn(mix, rr), R.c1);
+                out[e] = __fmul_rn(__fsub_rn(fminf(fmaxf(xi, a.qmin), a.qmax), R.c1), R.c0);
             }
-            float qa[S][4];
-            const bool small = small4(wv[u]);
-#pragma unroll
-            for (int sft = 0; sft < S; ++sft) {
-                const float4 q = div4_exact(wv[u], R[sft], small);
-                qa[sft][0] = q.x; qa[sft][1] = q.y; qa[sft][2] = q.z; qa[sft][3] = q.w;
-            }
-            uint32_t g = k0 / kk, rem = k0 - g * kk;
-            float pv[S], p1[S];
-#pragma unroll
-            for (int sft = 0; sft < S; ++sft) pv[sft] = __ldg(p + g * S + sft);
-            const uint32_t n0 = kk - rem;          // elements of this vector that still belong to group g
-            if (WIDE) {
-                const uint32_t g1 = g < last_group ? g + 1 : g;
-#pragma unroll
-                for (int sft = 0; sft < S; ++sft) p1[sft] = __ldg(p + g1 * S + sft);
-            }
-            const float be[4] = {bv[u].x, bv[u].y, bv[u].z, bv[u].w};
-            float out[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                if (WIDE) {
-                    if (e > 0 && (uint32_t)e == n0) {
-#pragma unroll
-                        for (int sft = 0; sft < S; ++sft) pv[sft] = p1[sft];
-                    }
-                } else if (rem == kk) {            // next input channel: its own group probabilities
-                    rem = 0; ++g;
-#pragma unroll
-                    for (int sft = 0; sft < S; ++sft) pv[sft] = __ldg(p + g * S + sft);
-                }
-                float uu[S], t[S]; bool inside; float dh;
-#pragma unroll
-                for (int sft = 0; sft < S; ++sft) uu[sft] = qa[sft][e];
-                out[e] = shift_eval<MODE, S>(uu, ds, d, z, pv, be[e], hard_targets, hard_round, qmin, qmax, t, inside, dh);
-                ++rem;
-            }
-            st_stream4(y + i * 4, make_float4(out[0], out[1], out[2], out[3]));
         }
-        tw.step(SSQ_THREADS);
+        st_stream4(a.y + (size_t)i * 4, make_float4(out[0], out[1], out[2], out[3]));
     }
 }
 
-// backward: a thread owns 4 adjacent columns and walks the rows of its slab, two rows in flight; per-column sums of
-// d y / d p[g, i] in registers -> partial[slab][K][S] (the finish kernel adds slabs and the kk columns of a group in fp64)
-template <int MODE, int S, bool SOFT>
-__global__ void __launch_bounds__(SSQ_THREADS, 4)
-fq_shift_bwd_vec(const float* __restrict__ gy, const float* __restrict__ w, const float* __restrict__ shift_delta,
-                 const float* __restrict__ delta, const float* __restrict__ zp, const float* __restrict__ p,
-                 const float* __restrict__ beta, float* __restrict__ gbeta, float* __restrict__ partial,
-                 int64_t oc, uint32_t K4, uint32_t kk, int hard_round_rt, float qmin, float qmax, int64_t rows_per_slab) {
-    const uint32_t col4 = blockIdx.x * blockDim.x + threadIdx.x;
-    if (col4 >= K4) return;
-    const int hard_round = SOFT ? 0 : hard_round_rt;
-    const int64_t K = (int64_t)K4 * 4;
-    const int64_t r0 = (int64_t)blockIdx.y * rows_per_slab;
-    const int64_t r1 = r0 + rows_per_slab < oc ? r0 + rows_per_slab : oc;
+// backward: CTA = 1024 adjacent columns (one float4 per thread) x a slab of rows, two rows in flight per thread; per-column
+// sums of d y / d p[g, i] stay in registers -> partial[slab][K][S] (the finish kernel adds slabs and the kk columns of a group in
+// fp64). The slab's row constants are staged in shared memory SSQ_SHIFT_RB rows at a time (one thread per row computes them).
+// Resident CTAs per SM: 4 for the dequantised mixture (61 registers), 3 for adaShift (80 registers, no spills) — the slab
+// count is chosen so that the grid is exactly one wave at that occupancy (slab_plan).
+#define SSQ_SHIFT_RB 64
+#define SSQ_K1C_BWD_CTAS(MODE) ((MODE) == SSQ_SHIFT_ADASHIFT ? 3 : 4)
+template <int MODE, int S, bool SOFT, int GK>
+__global__ void __launch_bounds__(SSQ_THREADS, SSQ_K1C_BWD_CTAS(MODE))
+fq_shift_bwd_vec(const __grid_constant__ ShiftArgs a) {
+    constexpr int NQ = (2 * S + 3 + 3) / 4;        // float4s per row: ds[S], r[S], c0, c1, ok
+    __shared__ float4 srow[SSQ_SHIFT_RB][NQ];
+    const uint32_t col4 = blockIdx.x * SSQ_THREADS + threadIdx.x;
+    const bool live = col4 < a.K4;
+    const int hard_round = SOFT ? 0 : a.hard_round;
+    const int64_t K = (int64_t)a.K4 * 4;
+    const int64_t r0 = (int64_t)blockIdx.y * a.rows_per_slab;
+    const int64_t r1 = r0 + a.rows_per_slab < a.oc ? r0 + a.rows_per_slab : a.oc;
+    const int nrows = (int)(r1 - r0);
     float pe[4][S], acc[4][S];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const uint32_t g = (col4 * 4 + e) / kk;
-#pragma unroll
-        for (int sft = 0; sft < S; ++sft) { pe[e][sft] = __ldg(p + g * S + sft); acc[e][sft] = 0.f; }
-    }
-    auto row = [&](int64_t r, const float4& g4, const float4& w4, const float4& b4) {
-        float ds[S], qa[S][4];
-        const bool small = small4(w4);
-#pragma unroll
-        for (int sft = 0; sft < S; ++sft) {
-            ds[sft] = __ldg(shift_delta + (int64_t)sft * oc + r);
-            const float4 q = div4_exact(w4, make_recip(ds[sft]), small);
-            qa[sft][0] = q.x; qa[sft][1] = q.y; qa[sft][2] = q.z; qa[sft][3] = q.w;
-        }
-        const float d = __ldg(delta + r), z = __ldg(zp + r);
-        const float ge[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
-        float gb[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            float uu[S], t[S]; bool inside; float dh;
-#pragma unroll
-            for (int sft = 0; sft < S; ++sft) uu[sft] = qa[sft][e];
-            (void)shift_eval<MODE, S>(uu, ds, d, z, pe[e], be[e], 0, hard_round, qmin, qmax, t, inside, dh);
-            float gm = ge[e];                       // gradient wrt the mixture
-            gb[e] = 0.f;
-            if (MODE == SSQ_SHIFT_ADASHIFT) {
-                gm = inside ? ge[e] * d : 0.f;
-                gb[e] = hard_round ? 0.f : gm * dh;
-            }
-#pragma unroll
-            for (int sft = 0; sft < S; ++sft) acc[e][sft] += gm * t[sft];
-        }
-        if (MODE == SSQ_SHIFT_ADASHIFT && gbeta) st_stream4(gbeta + r * K + (int64_t)col4 * 4, make_float4(gb[0], gb[1], gb[2], gb[3]));
-    };
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    int64_t r = r0;
-    for (; r + 1 < r1; r += 2) {
-        const int64_t ea = r * K + (int64_t)col4 * 4, eb = ea + K;
-        const float4 ga = ld_stream4(gy + ea), wa = ld_stream4(w + ea), gbv = ld_stream4(gy + eb), wb = ld_stream4(w + eb);
-        const float4 ba = (MODE == SSQ_SHIFT_ADASHIFT) ? ld_stream4(beta + ea) : zero4;
-        const float4 bb = (MODE == SSQ_SHIFT_ADASHIFT) ? ld_stream4(beta + eb) : zero4;
-        row(r, ga, wa, ba);
-        row(r + 1, gbv, wb, bb);
-    }
-    if (r < r1) {
-        const int64_t ea = r * K + (int64_t)col4 * 4;
-        row(r, ld_stream4(gy + ea), ld_stream4(w + ea), (MODE == SSQ_SHIFT_ADASHIFT) ? ld_stream4(beta + ea) : zero4);
-    }
 #pragma unroll
     for (int e = 0; e < 4; ++e)
 #pragma unroll
-        for (int sft = 0; sft < S; ++sft)
-            partial[((int64_t)blockIdx.y * K + (int64_t)col4 * 4 + e) * S + sft] = acc[e][sft];
+        for (int s = 0; s < S; ++s) { pe[e][s] = 0.f; acc[e][s] = 0.f; }
+    if (live && MODE == SSQ_SHIFT_ADASHIFT) group_probs<S, GK>(a, col4 * 4, pe);
+    auto row = [&](int64_t r, int lr, const float4& g4, const float4& w4, const float4& b4) {
+        RowP<S> R;
+        {
+            float f[4 * NQ];
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) { const float4 v = srow[lr][j]; f[4 * j] = v.x; f[4 * j + 1] = v.y; f[4 * j + 2] = v.z; f[4 * j + 3] = v.w; }
+#pragma unroll
+            for (int s = 0; s < S; ++s) { R.ds[s] = f[s]; R.r[s] = f[S + s]; }
+            R.c0 = f[2 * S]; R.c1 = f[2 * S + 1]; R.ok = f[2 * S + 2] != 0.f;
+        }
+        if (!(R.ok && small4(w4))) {
+            const SlowTerms o = shift_bwd_slow<MODE>(a, r, col4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+#pragma unroll
+                for (int s = 0; s < S; ++s) acc[e][s] += o.gm_t[e][s];
+            return;
+        }
+        const float xe[4] = {w4.x, w4.y, w4.z, w4.w}, ge[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
+        float gb[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float t[S];
+            candidates<MODE, S>(xe[e], R, t);
+            float gm = ge[e];                       // gradient wrt the mixture
+            gb[e] = 0.f;
+            if (MODE == SSQ_SHIFT_ADASHIFT) {
+                const float mix = mixture<S>(t, pe[e], 0);
+                float rr, dh = 0.f;
+                if (hard_round) rr = (be[e] >= 0.f) ? 1.f : 0.f;
+                else dh = rect_sigmoid_grad(be[e], rr);
+                const float xi = __fadd_rn(__fadd_rn(mix, rr), R.c1);
+                const bool inside = (xi >= a.qmin) && (xi <= a.qmax);
+                gm = inside ? ge[e] * R.c0 : 0.f;
+                gb[e] = hard_round ? 0.f : gm * dh;
+            }
+#pragma unroll
+            for (int s = 0; s < S; ++s) acc[e][s] += gm * t[s];
+        }
+        if (MODE == SSQ_SHIFT_ADASHIFT && a.gbeta) st_stream4(a.gbeta + r * K + (int64_t)col4 * 4, make_float4(gb[0], gb[1], gb[2], gb[3]));
+    };
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c0 = 0; c0 < nrows; c0 += SSQ_SHIFT_RB) {
+        const int nrow = nrows - c0 < SSQ_SHIFT_RB ? nrows - c0 : SSQ_SHIFT_RB;
+        __syncthreads();
+        if ((int)threadIdx.x < nrow) {
+            RowP<S> R;
+            row_params<MODE, S>(R, a, r0 + c0 + threadIdx.x);
+            float f[4 * NQ];
+#pragma unroll
+            for (int j = 0; j < 4 * NQ; ++j) f[j] = 0.f;
+#pragma unroll
+            for (int s = 0; s < S; ++s) { f[s] = R.ds[s]; f[S + s] = R.r[s]; }
+            f[2 * S] = R.c0; f[2 * S + 1] = R.c1; f[2 * S + 2] = R.ok ? 1.f : 0.f;
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) srow[threadIdx.x][j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        }
+        __syncthreads();
+        if (!live) continue;
+        int lr = 0;
+        for (; lr + 1 < nrow; lr += 2) {
+            const int64_t r = r0 + c0 + lr, ea = r * K + (int64_t)col4 * 4, eb = ea + K;
+            const float4 ga = ld_stream4(a.gy + ea), wa = ld_stream4(a.w + ea), gbv = ld_stream4(a.gy + eb), wb = ld_stream4(a.w + eb);
+            const float4 ba = (MODE == SSQ_SHIFT_ADASHIFT) ? ld_stream4(a.beta + ea) : zero4;
+            const float4 bb = (MODE == SSQ_SHIFT_ADASHIFT) ? ld_stream4(a.beta + eb) : zero4;
+            row(r, lr, ga, wa, ba);
+            row(r + 1, lr + 1, gbv, wb, bb);
+        }
+        if (lr < nrow) {
+            const int64_t r = r0 + c0 + lr, ea = r * K + (int64_t)col4 * 4;
+            row(r, lr, ld_stream4(a.gy + ea), ld_stream4(a.w + ea), (MODE == SSQ_SHIFT_ADASHIFT) ? ld_stream4(a.beta + ea) : zero4);
+        }
+    }
+    if (!live) return;
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+            a.partial[((int64_t)blockIdx.y * K + (int64_t)col4 * 4 + e) * S + s] = acc[e][s];
 }
 
+// one warp per (group, shift): lanes stride over the nslab * kk partials, fixed shuffle tree in fp64 (deterministic)
 __global__ void __launch_bounds__(SSQ_THREADS)
 fq_shift_bwd_finish_kernel(const float* __restrict__ partial, float* __restrict__ gp, int64_t ic, int64_t K, int64_t kk,
                            int S, int nslab) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= ic * S) return;
+    const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= ic * S) return;                          // whole warps leave together
+    const int lane = threadIdx.x & 31;
     const int64_t g = t / S; const int i = (int)(t - g * S);
+    const int64_t items = (int64_t)nslab * kk;
     double s = 0.0;
-    for (int sl = 0; sl < nslab; ++sl)
-        for (int64_t k = g * kk; k < (g + 1) * kk; ++k) s += (double)partial[((int64_t)sl * K + k) * S + i];
-    gp[t] = (float)s;
+    for (int64_t j = lane; j < items; j += 32) {
+        const int64_t sl = j / kk, k = g * kk + (j - sl * kk);
+        s += (double)partial[(sl * K + k) * S + i];
+    }
+    s = warp_sum(s);
+    if (lane == 0) gp[t] = (float)s;
 }
 
-static inline void slab_plan(int64_t oc, int64_t K, int& nslab, int64_t& rows_per_slab, bool vec = false) {
+static inline void slab_plan(int64_t oc, int64_t K, int& nslab, int64_t& rows_per_slab, int vec_ctas = 0) {
+    const bool vec = vec_ctas > 0;
     int64_t colblocks = ((vec ? K / 4 : K) + SSQ_THREADS - 1) / SSQ_THREADS;
-    // vec: ~3 resident CTAs per SM (about 80 registers), slabs of at least 4 rows so the partials stay small
-    int64_t want = ((int64_t)SSQ_NUM_SMS * (vec ? 4 : SSQ_CTAS_PER_SM) + colblocks - 1) / colblocks;
+    // vec: ONE wave of column-block x slab CTAs at the occupancy the launch bounds guarantee (rounding the slab count up
+    // gave 612 CTAs for 592 slots: a second wave of 20 CTAs that cost as much as the first); slabs of at least 4 rows so the
+    // partials stay small
+    int64_t want = vec ? ((int64_t)SSQ_NUM_SMS * vec_ctas) / colblocks
+                       : ((int64_t)SSQ_NUM_SMS * SSQ_CTAS_PER_SM + colblocks - 1) / colblocks;
     if (vec && want > (oc + 3) / 4) want = (oc + 3) / 4;
     if (want > oc) want = oc;
     if (want < 1) want = 1;
     rows_per_slab = (oc + want - 1) / want;
     nslab = (int)((oc + rows_per_slab - 1) / rows_per_slab);
+}
+
+static inline unsigned finish_grid(int64_t ic, int nshift) {
+    return (unsigned)((ic * nshift * 32 + SSQ_THREADS - 1) / SSQ_THREADS);        // one warp per (group, shift)
+}
+static inline int group_kind(int64_t kk, const float* p) { return kk >= 4 ? 1 : (kk == 1 && aligned16(p) ? 2 : 0); }
+static inline ShiftArgs shift_args(const float* w, const float* shift_delta, const float* delta, const float* zp, const float* p,
+                                   const float* beta, const float* gy, float* y, float* gbeta, float* partial,
+                                   int64_t oc, int64_t K, int64_t kk, int nshift, int hard_targets, int hard_round,
+                                   float qmin, float qmax, int64_t rows_per_slab) {
+    ShiftArgs a;
+    a.w = w; a.shift_delta = shift_delta; a.delta = delta; a.zp = zp; a.p = p; a.beta = beta; a.gy = gy;
+    a.y = y; a.gbeta = gbeta; a.partial = partial;
+    a.oc = oc; a.rows_per_slab = rows_per_slab;
+    a.K4 = (uint32_t)(K / 4); a.kk = (uint32_t)kk; a.total4 = (uint32_t)(oc * (K / 4)); a.last_group = (uint32_t)(K / kk - 1);
+    a.dK4 = make_fastdiv(a.K4); a.dkk = make_fastdiv(a.kk >= 2 ? a.kk : 2);   // kk == 1 never divides (GK 2, or k0 + e itself)
+    a.S = nshift; a.hard_targets = hard_targets; a.hard_round = hard_round;
+    a.q_int = (qmin == (float)(int64_t)qmin) && (qmax == (float)(int64_t)qmax) && qmin >= -0x1p22f && qmin <= 0x1p22f &&
+              qmax >= -0x1p22f && qmax <= 0x1p22f;
+    a.qmin = qmin; a.qmax = qmax;
+    return a;
 }
 
 }  // namespace ssq
@@ -437,19 +601,21 @@ extern "C" int ssq_fq_shift_fwd(const float* w, const float* shift_delta, const 
     int grid = grid_for((n + SSQ_THREADS - 1) / SSQ_THREADS);
     cudaStream_t st = (cudaStream_t)stream;
     if (mode != SSQ_SHIFT_DEQUANT && mode != SSQ_SHIFT_ADASHIFT) return SSQ_ERR_MODE;
-    const bool vec = !per_element && (K % 4 == 0) && K / 4 < 0x7fffffff && kk < 0x7fffffff && aligned16(w) && aligned16(y) &&
-                     (!beta || aligned16(beta));
+    const bool vec = !per_element && (K % 4 == 0) && K >= 8 && n / 4 < 0x7fffffff && aligned16(w) && aligned16(y) && (!beta || aligned16(beta));
     if (vec) {
-        const unsigned vgrid = tile_grid((n / 4 + SSQ_THREADS * 2 - 1) / (SSQ_THREADS * 2), false);
-        const bool soft = !hard_targets && !hard_round, wide = kk >= 4;
-#define FWDK(M, SS, SO, WI) fq_shift_fwd_vec<M, SS, SO, WI><<<vgrid, SSQ_THREADS, 0, st>>>(w, shift_delta, delta, zero_point, p, beta, y, oc, \
-        (uint32_t)(K / 4), (uint32_t)kk, hard_targets, hard_round, qmin, qmax)
-#define FWDV(M, SS) do { if (soft) { if (wide) FWDK(M, SS, true, true); else FWDK(M, SS, true, false); } \
-                         else { if (wide) FWDK(M, SS, false, true); else FWDK(M, SS, false, false); } } while (0)
+        ShiftArgs a = shift_args(w, shift_delta, delta, zero_point, p, beta, nullptr, y, nullptr, nullptr, oc, K, kk, nshift,
+                                 hard_targets, hard_round, qmin, qmax, 0);
+        const unsigned vgrid = tile_grid((n / 4 + SSQ_THREADS * SSQ_K1C_FWD_U - 1) / (SSQ_THREADS * SSQ_K1C_FWD_U), false);
+        const bool soft = !hard_targets && !hard_round;
+        const int gk = group_kind(kk, p);
+#define FWDK(M, SS, SO, GK) fq_shift_fwd_vec<M, SS, SO, GK><<<vgrid, SSQ_THREADS, 0, st>>>(a)
+#define FWDG(M, SS, SO) do { if (gk == 1) FWDK(M, SS, SO, 1); else if (gk == 2) FWDK(M, SS, SO, 2); else FWDK(M, SS, SO, 0); } while (0)
+#define FWDV(M, SS) do { if (soft) FWDG(M, SS, true); else FWDG(M, SS, false); } while (0)
 #define FWDS(M) switch (nshift) { case 1: FWDV(M, 1); break; case 2: FWDV(M, 2); break; case 3: FWDV(M, 3); break; default: FWDV(M, 4); }
         if (mode == SSQ_SHIFT_DEQUANT) { FWDS(SSQ_SHIFT_DEQUANT) } else { FWDS(SSQ_SHIFT_ADASHIFT) }
 #undef FWDS
 #undef FWDV
+#undef FWDG
 #undef FWDK
         return launch_status();
     }
@@ -465,8 +631,11 @@ extern "C" size_t ssq_shift_bwd_ws_bytes(int64_t oc, int64_t ic, int64_t kk, int
     if (per_element || oc <= 0 || ic <= 0 || kk <= 0) return 16;
     int nslab, nslab_v = 0; int64_t rps;
     slab_plan(oc, ic * kk, nslab, rps);
-    if ((ic * kk) % 4 == 0) slab_plan(oc, ic * kk, nslab_v, rps, true);
-    if (nslab_v > nslab) nslab = nslab_v;
+    if ((ic * kk) % 4 == 0)
+        for (int mode = 0; mode < 2; ++mode) {           // the mode is not known here: room for either plan
+            slab_plan(oc, ic * kk, nslab_v, rps, SSQ_K1C_BWD_CTAS(mode));
+            if (nslab_v > nslab) nslab = nslab_v;
+        }
     return (size_t)nslab * (size_t)(ic * kk) * (size_t)nshift * sizeof(float) + 16;
 }
 
@@ -483,26 +652,30 @@ extern "C" int ssq_fq_shift_bwd(const float* gy, const float* w, const float* sh
     if (!per_element && (!ws || ws_bytes < ssq_shift_bwd_ws_bytes(oc, ic, kk, nshift, per_element))) return SSQ_ERR_WORKSPACE;
     const int64_t K = ic * kk;
     if (mode != SSQ_SHIFT_DEQUANT && mode != SSQ_SHIFT_ADASHIFT) return SSQ_ERR_MODE;
-    const bool vec = !per_element && (K % 4 == 0) && K / 4 < 0x7fffffff && kk < 0x7fffffff && aligned16(gy) && aligned16(w) &&
+    const bool vec = !per_element && (K % 4 == 0) && K >= 8 && (oc * K) / 4 < 0x7fffffff && aligned16(gy) && aligned16(w) &&
                      (!beta || aligned16(beta)) && (!gbeta || aligned16(gbeta));
     int nslab; int64_t rps;
-    slab_plan(oc, K, nslab, rps, vec);
+    slab_plan(oc, K, nslab, rps, vec ? SSQ_K1C_BWD_CTAS(mode) : 0);
     if (nslab > 65535) return SSQ_ERR_SIZE;
     cudaStream_t st = (cudaStream_t)stream;
     float* partial = reinterpret_cast<float*>(ws);
     if (vec) {
         dim3 vgrid((unsigned)((K / 4 + SSQ_THREADS - 1) / SSQ_THREADS), (unsigned)nslab);
-#define BWDK(M, SS, SO) fq_shift_bwd_vec<M, SS, SO><<<vgrid, SSQ_THREADS, 0, st>>>(gy, w, shift_delta, delta, zero_point, p, beta, gbeta, partial, \
-        oc, (uint32_t)(K / 4), (uint32_t)kk, hard_round, qmin, qmax, rps)
-#define BWDV(M, SS) do { if (!hard_round) BWDK(M, SS, true); else BWDK(M, SS, false); } while (0)
+        ShiftArgs a = shift_args(w, shift_delta, delta, zero_point, p, beta, gy, nullptr, gbeta, partial, oc, K, kk, nshift,
+                                 0, hard_round, qmin, qmax, rps);
+        const int gk = group_kind(kk, p);
+#define BWDK(M, SS, SO, GK) fq_shift_bwd_vec<M, SS, SO, GK><<<vgrid, SSQ_THREADS, 0, st>>>(a)
+#define BWDG(M, SS, SO) do { if (gk == 1) BWDK(M, SS, SO, 1); else if (gk == 2) BWDK(M, SS, SO, 2); else BWDK(M, SS, SO, 0); } while (0)
+#define BWDV(M, SS) do { if (!hard_round) BWDG(M, SS, true); else BWDG(M, SS, false); } while (0)
 #define BWDS(M) switch (nshift) { case 1: BWDV(M, 1); break; case 2: BWDV(M, 2); break; case 3: BWDV(M, 3); break; default: BWDV(M, 4); }
         if (mode == SSQ_SHIFT_DEQUANT) { BWDS(SSQ_SHIFT_DEQUANT) } else { BWDS(SSQ_SHIFT_ADASHIFT) }
 #undef BWDS
 #undef BWDV
+#undef BWDG
 #undef BWDK
         int ev = launch_status();
         if (ev) return ev;
-        fq_shift_bwd_finish_kernel<<<(unsigned)((ic * nshift + SSQ_THREADS - 1) / SSQ_THREADS), SSQ_THREADS, 0, st>>>(partial, gp, ic, K, kk, nshift, nslab);
+        fq_shift_bwd_finish_kernel<<<finish_grid(ic, nshift), SSQ_THREADS, 0, st>>>(partial, gp, ic, K, kk, nshift, nslab);
         return launch_status();
     }
     dim3 grid((unsigned)((K + SSQ_THREADS - 1) / SSQ_THREADS), (unsigned)nslab);
@@ -513,6 +686,6 @@ extern "C" int ssq_fq_shift_bwd(const float* gy, const float* w, const float* sh
     else return SSQ_ERR_MODE;
     int e = launch_status();
     if (e || per_element) return e;
-    fq_shift_bwd_finish_kernel<<<(unsigned)((ic * nshift + SSQ_THREADS - 1) / SSQ_THREADS), SSQ_THREADS, 0, st>>>(partial, gp, ic, K, kk, nshift, nslab);
+    fq_shift_bwd_finish_kernel<<<finish_grid(ic, nshift), SSQ_THREADS, 0, st>>>(partial, gp, ic, K, kk, nshift, nslab);
     return launch_status();
 }
