@@ -371,14 +371,14 @@ fq_shift_fwd_vec(const __grid_constant__ ShiftArgs a) {
         }
     }
     RowP<S> R;
-    uint32_t r_have = 0xffffffffu;
+    uint32_t r_have = 0xffffffffu, slow_mask = 0;      // slow vectors are redone after the loop: no call inside it
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const uint32_t i = i0 + u * SSQ_THREADS;
         if (i >= a.total4) break;
         const uint32_t row = fastdiv(i, a.dK4), k0 = (i - row * a.K4) * 4;
         if (row != r_have) { row_params<MODE, S>(R, a, row); r_have = row; }
-        if (!(R.ok && small4(wv[u]))) { shift_fwd_slow<MODE>(a, i); continue; }
+        if (!(R.ok && small4(wv[u]))) { slow_mask |= 1u << u; continue; }
         float pe[4][S];
         group_probs<S, GK>(a, k0, pe);
         const float xe[4] = {wv[u].x, wv[u].y, wv[u].z, wv[u].w}, be[4] = {bv[u].x, bv[u].y, bv[u].z, bv[u].w};
@@ -397,6 +397,10 @@ fq_shift_fwd_vec(const __grid_constant__ ShiftArgs a) {
         }
         st_stream4(a.y + (size_t)i * 4, make_float4(out[0], out[1], out[2], out[3]));
     }
+    if (slow_mask) {
+        for (int u = 0; u < U; ++u)
+            if ((slow_mask >> u) & 1u) shift_fwd_slow<MODE>(a, i0 + u * SSQ_THREADS);
+    }
 }
 
 // backward: CTA = 1024 adjacent columns (one float4 per thread) x a slab of rows, two rows in flight per thread; per-column
@@ -409,8 +413,9 @@ fq_shift_fwd_vec(const __grid_constant__ ShiftArgs a) {
 template <int MODE, int S, bool SOFT, int GK>
 __global__ void __launch_bounds__(SSQ_THREADS, SSQ_K1C_BWD_CTAS(MODE))
 fq_shift_bwd_vec(const __grid_constant__ ShiftArgs a) {
-    constexpr int NQ = (2 * S + 3 + 3) / 4;        // float4s per row: ds[S], r[S], c0, c1, ok
+    constexpr int NQ = (2 * S + 2 + 3) / 4;        // float4s per row: ds[S], r[S], c0, c1
     __shared__ float4 srow[SSQ_SHIFT_RB][NQ];
+    __shared__ uint32_t sok[SSQ_SHIFT_RB];
     const uint32_t col4 = blockIdx.x * SSQ_THREADS + threadIdx.x;
     const bool live = col4 < a.K4;
     const int hard_round = SOFT ? 0 : a.hard_round;
@@ -424,7 +429,18 @@ fq_shift_bwd_vec(const __grid_constant__ ShiftArgs a) {
 #pragma unroll
         for (int s = 0; s < S; ++s) { pe[e][s] = 0.f; acc[e][s] = 0.f; }
     if (live && MODE == SSQ_SHIFT_ADASHIFT) group_probs<S, GK>(a, col4 * 4, pe);
-    auto row = [&](int64_t r, int lr, const float4& g4, const float4& w4, const float4& b4) {
+    uint64_t slow_rows = 0;
+    // fast-path test of one row's vectors. It reads one lane of EVERY loaded vector (x * 0 keeps NaN / Inf and cannot be folded
+    // away), so all loads of a row pair are consumed before the first branch: without that ptxas sinks the second row's loads
+    // below the first row's branch and the two-rows-in-flight pipeline degenerates (0.83 -> 0.74 of peak).
+    auto fast_ok = [&](int lr, const float4& g4, const float4& w4, const float4& b4) {
+        float sum = (fabsf(w4.x) + fabsf(w4.y)) + (fabsf(w4.z) + fabsf(w4.w));
+        sum = fmaf(g4.x, 0.0f, sum);
+        if (MODE == SSQ_SHIFT_ADASHIFT) sum = fmaf(b4.x, 0.0f, sum);
+        return (sok[lr] != 0u) && (sum < SSQ_DIV_XMAX);
+    };
+    auto row = [&](int64_t r, int lr, const float4& g4, const float4& w4, const float4& b4, bool fast) {
+        if (!fast) { slow_rows |= 1ull << lr; return; }   // redone at the end of the chunk: no call in the row loop
         RowP<S> R;
         {
             float f[4 * NQ];
@@ -432,15 +448,7 @@ fq_shift_bwd_vec(const __grid_constant__ ShiftArgs a) {
             for (int j = 0; j < NQ; ++j) { const float4 v = srow[lr][j]; f[4 * j] = v.x; f[4 * j + 1] = v.y; f[4 * j + 2] = v.z; f[4 * j + 3] = v.w; }
 #pragma unroll
             for (int s = 0; s < S; ++s) { R.ds[s] = f[s]; R.r[s] = f[S + s]; }
-            R.c0 = f[2 * S]; R.c1 = f[2 * S + 1]; R.ok = f[2 * S + 2] != 0.f;
-        }
-        if (!(R.ok && small4(w4))) {
-            const SlowTerms o = shift_bwd_slow<MODE>(a, r, col4);
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-#pragma unroll
-                for (int s = 0; s < S; ++s) acc[e][s] += o.gm_t[e][s];
-            return;
+            R.c0 = f[2 * S]; R.c1 = f[2 * S + 1];
         }
         const float xe[4] = {w4.x, w4.y, w4.z, w4.w}, ge[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
         float gb[4];
@@ -477,7 +485,8 @@ fq_shift_bwd_vec(const __grid_constant__ ShiftArgs a) {
             for (int j = 0; j < 4 * NQ; ++j) f[j] = 0.f;
 #pragma unroll
             for (int s = 0; s < S; ++s) { f[s] = R.ds[s]; f[S + s] = R.r[s]; }
-            f[2 * S] = R.c0; f[2 * S + 1] = R.c1; f[2 * S + 2] = R.ok ? 1.f : 0.f;
+            f[2 * S] = R.c0; f[2 * S + 1] = R.c1;
+            sok[threadIdx.x] = R.ok ? 1u : 0u;
 #pragma unroll
             for (int j = 0; j < NQ; ++j) srow[threadIdx.x][j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
         }
@@ -489,12 +498,23 @@ fq_shift_bwd_vec(const __grid_constant__ ShiftArgs a) {
             const float4 ga = ld_stream4(a.gy + ea), wa = ld_stream4(a.w + ea), gbv = ld_stream4(a.gy + eb), wb = ld_stream4(a.w + eb);
             const float4 ba = (MODE == SSQ_SHIFT_ADASHIFT) ? ld_stream4(a.beta + ea) : zero4;
             const float4 bb = (MODE == SSQ_SHIFT_ADASHIFT) ? ld_stream4(a.beta + eb) : zero4;
-            row(r, lr, ga, wa, ba);
-            row(r + 1, lr + 1, gbv, wb, bb);
+            const bool fa = fast_ok(lr, ga, wa, ba), fb = fast_ok(lr + 1, gbv, wb, bb);
+            row(r, lr, ga, wa, ba, fa);
+            row(r + 1, lr + 1, gbv, wb, bb, fb);
         }
         if (lr < nrow) {
             const int64_t r = r0 + c0 + lr, ea = r * K + (int64_t)col4 * 4;
-            row(r, lr, ld_stream4(a.gy + ea), ld_stream4(a.w + ea), (MODE == SSQ_SHIFT_ADASHIFT) ? ld_stream4(a.beta + ea) : zero4);
+            const float4 ga = ld_stream4(a.gy + ea), wa = ld_stream4(a.w + ea), ba = (MODE == SSQ_SHIFT_ADASHIFT) ? ld_stream4(a.beta + ea) : zero4;
+            row(r, lr, ga, wa, ba, fast_ok(lr, ga, wa, ba));
+        }
+        while (slow_rows) {
+            const int sl = __ffsll((long long)slow_rows) - 1;
+            slow_rows &= slow_rows - 1;
+            const SlowTerms o = shift_bwd_slow<MODE>(a, r0 + c0 + sl, col4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+#pragma unroll
+                for (int s = 0; s < S; ++s) acc[e][s] += o.gm_t[e][s];
         }
     }
     if (!live) return;

@@ -373,6 +373,81 @@ def test_shift_oracle_resnet_shape(ops):
             assert_close(host(gb), gb_ref, what=name + " gbeta")
 
 
+def _misaligned(t):
+    """same values at an address that is 4 (mod 16): forces the scalar K1c kernels"""
+    buf = torch.empty(t.numel() + 1, device=t.device, dtype=t.dtype)
+    v = buf[1:]
+    v.copy_(t.reshape(-1))
+    return v.view(t.shape)
+
+
+def _same_bits(a, b):
+    a = a.reshape(-1); b = b.reshape(-1)
+    return bool(((a.view(torch.int32) == b.view(torch.int32)) | (torch.isnan(a) & torch.isnan(b))).all())
+
+
+@pytest.mark.parametrize("shape", [(64, 64, 3, 3), (96, 64, 1, 1), (48, 32, 1, 2), (40, 24, 5, 5), (33, 20, 1, 1), (7, 4, 1, 3), (3, 4, 1, 1)])
+@pytest.mark.parametrize("S", [1, 2, 3, 4])
+def test_shift_vector_paths_vs_oracle_and_scalar(ops, shape, S):
+    """K1c vector kernels (group layouts kk >= 4 / kk == 1 / narrow groups, K = 4 fallback) against the oracle, and bit-for-bit
+    against the scalar kernels of the same library, incl. the out-of-line slow path: NaN / Inf / huge / denormal weights, scales
+    outside the hoisted-reciprocal range and a non-integer zero point"""
+    oc, ic, kh, kw = shape
+    r = rng(oc * 1000 + ic * 10 + kh * kw + S)
+    shifts = [0.96875, 1.03125, 1.0, 0.9375][:S]
+    w = (r.standard_normal(shape) * 0.05).astype(np.float32)
+    d = (np.abs(w.reshape(oc, -1)).max(1) / 3 * 1.3).astype(np.float32).reshape(oc, 1, 1, 1)
+    z = r.integers(0, 3, (oc, 1, 1, 1)).astype(np.float32)
+    alpha = (r.standard_normal((ic, S)) * 1.5).astype(np.float32)
+    beta = (r.standard_normal(shape) * 2).astype(np.float32)
+    gy = r.standard_normal(shape).astype(np.float32)
+    p_ref = O.shift_probs(alpha)
+    W, D, Z, A, B, GY = dev(w), dev(d), dev(z), dev(alpha), dev(beta), dev(gy)
+    sd = torch.stack([D.flatten() * s for s in shifts])
+    # the oracle's own probabilities: with p one ulp apart, a mixture of equal floors lands one ulp either side of the clamp
+    # bound and the (legitimately discontinuous) inside-mask of the adaShift gradient flips
+    assert_close(host(ops.shift_probs_fwd(A)), p_ref, what="group probabilities")
+    P = dev(p_ref)
+    for mode, name in ((ops.SHIFT_DEQUANT, "dequant"), (ops.SHIFT_ADASHIFT, "adashift")):
+        for ht, hr in ((False, False), (True, True), (False, True)):
+            y = ops.fq_shift_fwd(W, sd, D, Z, P, B, mode, ht, hr, 0.0, 3.0, False)
+            ref = O.shift_forward(w, d, z, shifts, p_ref, 0, 3, name, hard_targets=ht, beta=beta, hard_round=hr)
+            if ht and (hr or mode == ops.SHIFT_DEQUANT):
+                assert_exact(host(y), ref, f"{name} hard ht={ht} hr={hr}")
+            else:
+                assert_close(host(y), ref, what=f"{name} ht={ht} hr={hr}")
+            ys = ops.fq_shift_fwd(_misaligned(W), sd, D, Z, P, _misaligned(B), mode, ht, hr, 0.0, 3.0, False)
+            assert _same_bits(y, ys), f"{name} ht={ht} hr={hr}: vector and scalar kernels differ"
+        gp, gb = ops.fq_shift_bwd(GY, W, sd, D, Z, P, B, mode, False, 0.0, 3.0, False, mode == ops.SHIFT_ADASHIFT)
+        gp_ref, gb_ref = O.shift_backward(gy, w, d, z, shifts, p_ref, 0, 3, name, beta=beta)
+        assert_close(host(gp), gp_ref, rtol=3e-5, what=name + " gp")
+        if gb_ref is not None:
+            assert_close(host(gb), gb_ref, what=name + " gbeta")
+    # slow path: the same float4 / row mixes ordinary and special values
+    if oc * ic * kh * kw >= 80:
+        ws = w.copy().reshape(-1)
+        ws[[3, 17, 40, 60, 70, 75, 76, 77, 78]] = [np.nan, np.inf, -np.inf, 1e30, -3e38, 0.0, -0.0, 1e-40, -1e-30]
+        ds = d.copy(); ds[1] = 1e-25
+        if oc > 2:
+            ds[2] = 1e25
+        zs = z.copy(); zs[0] = 1.25
+        WS, DS, ZS = dev(ws.reshape(shape)), dev(ds), dev(zs)
+        sds = torch.stack([DS.flatten() * s for s in shifts])
+        gs = GY.clone(); gs.view(-1)[[3, 17, 40]] = 0.0
+        for mode in (ops.SHIFT_DEQUANT, ops.SHIFT_ADASHIFT):
+            y = ops.fq_shift_fwd(WS, sds, DS, ZS, P, B, mode, False, False, 0.0, 3.0, False)
+            ys = ops.fq_shift_fwd(_misaligned(WS), sds, DS, ZS, P, _misaligned(B), mode, False, False, 0.0, 3.0, False)
+            assert _same_bits(y, ys), f"mode {mode}: vector and scalar kernels differ on special values"
+            gp, gb = ops.fq_shift_bwd(gs, WS, sds, DS, ZS, P, B, mode, False, 0.0, 3.0, False, mode == ops.SHIFT_ADASHIFT)
+            gps, gbs = ops.fq_shift_bwd(_misaligned(gs), _misaligned(WS), sds, DS, ZS, P, _misaligned(B), mode, False, 0.0, 3.0, False,
+                                        mode == ops.SHIFT_ADASHIFT)
+            fin = torch.isfinite(gps)
+            assert bool((torch.isfinite(gp) == fin).all())
+            assert_close(host(gp[fin]), host(gps[fin]), rtol=3e-5, what="gp vector vs scalar (special values)")
+            if gb is not None:
+                assert bool(((gb == gbs) | (torch.isnan(gb) & torch.isnan(gbs))).all()), "gbeta vector vs scalar (special values)"
+
+
 # ------------------------------------------------------------------------------------------- Adam / loop / affine
 def test_adam_and_loop_advance(ops):
     g = golden("adam")
