@@ -17,7 +17,9 @@ __device__ __forceinline__ float clampf_(float v, float lo, float hi) {
 struct AdaOut { float y, q, reg; };
 
 // u = w/delta already divided
-template <bool SOFT, bool REG>
+// FINITE: u came from the hoisted-reciprocal fast path (finite numerator, delta in range), so floor + r + z is finite and the
+// clamp may use FMNMX (2 instructions) instead of the NaN-preserving compare/select pairs (4)
+template <bool SOFT, bool REG, bool FINITE = false>
 __device__ __forceinline__ AdaOut ada_fwd_one(float u, float a, const Recip& R, float z, float qmin, float qmax, float b) {
     AdaOut o;
     const float fl = floorf(u);
@@ -29,7 +31,8 @@ __device__ __forceinline__ AdaOut ada_fwd_one(float u, float a, const Recip& R, 
     } else {
         r = (a >= 0.f) ? 1.f : 0.f;
     }
-    o.q = clampf_(__fadd_rn(__fadd_rn(fl, r), z), qmin, qmax);
+    const float xi = __fadd_rn(__fadd_rn(fl, r), z);
+    o.q = FINITE ? fminf(fmaxf(xi, qmin), qmax) : clampf_(xi, qmin, qmax);
     o.y = __fmul_rn(__fsub_rn(o.q, z), R.d);
     return o;
 }
@@ -68,16 +71,21 @@ __device__ __forceinline__ double ada_fwd_span(const float* __restrict__ w, cons
         float4* __restrict__ c4 = codes ? reinterpret_cast<float4*>(codes + e0) : nullptr;
         const uint32_t n4 = (uint32_t)((e1 - e0) >> 2), step = (uint32_t)nthr;
         cw.init((uint64_t)(e0 >> 2) + (uint64_t)tid, nthr, inner >> 2, nchan);
+        Recip R; float z = 0.f; uint32_t c_have = 0xffffffffu;      // channel constants: recomputed only when the channel changes
         auto body = [&](uint32_t j, const float4& wv, const float4& av) {
-            const Recip R = make_recip(__ldg(delta + cw.c));
-            const float z = __ldg(zp + cw.c);
+            if (cw.c != c_have) { R = make_recip(__ldg(delta + cw.c)); z = __ldg(zp + cw.c); c_have = cw.c; }
             float4 y, q;
             AdaOut o;
             float rsum = 0.f;
-            const float4 t = div4_exact(wv, R);
-#define ONE(F) o = ada_fwd_one<SOFT, REGON>(t.F, av.F, R, z, qmin, qmax, b); y.F = o.y; q.F = o.q; rsum += o.reg;
-            ONE(x) ONE(y) ONE(z) ONE(w)
+            if (R.ok && small4(wv)) {
+#define ONE(F) o = ada_fwd_one<SOFT, REGON, true>(div_fast(wv.F, R), av.F, R, z, qmin, qmax, b); y.F = o.y; q.F = o.q; rsum += o.reg;
+                ONE(x) ONE(y) ONE(z) ONE(w)
 #undef ONE
+            } else {
+#define ONE(F) o = ada_fwd_one<SOFT, REGON, false>(__fdiv_rn(wv.F, R.d), av.F, R, z, qmin, qmax, b); y.F = o.y; q.F = o.q; rsum += o.reg;
+                ONE(x) ONE(y) ONE(z) ONE(w)
+#undef ONE
+            }
             st_stream4(reinterpret_cast<float*>(y4 + j), y);
             if (c4) st_stream4(reinterpret_cast<float*>(c4 + j), q);
             if (REGON) acc += (double)rsum;

@@ -403,17 +403,32 @@ fq_shift_fwd_vec(const __grid_constant__ ShiftArgs a) {
     }
 }
 
-// backward: CTA = 1024 adjacent columns (one float4 per thread) x a slab of rows, two rows in flight per thread; per-column
+// backward: CTA = 1024 adjacent columns (one float4 per thread) x a slab of rows, NR rows in flight per thread; per-column
 // sums of d y / d p[g, i] stay in registers -> partial[slab][K][S] (the finish kernel adds slabs and the kk columns of a group in
 // fp64). The slab's row constants are staged in shared memory SSQ_SHIFT_RB rows at a time (one thread per row computes them).
-// Resident CTAs per SM: 4 for the dequantised mixture (61 registers), 3 for adaShift (80 registers, no spills) — the slab
-// count is chosen so that the grid is exactly one wave at that occupancy (slab_plan).
+// Measured on B200 (scratch/k1c_probe.py): dequantised mixture 4 CTAs/SM x 3 rows in flight (64 registers), adaShift 2 CTAs/SM
+// x 4 rows (121 registers, no spills); the slab count makes the grid exactly one wave at that occupancy (slab_plan). A
+// TMA-bulk-copy ring (cp.async.bulk + mbarrier, 3-5 stages) was tried instead of register prefetch: 0.79 / 0.66 of peak
+// against 0.92 / 0.84 — the per-row barrier polling costs more issue slots than the register pipeline saves.
 #define SSQ_SHIFT_RB 64
-#define SSQ_K1C_BWD_CTAS(MODE) ((MODE) == SSQ_SHIFT_ADASHIFT ? 3 : 4)
+#ifndef SSQ_K1C_BWD_CTAS_ADA
+#define SSQ_K1C_BWD_CTAS_ADA 2
+#endif
+#ifndef SSQ_K1C_BWD_CTAS_DEQ
+#define SSQ_K1C_BWD_CTAS_DEQ 4
+#endif
+#ifndef SSQ_K1C_BWD_ROWS_ADA
+#define SSQ_K1C_BWD_ROWS_ADA 4
+#endif
+#ifndef SSQ_K1C_BWD_ROWS_DEQ
+#define SSQ_K1C_BWD_ROWS_DEQ 3
+#endif
+#define SSQ_K1C_BWD_CTAS(MODE) ((MODE) == SSQ_SHIFT_ADASHIFT ? SSQ_K1C_BWD_CTAS_ADA : SSQ_K1C_BWD_CTAS_DEQ)
 template <int MODE, int S, bool SOFT, int GK>
 __global__ void __launch_bounds__(SSQ_THREADS, SSQ_K1C_BWD_CTAS(MODE))
 fq_shift_bwd_vec(const __grid_constant__ ShiftArgs a) {
     constexpr int NQ = (2 * S + 2 + 3) / 4;        // float4s per row: ds[S], r[S], c0, c1
+    constexpr int NR = (MODE == SSQ_SHIFT_ADASHIFT) ? SSQ_K1C_BWD_ROWS_ADA : SSQ_K1C_BWD_ROWS_DEQ;
     __shared__ float4 srow[SSQ_SHIFT_RB][NQ];
     __shared__ uint32_t sok[SSQ_SHIFT_RB];
     const uint32_t col4 = blockIdx.x * SSQ_THREADS + threadIdx.x;
@@ -493,16 +508,21 @@ fq_shift_bwd_vec(const __grid_constant__ ShiftArgs a) {
         __syncthreads();
         if (!live) continue;
         int lr = 0;
-        for (; lr + 1 < nrow; lr += 2) {
-            const int64_t r = r0 + c0 + lr, ea = r * K + (int64_t)col4 * 4, eb = ea + K;
-            const float4 ga = ld_stream4(a.gy + ea), wa = ld_stream4(a.w + ea), gbv = ld_stream4(a.gy + eb), wb = ld_stream4(a.w + eb);
-            const float4 ba = (MODE == SSQ_SHIFT_ADASHIFT) ? ld_stream4(a.beta + ea) : zero4;
-            const float4 bb = (MODE == SSQ_SHIFT_ADASHIFT) ? ld_stream4(a.beta + eb) : zero4;
-            const bool fa = fast_ok(lr, ga, wa, ba), fb = fast_ok(lr + 1, gbv, wb, bb);
-            row(r, lr, ga, wa, ba, fa);
-            row(r + 1, lr + 1, gbv, wb, bb, fb);
+        for (; lr + NR <= nrow; lr += NR) {            // NR rows in flight per thread
+            float4 gq[NR], wq[NR], bq[NR];
+            bool fq[NR];
+#pragma unroll
+            for (int d = 0; d < NR; ++d) {
+                const int64_t ea = (r0 + c0 + lr + d) * K + (int64_t)col4 * 4;
+                gq[d] = ld_stream4(a.gy + ea); wq[d] = ld_stream4(a.w + ea);
+                bq[d] = (MODE == SSQ_SHIFT_ADASHIFT) ? ld_stream4(a.beta + ea) : zero4;
+            }
+#pragma unroll
+            for (int d = 0; d < NR; ++d) fq[d] = fast_ok(lr + d, gq[d], wq[d], bq[d]);
+#pragma unroll
+            for (int d = 0; d < NR; ++d) row(r0 + c0 + lr + d, lr + d, gq[d], wq[d], bq[d], fq[d]);
         }
-        if (lr < nrow) {
+        for (; lr < nrow; ++lr) {
             const int64_t r = r0 + c0 + lr, ea = r * K + (int64_t)col4 * 4;
             const float4 ga = ld_stream4(a.gy + ea), wa = ld_stream4(a.w + ea), ba = (MODE == SSQ_SHIFT_ADASHIFT) ? ld_stream4(a.beta + ea) : zero4;
             row(r, lr, ga, wa, ba, fast_ok(lr, ga, wa, ba));
