@@ -320,6 +320,14 @@ def kernel_microbench(dev, peak_gbs):
     res["fq_shift_bwd(adaShift,soft)"] = timeit(lambda: ops.fq_shift_bwd(g, w, sd, dflat, zflat, pr, alpha, ops.SHIFT_ADASHIFT, False, 0.0, 3.0, False, True), 16 * n)
     res["fq_shift_fwd(dequant mix)"] = timeit(lambda: ops.fq_shift_fwd(w, sd, dflat, zflat, pr, None, ops.SHIFT_DEQUANT, False, False, 0.0, 3.0, False), 8 * n)
     res["fq_shift_bwd(dequant mix)"] = timeit(lambda: ops.fq_shift_bwd(g, w, sd, dflat, zflat, pr, None, ops.SHIFT_DEQUANT, False, 0.0, 3.0, False, False), 8 * n)
+    # the same bytes as a 1x1 convolution [8192,18432,1,1]: every element its own group (contiguous probabilities, float4 loads)
+    w1 = w.view(8192, 18432, 1, 1); b1 = alpha.view_as(w1); g1 = g.view_as(w1)
+    d1 = (w1.abs().amax(dim=(1, 2, 3)) / 3 * 1.2).contiguous(); z1 = torch.full_like(d1, 2.0)
+    sd1 = torch.stack([d1 * st for st in shifts]).contiguous()
+    pr1 = ops.shift_probs_fwd(torch.randn(18432, 3, device=dev))
+    res["fq_shift_fwd(adaShift,soft,1x1)"] = timeit(lambda: ops.fq_shift_fwd(w1, sd1, d1, z1, pr1, b1, ops.SHIFT_ADASHIFT, False, False, 0.0, 3.0, False), 12 * n)
+    res["fq_shift_bwd(adaShift,soft,1x1)"] = timeit(lambda: ops.fq_shift_bwd(g1, w1, sd1, d1, z1, pr1, b1, ops.SHIFT_ADASHIFT, False, 0.0, 3.0, False, True), 16 * n)
+    del w1, b1, g1
     packed = ops.export_codes(w, d, z, 0.0, 3.0, 2, alpha=alpha)
     res["export_codes(2-bit,+alpha)"] = timeit(lambda: ops.export_codes(w, d, z, 0.0, 3.0, 2, alpha=alpha), 8 * n + n // 4)
     res["import_codes(2-bit)"] = timeit(lambda: ops.import_codes(packed, w.shape, d, z, 0.0, 2), 4 * n + n // 4)
@@ -529,9 +537,16 @@ def run_ours(args):
     e2e = None
     # ---- end to end: features in pinned host memory, per-step H2D of the mini-batch, D2H of the loss
     if not args.skip_e2e:
+        # the pinned cache is placed by first touch: allocate it (and run the step) from the GPU's own NUMA node, as the multi-rank
+        # launch does for the whole process; the affinity is restored afterwards so that the CPU baseline keeps every host core
+        saved_affinity = os.sched_getaffinity(0)
+        bound = D.bind_to_gpu_cpus(local) if world == 1 else 0
+        log(f"[rank {rank}] e2e: bound to {bound} GPU-local cores (0 = unchanged) of {len(saved_affinity)}")
         eng_h, _ = make_engines(Q, qnn, cali, dev, act_quant=False, multi_gpu=world > 1, host_resident=True, feats=feats,
                                 scaling=args.scaling)
         ms_e2e = timed_steps(eng_h, max(args.steps // 2, 3), max(args.warmup // 2, 3), dev, world, read_loss=True)
+        if world == 1:
+            os.sched_setaffinity(0, saved_affinity)
         e2e = {"value": work * n_units / (ms_e2e * 1e-3), "unit": "iters/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": sum(e.h2d_bytes_per_step() for e in eng_h), "d2h_bytes_per_step": 4 * n_units,
                "path": "ReconEngine(host_resident=True, host_stage='pull'): pinned host feature cache; inside each captured iteration a 16-CTA "

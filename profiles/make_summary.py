@@ -31,6 +31,8 @@ KERNELS = OrderedDict([
     ("gather_rows_kernel", ("mini-batch gather (ssq_gather_rows), activations [256,256,56,56]", 8, A)),
     ("fq_shift_fwd_vec", ("K1c fwd, adaShift soft, S = 3 (ssq_fq_shift_fwd)", 12, W)),
     ("fq_shift_bwd_vec", ("K1c bwd, adaShift soft, S = 3 (ssq_fq_shift_bwd)", 16, W)),
+    ("fq_shift_fwd_vec_deq", ("K1c fwd, dequantised mixture, S = 3 (ssq_fq_shift_fwd, -s 16)", 8, W)),
+    ("fq_shift_bwd_vec_deq", ("K1c bwd, dequantised mixture, S = 3 (ssq_fq_shift_bwd, -s 16)", 8, W)),
     ("export_vec_kernel", ("integer export, 2-bit + alpha (ssq_export_codes)", 8.25, W)),
     ("import_vec_kernel", ("integer import, 2-bit (ssq_import_codes)", 4.25, W)),
 ])
@@ -54,7 +56,7 @@ def kernels(tag):
     md = [f"# {tag} — ncu --set full of each hot kernel on DRAM-resident inputs\n",
           "Command per kernel (after `python bench.py --micro-only` exited 0 without ncu): `ncu --set full --clock-control none "
           "--import-source on -k regex:<kernel> -s 3 -c 1 -o gpurun_out/" + tag + "_full_<kernel> python bench.py --micro-only` "
-          "(scratch/r01c_gpu.sh).",
+          "(profiles/capture_r01.sh, profiles/capture_r01e.sh).",
           "`traffic` = dram__bytes_read.sum + dram__bytes_write.sum of that one launch; algorithmic bytes = SURVEY §8d per-element "
           "figure x elements. ncu's DRAM % is against its own ~8.2 TB/s peak; the roofline fraction in bench.py is against the "
           f"measured {peak:.1f} GB/s copy peak (MEASURED_PEAKS.json). Durations under ncu are cold-cache single launches; the "
@@ -105,10 +107,13 @@ def launch_list(tag, steps=3, units=9):
         v = float(r["Metric Value"].replace(",", ""))
         unit = r.get("Metric Unit", "ns")
         recs.append((r["Kernel Name"], v * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "nsecond": 1e-3, "usecond": 1.0}.get(unit, 1e-3)))
-    # the timed region = the last `steps` steps: find it as the last steps*units loop_advance launches
+    # launch order of bench.py: 3 eager warm-up iterations per engine (3*units loop_advance launches), then `steps` untimed + `steps`
+    # timed steps (one graph replay per unit each), then the per-unit timing loops and the in-step event pass. The timed region is
+    # therefore loop_advance launches [3*units + steps*units, 3*units + 2*steps*units)
     adv = [i for i, (n, _) in enumerate(recs) if "loop_advance" in n]
-    start = adv[-steps * units]
-    region = recs[start:]
+    first = 3 * units + steps * units
+    start, stop = adv[first], adv[first + steps * units]
+    region = recs[start:stop]
     agg = defaultdict(lambda: [0, 0.0])
     for n, us in region:
         agg[n][0] += 1; agg[n][1] += us
@@ -121,7 +126,7 @@ def launch_list(tag, steps=3, units=9):
     md = [f"# {tag} — ncu launch list of the bench step (gpu__time_duration.sum, --clock-control none)\n",
           "Command (after the same command exited 0 without ncu): `ncu --metrics gpu__time_duration.sum --clock-control none --csv "
           "python bench.py --steps 3 --warmup 3 --images 64 --skip-e2e --skip-act --skip-cpu --skip-micro --skip-tf32 --skip-shift --cudnn-benchmark 0`\n",
-          f"Whole run: {len(recs)} launches. Timed region below = the last {steps} steps x {units} units = {steps * units} captured iterations "
+          f"Whole run: {len(recs)} launches. Timed region below = the {steps} timed steps x {units} units = {steps * units} captured iterations "
           f"({len(region)} kernel nodes, {len(region) / (steps * units):.0f} per iteration on average). Per-launch times are cold-cache and "
           "serialised: compare SHARES.\n",
           f"Total {total / 1e3:.3f} ms for {steps} steps = {total / 1e3 / steps:.3f} ms/step under ncu. ssq kernels: {100 * ours / total:.1f} % of "
