@@ -167,8 +167,11 @@ __device__ __forceinline__ void ada_bwd_span(const float* __restrict__ gwq, cons
 
 // ---- single tensor ----------------------------------------------------------------------------------------
 #define SSQ_ST_TILE 8192      // elements per tile: 2048 float4s, 8 per thread, taken two at a time
+#ifndef SSQ_K1B_FWD_CTAS
+#define SSQ_K1B_FWD_CTAS 5      // 48 registers: 0.953 of the HBM peak (4 CTAs / 60 registers: 0.913, 6: 0.937, 8: 0.82)
+#endif
 template <bool SOFT, bool REG>
-__global__ void __launch_bounds__(SSQ_THREADS, 4)
+__global__ void __launch_bounds__(SSQ_THREADS, SSQ_K1B_FWD_CTAS)
 ada_fwd_kernel(const float* __restrict__ w, const float* __restrict__ alpha, const float* __restrict__ delta,
                const float* __restrict__ zp, float* __restrict__ wq, float* __restrict__ codes,
                int64_t n, int64_t inner, int64_t nchan, float qmin, float qmax, bool vec,
