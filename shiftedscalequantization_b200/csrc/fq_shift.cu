@@ -6,6 +6,7 @@
 // The reference reads S cached weight-sized tensors x_q[i]; here the S candidates are recomputed from the
 // weight in registers (12 B/elem instead of (S+2)*4 B/elem).
 #include "ssq_common.cuh"
+#include "ssq_fastdiv.h"
 
 namespace ssq {
 
@@ -194,17 +195,6 @@ fq_shift_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ w, c
 //  * dequantised candidates use clamp(rint(u) + z, qmin, qmax) - z == clamp(rint(u), qmin - z, qmax - z), exact whenever z, qmin,
 //    qmax are integers below 2^22 (checked per row; anything else takes the slow path). fma(k, ds, +0) keeps the reference's +0
 //    where rint(u) is -0.
-struct FastDiv { uint32_t mul, sh; };            // n / d for n < 2^31, d >= 2: umulhi(n, mul) >> sh
-static inline FastDiv make_fastdiv(uint32_t d) {
-    FastDiv f;
-    uint32_t s = 0;
-    while ((1ull << s) < (uint64_t)d) ++s;         // ceil(log2 d) >= 1
-    f.mul = (uint32_t)(((1ull << (31 + s)) / d) + 1ull);   // < 2^32 because d > 2^(s-1); error term n * (mul * d - 2^(31+s)) < 2^(31+s)
-    f.sh = s - 1;
-    return f;
-}
-__device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv& f) { return __umulhi(n, f.mul) >> f.sh; }
-
 struct ShiftArgs {
     const float *w, *shift_delta, *delta, *zp, *p, *beta, *gy;
     float *y, *gbeta, *partial;

@@ -221,3 +221,50 @@ def test_two_rank_gloo_plumbing(tmp_path):
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout
+
+
+_FASTDIV_CHECK = r'''
+#include <cstdio>
+#include <cstdint>
+#include <cstdlib>
+#include "ssq_fastdiv.h"
+// the K1c kernels' multiply-shift division (host constants + the very function the device code calls) against the built-in
+// division: every divisor up to 20000 plus the shapes of real layers and random / extreme ones, numerators around every
+// multiple boundary and across the whole 31-bit index range
+static int check(uint32_t d) {
+    const ssq::FastDiv f = ssq::make_fastdiv(d);
+    auto one = [&](uint64_t n) { if (n >= (1ull << 31)) return 0; return ssq::fastdiv((uint32_t)n, f) == (uint32_t)n / d ? 0 : 1; };
+    int bad = 0;
+    const uint64_t top = (1ull << 31) - 1;
+    for (uint64_t q = 0; q < 64; ++q) for (int e = -2; e <= 2; ++e) { const int64_t n = (int64_t)(q * d) + e; if (n >= 0) bad += one((uint64_t)n); }
+    for (uint64_t q = top / d; q + 4 > top / d && q <= top / d; --q) { for (int e = -2; e <= 2; ++e) { const int64_t n = (int64_t)(q * d) + e; if (n >= 0) bad += one((uint64_t)n); } if (q == 0) break; }
+    for (int k = 0; k < 31; ++k) for (int e = -1; e <= 1; ++e) { const int64_t n = (int64_t)(1ull << k) + e; if (n >= 0) bad += one((uint64_t)n); }
+    uint64_t x = 0x9E3779B97F4A7C15ull * (d + 1);
+    for (int i = 0; i < 2000; ++i) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; bad += one(x & top); }
+    bad += one(top);
+    return bad;
+}
+int main() {
+    long bad = 0, n = 0;
+    for (uint32_t d = 2; d <= 20000; ++d) { bad += check(d); ++n; }
+    const uint32_t shapes[] = {144, 288, 576, 1152, 2304, 4608, 9216, 16, 32, 64, 128, 256, 512, 36864, 18432, 9, 25, 49, 3, 5, 7, 27, 147,
+                               (1u << 30) - 1, 1u << 30, (1u << 30) + 1, (1u << 31) - 1, 1u << 31, 0x7fffffffu, 0xfffffffu, 1000003u, 2147483629u};
+    for (uint32_t d : shapes) { bad += check(d); ++n; }
+    uint64_t x = 88172645463325252ull;
+    for (int i = 0; i < 20000; ++i) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; uint32_t d = (uint32_t)(x >> 33); if (d < 2) d = 2; bad += check(d); ++n; }
+    std::printf("%ld divisors, %ld mismatches\n", n, bad);
+    return bad ? 1 : 0;
+}
+'''
+
+
+def test_fastdiv_matches_integer_division(tmp_path):
+    """host logic of the K1c kernels: ssq_fastdiv.h (compiled here with g++) == n / d over the 31-bit index space"""
+    src = tmp_path / "fastdiv_check.cpp"
+    src.write_text(_FASTDIV_CHECK)
+    exe = tmp_path / "fastdiv_check"
+    inc = os.path.join(ROOT, "shiftedscalequantization_b200", "csrc")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I", inc, "-o", str(exe), str(src)], check=True, capture_output=True, text=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert " 0 mismatches" in out.stdout
