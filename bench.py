@@ -549,10 +549,16 @@ def run_ours(args):
             os.sched_setaffinity(0, saved_affinity)
         e2e = {"value": work * n_units / (ms_e2e * 1e-3), "unit": "iters/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": sum(e.h2d_bytes_per_step() for e in eng_h), "d2h_bytes_per_step": 4 * n_units,
-               "path": "ReconEngine(host_resident=True, host_stage='pull'): pinned host feature cache; inside each captured iteration a 16-CTA "
-                       "kernel (ssq_pull_rows_host) reads the NEXT mini-batch's input and target rows out of mapped host memory over PCIe "
-                       "beside the current iteration's kernels; every iteration's loss is copied to a pinned 2-deep ring and read on the "
-                       "host one launch later (all losses read inside the timed region)"}
+               "h2d_dense_bytes_per_step": sum(4 * (e.cur_inp.numel() + e.cur_out.numel()) for e in eng_h),
+               "path": "ReconEngine(host_resident=True, host_stage='pull'): pinned host feature cache, post-ReLU tensors kept zero-packed "
+                       "(non-zero values on the host; bit mask + chunk offsets, 3 % of the dense size, on the device); inside each captured "
+                       "iteration a 16-24-CTA kernel (ssq_pull_rows_host[_packed]) reads the NEXT mini-batch's input and target rows out "
+                       "of mapped host memory over PCIe beside the current iteration's kernels and expands them to dense rows "
+                       "(h2d_bytes_per_step = the bytes that cross PCIe, h2d_dense_bytes_per_step = the dense rows they become); every "
+                       "iteration's loss is copied to a pinned 2-deep ring and read on the host one launch later (all losses read inside "
+                       "the timed region)"}
+        log(f"[rank {rank}] e2e per-unit PCIe bytes / dense bytes: "
+            + ", ".join(f"{e.h2d_bytes_per_step() / max(4 * (e.cur_inp.numel() + e.cur_out.numel()), 1):.2f}" for e in eng_h))
         release(eng_h)
     torch.cuda.empty_cache()
 

@@ -270,6 +270,16 @@ int ssq_stage_rows_h2d(const float* host_src, const int64_t* rows, float* dev_ds
 int ssq_pull_rows_host(const float* host_src_mapped, const int64_t* idx_table, const int64_t* step_dev,
                        int64_t lookahead, int64_t n_steps, float* dev_dst, int64_t batch, int64_t per_sample,
                        int max_ctas, void* stream);
+/* same transfer from a ZERO-PACKED host cache (cached features are post-ReLU: a third to a half of the elements are +0.0f, and
+ * this mode is PCIe-bound). The host keeps only the non-zero values of every row, packed in element order (host_vals: mapped
+ * pinned memory, 16-byte aligned, >= 4 floats of slack after the last value); the index stays on the DEVICE: mask[r][per_sample/32]
+ * (bit e%32 of word e/32 set iff the 32 bits of element e are not all zero) and chunk_off[N*per_sample/1024 + 1], the exclusive
+ * prefix sum of the per-1024-element chunk counts, row-major. per_sample must be a multiple of 1024. The expansion is lossless
+ * (-0.0f, denormals, NaNs are values). The reference keeps the cache as dense CPU tensors (quant/data_utils.py:29-36); the packed
+ * form is this library's own. */
+int ssq_pull_rows_host_packed(const uint32_t* mask, const float* host_vals_mapped, const int64_t* chunk_off,
+                              const int64_t* idx_table, const int64_t* step_dev, int64_t lookahead, int64_t n_steps,
+                              float* dev_dst, int64_t batch, int64_t per_sample, int max_ctas, void* stream);
 /* advance the device-side iteration state used by a graph-captured loop: step += 1, and
  * copy row `step` of idx_table/b_table/lr_table into the live slots. */
 int ssq_loop_advance(int64_t* step_dev, const int64_t* idx_table, int64_t* idx_live, int batch,

@@ -441,3 +441,39 @@ def unpack_rows(packed, k: int, qmin, n_bits: int):
     parts = [(packed >> (e * sb)) & ((1 << sb) - 1) for e in range(per)]
     u = np.stack(parts, axis=-1).reshape(rows, -1)[:, :k]
     return (u.astype(F) + F(qmin)).astype(F)
+
+
+# ------------------------------------------------------------------------------------------------ zero-packed host cache
+# No reference counterpart (quant/data_utils.py:29-36 keeps dense CPU tensors): this is the library's own transport format for
+# the host-resident cache (include/ssq_b200.h, ssq_pull_rows_host_packed); parity = the round trip is the identity, bit for bit.
+SPARSE_CHUNK = 1024
+
+
+def sparse_pack_rows(x):
+    """x [N, P] fp32, P % 1024 == 0 -> (mask uint32 [N, P/32], vals fp32 [nnz], chunk_off int64 [N*P/1024 + 1]).
+    An element is dropped iff its 32 bits are all zero (+0.0f); bit e%32 of word e/32 marks element e."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    n, p = x.shape
+    assert p % SPARSE_CHUNK == 0
+    nz = x.view(np.uint32) != 0
+    weights = (np.uint64(1) << np.arange(32, dtype=np.uint64))
+    mask = (nz.reshape(n, p // 32, 32).astype(np.uint64) * weights).sum(-1).astype(np.uint32)
+    counts = nz.reshape(n, p // SPARSE_CHUNK, SPARSE_CHUNK).sum(-1).astype(np.int64).reshape(-1)
+    chunk_off = np.concatenate([np.zeros(1, np.int64), np.cumsum(counts)])
+    return mask, x[nz], chunk_off
+
+
+def sparse_unpack_rows(mask, vals, chunk_off, rows, per_sample):
+    """dense [len(rows), per_sample] rows of a zero-packed cache (plain loops over chunks: small cases only)"""
+    c = per_sample // SPARSE_CHUNK
+    out = np.zeros((len(rows), per_sample), np.float32)
+    for j, r in enumerate(rows):
+        for ch in range(c):
+            bits = np.zeros(SPARSE_CHUNK, bool)
+            for wd in range(32):
+                m = int(mask[r, ch * 32 + wd])
+                bits[wd * 32:(wd + 1) * 32] = [(m >> b) & 1 for b in range(32)]
+            base = int(chunk_off[r * c + ch])
+            seg = out[j, ch * SPARSE_CHUNK:(ch + 1) * SPARSE_CHUNK]
+            seg[bits] = vals[base:base + int(bits.sum())]
+    return out

@@ -70,6 +70,7 @@ PROTOTYPES = {
     "ssq_import_codes": (_i32, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _f, _i32, _p]),
     "ssq_stage_rows_h2d": (_i32, [_p, _p, _p, _i64, _i64, _p]),
     "ssq_pull_rows_host": (_i32, [_p, _p, _p, _i64, _i64, _p, _i64, _i64, _i32, _p]),
+    "ssq_pull_rows_host_packed": (_i32, [_p, _p, _p, _p, _p, _i64, _i64, _p, _i64, _i64, _i32, _p]),
     "ssq_loop_advance": (_i32, [_p, _p, _p, _i32, _p, _p, _p, _p, _i64, _p]),
 }
 

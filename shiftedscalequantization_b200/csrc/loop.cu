@@ -123,6 +123,104 @@ pull_rows_kernel(const float* __restrict__ host_src, const int64_t* __restrict__
     }
 }
 
+
+// Host-resident feature cache, zero-packed pull variant. Cached features are post-ReLU tensors: a third to a half of their
+// elements are +0.0f, and the host-resident mode is PCIe-bound on the large early units. The host cache therefore keeps only the
+// non-zero values, packed in element order; the index that locates them stays on the device (3 % of the dense size): a bit mask
+// (1 bit per element: bit pattern != 0) and `chunk_off`, the offset of every 1024-element chunk's values. With the index in HBM a
+// chunk costs ONE PCIe round trip. One warp expands one chunk: lane = one 32-bit mask word, the chunk's packed values
+// are read with aligned 128-bit loads (all issued before the first use) into a per-warp shared-memory stage, a warp scan of the
+// popcounts gives each lane its first value, and the dense row is written to HBM. Lossless by construction: only elements whose
+// 32 bits are all zero are dropped (so -0.0f, denormals, NaN payloads survive).
+#define SSQ_PACK_CHUNK 1024
+struct PackedChunk {                       // one warp's view of one 1024-element chunk: everything that is in flight for it
+    float4 v[9];                           // 9 x 32 float4 >= 3 + 1024 + 3 floats
+    float* out;
+    uint32_t m;
+    int nvec, lead;                        // float4s to stage; values of the aligned over-read that precede the chunk's first
+};
+__global__ void __launch_bounds__(SSQ_THREADS, 2)
+pull_rows_packed_kernel(const uint32_t* __restrict__ mask, const float* __restrict__ host_vals,
+                        const int64_t* __restrict__ chunk_off, const int64_t* __restrict__ idx_table,
+                        const int64_t* __restrict__ step_dev, int64_t lookahead, int64_t n_steps,
+                        float* __restrict__ dst, int64_t batch, int64_t per_sample) {
+    constexpr int WARPS = SSQ_THREADS / 32, NV = 9;
+    __shared__ __align__(16) float stage[WARPS][SSQ_PACK_CHUNK + 16];
+    int64_t s = *step_dev + lookahead;
+    if (s >= n_steps) s = n_steps - 1;
+    if (s < 0) s = 0;
+    const int64_t* __restrict__ rows = idx_table + s * batch;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t C = per_sample / SSQ_PACK_CHUNK, W = per_sample / 32;
+    const int64_t nwarps = (int64_t)gridDim.x * WARPS, total = batch * C;
+    float* __restrict__ st = stage[warp];
+    // issue every load of chunk `ch` (mask word from HBM, packed values over PCIe); nothing waits here
+    auto load = [&](PackedChunk& k, int64_t ch) {
+        const int64_t j = ch / C, c = ch - j * C, r = __ldg(rows + j);
+        const int64_t g = r * C + c;
+        const int64_t base = __ldg(chunk_off + g), cnt = __ldg(chunk_off + g + 1) - base;
+        k.m = __ldg(mask + r * W + c * 32 + lane);
+        const int64_t start = base & ~(int64_t)3;                 // aligned over-read of at most 3 + 3 values
+        k.nvec = (int)((base + cnt - start + 3) >> 2);
+        k.lead = (int)(base - start);
+        k.out = dst + j * per_sample + c * SSQ_PACK_CHUNK + lane * 32;
+#pragma unroll
+        for (int u = 0; u < NV; ++u) {
+            const int q = lane + 32 * u;
+            k.v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q < k.nvec) k.v[u] = ld_stream4(host_vals + start + 4 * (int64_t)q);
+        }
+    };
+    // stage the values, scan the popcounts, write the dense 1024 elements
+    auto expand = [&](const PackedChunk& k) {
+        // every store's address depends on every load (x * 0 -> 0, NaN/Inf -> NaN -> cvt 0: always 0, but only known once all
+        // loads have landed): ptxas otherwise stores the first vectors before issuing the last loads, i.e. two PCIe round trips
+        float dep = fmaf(__uint_as_float(k.m), 0.0f, 0.0f);
+#pragma unroll
+        for (int u = 0; u < NV; ++u) dep = fmaf(k.v[u].x, 0.0f, dep);
+        float* __restrict__ stz = st + __float2int_rz(dep);
+#pragma unroll
+        for (int u = 0; u < NV; ++u) {
+            const int q = lane + 32 * u;
+            if (q < k.nvec) *reinterpret_cast<float4*>(stz + 4 * q) = k.v[u];
+        }
+        __syncwarp();
+        const int pc = __popc(k.m);
+        int incl = pc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        int pos = k.lead + incl - pc;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const bool on = (k.m >> (4 * q + e)) & 1u;
+                o[e] = on ? st[pos] : 0.f;
+                pos += on ? 1 : 0;
+            }
+            st_stream4(k.out + 4 * q, make_float4(o[0], o[1], o[2], o[3]));
+        }
+        __syncwarp();
+    };
+    // two chunks per warp in flight: the next chunk's loads are issued before the current one is expanded
+    PackedChunk A, B;
+    int64_t ch = (int64_t)blockIdx.x * WARPS + warp;
+    bool has_a = ch < total;
+    if (has_a) load(A, ch);
+    while (has_a) {
+        const int64_t nb = ch + nwarps;
+        const bool has_b = nb < total;
+        if (has_b) load(B, nb);
+        expand(A);
+        if (!has_b) break;
+        ch = nb + nwarps;
+        has_a = ch < total;
+        if (has_a) load(A, ch);
+        expand(B);
+    }
+}
+
 }  // namespace ssq
 
 using namespace ssq;
@@ -178,6 +276,22 @@ extern "C" int ssq_pull_rows_host(const float* host_src_mapped, const int64_t* i
     if (grid < 1) grid = 1;
     pull_rows_kernel<<<(int)grid, SSQ_THREADS, 0, (cudaStream_t)stream>>>(host_src_mapped, idx_table, step_dev, lookahead, n_steps,
                                                                       dev_dst, batch, per_sample, vec);
+    return launch_status();
+}
+
+extern "C" int ssq_pull_rows_host_packed(const uint32_t* mask, const float* host_vals_mapped, const int64_t* chunk_off,
+                                         const int64_t* idx_table, const int64_t* step_dev, int64_t lookahead, int64_t n_steps,
+                                         float* dev_dst, int64_t batch, int64_t per_sample, int max_ctas, void* stream) {
+    if (batch == 0 || per_sample == 0) return SSQ_OK;
+    if (!mask || !host_vals_mapped || !chunk_off || !idx_table || !step_dev || !dev_dst) return SSQ_ERR_NULL;
+    if (batch < 0 || per_sample < 0 || n_steps <= 0 || per_sample % SSQ_PACK_CHUNK != 0) return SSQ_ERR_SIZE;
+    if (!aligned16(host_vals_mapped) || !aligned16(dev_dst)) return SSQ_ERR_ALIGN;
+    const int64_t chunks = batch * (per_sample / SSQ_PACK_CHUNK);
+    int64_t grid = (chunks + SSQ_THREADS / 32 - 1) / (SSQ_THREADS / 32);
+    const int64_t cap = max_ctas > 0 ? max_ctas : 32;
+    if (grid > cap) grid = cap;
+    pull_rows_packed_kernel<<<(int)grid, SSQ_THREADS, 0, (cudaStream_t)stream>>>(mask, host_vals_mapped, chunk_off, idx_table,
+                                                                             step_dev, lookahead, n_steps, dev_dst, batch, per_sample);
     return launch_status();
 }
 

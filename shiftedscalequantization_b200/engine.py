@@ -88,12 +88,15 @@ class ReconEngine:
                  act_quantizers: Sequence[nn.Module] = (), use_graph: Optional[bool] = None,
                  idx_table: Optional[torch.Tensor] = None, verbose: bool = True,
                  host_resident: bool = False, device: Optional[torch.device] = None, host_stage: str = 'pull',
-                 scaling: str = 'weak'):
+                 scaling: str = 'weak', host_pack: Optional[bool] = None):
         """host_resident=True keeps the cached features in (pinned) host memory, as the reference does with
         keep_gpu=False (quant/data_utils.py:34-36, `cached_inps[idx].to(device)` at block_recon.py:91-92): every
         step moves its mini-batch rows host->device. host_stage='pull' (default): a kernel inside the captured
         iteration reads the NEXT mini-batch's rows out of the mapped pinned cache while the current iteration
-        computes (no host work per step); 'dma': one cudaMemcpyAsync per row on a copy stream, issued by the host."""
+        computes (no host work per step); 'dma': one cudaMemcpyAsync per row on a copy stream, issued by the host.
+        host_pack (pull mode; default on): cached tensors whose rows are a multiple of 1024 elements and at most 80 % non-zero —
+        post-ReLU features — are kept zero-packed on the host (non-zero values only; bit mask and chunk offsets on the device, 3 %
+        of the dense size) and expanded by the pulling kernel, so fewer bytes cross PCIe; lossless, same trajectory."""
         """scaling (multi_gpu only): 'weak' = every rank draws its own mini-batch of `batch_size` from its shard and the
         gradients are SUMMED (the reference's link.allreduce semantics, block_recon.py:100-102; global batch = R x batch);
         'strong' = the ranks split ONE global mini-batch of `batch_size` (every rank holds the whole cache and the same
@@ -108,6 +111,7 @@ class ReconEngine:
             raise ValueError('host_stage must be "pull" or "dma"')
         self.host_pull = self.host_resident and host_stage == 'pull'
         self.host_dma = self.host_resident and host_stage == 'dma'
+        self.host_pack = self.host_pull and (True if host_pack is None else bool(host_pack))
         self.dev = torch.device(device) if device is not None else cached_inps.device
         if self.dev.type != 'cuda':
             raise ops._lib.SsqError('reconstruction runs on CUDA only (no CPU fallback)')
@@ -159,7 +163,7 @@ class ReconEngine:
         self.reg_dev = torch.zeros(1, device=self.dev)
         if self.host_pull:
             self._pull_stream = torch.cuda.Stream(self.dev)
-            self._pull_bufs = [(src, torch.empty_like(cur), cur) for src, cur in
+            self._pull_bufs = [(self._maybe_pack(src), torch.empty_like(cur), cur) for src, cur in
                                ((self.cached_inps, self.cur_inp), (self.cached_outs, self.cur_out), (self.cached_grads, self.cur_grad))
                                if src is not None]
             self._pull_primed = False
@@ -253,10 +257,21 @@ class ReconEngine:
         if self.host_pull:
             torch.cuda.current_stream(self.dev).wait_stream(self._pull_stream)      # join the prefetch branch
 
+    def _maybe_pack(self, src: torch.Tensor):
+        """zero-packed form of a pinned cache tensor when that saves PCIe bytes (post-ReLU features), else the tensor itself"""
+        if not (self.host_pack and ops.packable(src)):
+            return src
+        packed = ops.pack_rows_sparse(src, self.dev)
+        return packed if packed.density <= 0.8 else src      # the packed stream reaches 0.87 of the dense pull's PCIe rate
+
     def _pull(self, lookahead: int):
         for src, stage, _cur in self._pull_bufs:
-            ops.pull_rows_host(src, self.idx_table, self.step_dev, lookahead, self.idx_table.shape[0], stage,
-                               max_ctas=16, stream=self._pull_stream)
+            if isinstance(src, ops.PackedRows):
+                ops.pull_rows_host_packed(src, self.idx_table, self.step_dev, lookahead, self.idx_table.shape[0], stage,
+                                          max_ctas=16, stream=self._pull_stream)
+            else:
+                ops.pull_rows_host(src, self.idx_table, self.step_dev, lookahead, self.idx_table.shape[0], stage,
+                                   max_ctas=16, stream=self._pull_stream)
 
     def _prime_pull(self):
         """first mini-batch of a run: pull row *step_dev (not yet advanced) before the first iteration"""
@@ -345,6 +360,9 @@ class ReconEngine:
     def h2d_bytes_per_step(self) -> int:
         if not self.host_resident:
             return 0
+        if self.host_pull:           # packed tensors move their non-zero values only (average over the cache's rows)
+            return int(sum(round(self.batch * src.host_bytes_per_row()) if isinstance(src, ops.PackedRows) else 4 * cur.numel()
+                           for src, _stage, cur in self._pull_bufs))
         n = self.cur_inp.numel() + self.cur_out.numel() + (0 if self.cur_grad is None else self.cur_grad.numel())
         return 4 * n
 

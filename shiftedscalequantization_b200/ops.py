@@ -646,6 +646,69 @@ def pull_rows_host(host_src: torch.Tensor, idx_table: torch.Tensor, step_dev: to
           dev_dst.data_ptr(), batch, per_sample, int(max_ctas), st)
 
 
+PACK_CHUNK = 1024
+
+
+class PackedRows:
+    """zero-packed host-resident rows (include/ssq_b200.h, ssq_pull_rows_host_packed): the non-zero values of every row in pinned
+    host memory, the bit mask and the per-chunk value offsets on the device"""
+
+    def __init__(self, vals_host, mask_dev, chunk_off_dev, shape):
+        self.vals, self.mask, self.chunk_off, self.shape = vals_host, mask_dev, chunk_off_dev, tuple(shape)
+        self.per_sample = int(mask_dev.shape[1]) * 32
+        self.nnz = int(vals_host.numel()) - 8
+
+    @property
+    def density(self) -> float:
+        return self.nnz / float(self.shape[0] * self.per_sample)
+
+    def host_bytes_per_row(self) -> float:
+        return 4.0 * self.nnz / self.shape[0]
+
+
+def packable(t: torch.Tensor) -> bool:
+    return t is not None and t.dtype == torch.float32 and t.dim() >= 2 and t.shape[0] > 0 and (t[0].numel() % PACK_CHUNK) == 0
+
+
+def pack_rows_sparse(t: torch.Tensor, dev, rows_per_slice: int = 64) -> PackedRows:
+    """build the zero-packed form of a [N, ...] fp32 tensor (host or device) with device-side torch ops, `rows_per_slice` rows
+    at a time (set-up cost, outside every timed region). An element is dropped iff its 32 bits are all zero."""
+    if not packable(t):
+        raise _lib.SsqError("pack_rows_sparse needs an fp32 [N, ...] tensor whose rows are a multiple of 1024 elements")
+    n, per = t.shape[0], t[0].numel()
+    w, c = per // 32, per // PACK_CHUNK
+    weights = torch.ones(32, dtype=torch.int64, device=dev) << torch.arange(32, dtype=torch.int64, device=dev)
+    masks, vals, counts = [], [], []
+    for i in range(0, n, rows_per_slice):
+        x = t[i:i + rows_per_slice].to(dev).reshape(-1, per).contiguous()
+        nz = x.view(torch.int32) != 0
+        counts.append(nz.view(-1, c, PACK_CHUNK).sum(-1, dtype=torch.int64))
+        m = (nz.view(-1, w, 32).to(torch.int64) * weights).sum(-1)            # [rows, w] in [0, 2^32)
+        masks.append(torch.where(m >= 2 ** 31, m - 2 ** 32, m).to(torch.int32))
+        vals.append(x[nz].cpu())
+    vals.append(torch.zeros(8))                                                # slack for the aligned over-read of the last chunk
+    vals_host = torch.cat(vals).pin_memory()
+    chunk_off = torch.zeros(n * c + 1, dtype=torch.int64, device=dev)
+    chunk_off[1:] = torch.cat(counts).reshape(-1).cumsum(0)
+    return PackedRows(vals_host, torch.cat(masks).contiguous(), chunk_off, t.shape)
+
+
+def pull_rows_host_packed(packed: PackedRows, idx_table: torch.Tensor, step_dev: torch.Tensor, lookahead: int, n_steps: int,
+                          dev_dst: torch.Tensor, max_ctas: int = 24, stream=None):
+    """pull_rows_host from a zero-packed cache: only the non-zero values cross PCIe, the SMs expand them into dense rows"""
+    if packed.vals.is_cuda or not packed.vals.is_pinned() or not packed.mask.is_cuda or not packed.chunk_off.is_cuda:
+        raise _lib.SsqError("packed rows: values must be pinned host memory, mask / chunk offsets device tensors")
+    _req(dev_dst, "dev_dst")
+    if not (idx_table.is_cuda and step_dev.is_cuda and idx_table.dtype == torch.int64 and step_dev.dtype == torch.int64):
+        raise _lib.SsqError("idx_table / step_dev must be int64 device tensors")
+    batch = idx_table.shape[-1]
+    if dev_dst.numel() != batch * packed.per_sample:
+        raise _lib.SsqError("dev_dst does not hold one mini-batch of rows")
+    st = (stream or torch.cuda.current_stream(dev_dst.device)).cuda_stream
+    _call("ssq_pull_rows_host_packed", packed.mask.data_ptr(), packed.vals.data_ptr(), packed.chunk_off.data_ptr(), idx_table.data_ptr(),
+          step_dev.data_ptr(), int(lookahead), int(n_steps), dev_dst.data_ptr(), batch, packed.per_sample, int(max_ctas), st)
+
+
 def loop_advance(step_dev, idx_table, idx_live, b_table, b_live, lr_table, lr_live, n_steps: int):
     batch = 0 if idx_live is None else idx_live.numel()
     _call("ssq_loop_advance", step_dev.data_ptr(), _ptr(idx_table), _ptr(idx_live), batch, _ptr(b_table), _ptr(b_live),

@@ -478,6 +478,44 @@ def test_chan_affine(ops):
     assert_close(host(gb), gy.astype(np.float64).sum((0, 2, 3)))
 
 
+def test_pull_rows_host_packed_is_lossless(ops):
+    """zero-packed host cache: device-side packing == the oracle's packing, and the pulling kernel rebuilds the dense mini-batch
+    rows bit for bit from mapped pinned memory (incl. -0.0, denormals, NaN, empty / full chunks, values straddling the 16-byte
+    alignment of the packed stream), for every step of the index table incl. the lookahead clamp"""
+    r = rng(77)
+    n, shape = 40, (3, 32, 32)                                  # 3072 elements = 3 chunks per row
+    x = np.maximum(r.standard_normal((n,) + shape), 0).astype(np.float32)
+    flat = x.reshape(n, -1)
+    flat[1, :1024] = 0.0
+    flat[2, 1024:2048] = r.standard_normal(1024).astype(np.float32) + 3.0
+    flat[3, 5] = -0.0; flat[3, 6] = np.float32(1e-42); flat[3, 7] = np.nan; flat[3, 8] = -np.inf
+    flat[5] = 0.0
+    t = torch.from_numpy(x)
+    assert ops.packable(t) and not ops.packable(torch.zeros(4, 1000))
+    packed = ops.pack_rows_sparse(t, torch.device("cuda"), rows_per_slice=16)
+    mask, vals, off = O.sparse_pack_rows(flat)
+    assert np.array_equal(packed.mask.cpu().numpy().view(np.uint32), mask)
+    assert np.array_equal(packed.vals[:-8].numpy().view(np.uint32), vals.view(np.uint32)) and packed.nnz == vals.size
+    assert np.array_equal(packed.chunk_off.cpu().numpy(), off)
+    assert packed.vals.is_pinned() and abs(packed.density - vals.size / flat.size) < 1e-12
+    steps, batch = 5, 8
+    tab = torch.from_numpy(r.integers(0, n, (steps, batch))).cuda()
+    tab[0, :6] = torch.tensor([1, 2, 3, 5, 3, 0], device="cuda")
+    step = torch.zeros(1, dtype=torch.int64, device="cuda")
+    dst = torch.full((batch,) + shape, 7.0, device="cuda")
+    for s in range(steps + 2):                                  # two replays past the table keep its last row
+        step.fill_(s)
+        for look in (0, 1):
+            dst.fill_(7.0)
+            ops.pull_rows_host_packed(packed, tab, step, look, steps, dst, max_ctas=3)
+            rows = tab[min(s + look, steps - 1)].cpu().numpy()
+            want = flat[rows]
+            got = host(dst).reshape(batch, -1)
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (s, look)
+            if s == 0 and look == 0:
+                assert np.array_equal(got.view(np.uint32), O.sparse_unpack_rows(mask, vals, off, rows, flat.shape[1]).view(np.uint32))
+
+
 def test_bad_arguments_raise(ops):
     from shiftedscalequantization_b200._lib import SsqError
     with pytest.raises(SsqError):

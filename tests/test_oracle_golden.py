@@ -160,3 +160,20 @@ def test_mse_search_vs_reference_numpy_restatement():
     d, z, raw, idx = O.mse_search(g["w"], 4)
     assert_exact(z.astype(np.float64), g["zero_point"], "zero point vs myQuant")
     assert_close(d.astype(np.float64), g["delta"], rtol=2e-7, what="delta vs myQuant")
+
+
+def test_sparse_row_packing_round_trip():
+    """the zero-packed host cache format (no reference counterpart): pack -> unpack is the identity bit for bit, incl. -0.0,
+    denormals, NaN payloads, all-zero and all-non-zero chunks"""
+    from oracle import ssq_oracle as O
+    r = np.random.default_rng(5)
+    x = np.maximum(r.standard_normal((6, 3072)), 0).astype(np.float32)       # post-ReLU: about half zeros
+    x[1, :1024] = 0.0                                                          # an empty chunk
+    x[2, 1024:2048] = r.standard_normal(1024).astype(np.float32) + 3.0        # a full chunk
+    x[3, 5] = -0.0; x[3, 6] = np.float32(1e-42); x[3, 7] = np.nan; x[3, 8] = -np.inf
+    mask, vals, off = O.sparse_pack_rows(x)
+    assert mask.shape == (6, 96) and off.shape == (6 * 3 + 1,) and off[-1] == vals.size == int((x.view(np.uint32) != 0).sum())
+    assert off[4] - off[3] == 0 and off[8] - off[7] == 1024
+    rows = [4, 1, 3, 3, 0, 2]
+    y = O.sparse_unpack_rows(mask, vals, off, rows, 3072)
+    assert np.array_equal(y.view(np.uint32), x[rows].view(np.uint32))

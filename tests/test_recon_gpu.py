@@ -112,7 +112,8 @@ def test_host_resident_engine_is_bit_identical_and_reads_every_loss(monkeypatch)
     from shiftedscalequantization_b200.quant.data_utils import save_inp_oup_data
     iters, bs = 20, 16
     out = {}
-    for host in (False, 'pull', 'dma'):
+    from shiftedscalequantization_b200 import ops
+    for host in (False, 'pull', 'pull_dense', 'dma'):
         Q, qnn, cali = build_qnn()
         block = qnn.model.layer2[0]
         qnn.set_quant_state(False, False); block.set_quant_state(True, False)
@@ -126,10 +127,16 @@ def test_host_resident_engine_is_bit_identical_and_reads_every_loss(monkeypatch)
         tab = index_table(inps.shape[0], bs, iters)
         eng = ReconEngine(block, mods, inps, outs, None, act_quant=False, iters=iters, weight=0.01, b_range=(20, 2),
                           warmup=0.2, p=2.0, batch_size=bs, use_graph=True, idx_table=tab, verbose=False,
-                          host_resident=bool(host), host_stage=host or 'pull', device=torch.device('cuda'))
+                          host_resident=bool(host), host_stage='dma' if host == 'dma' else 'pull', device=torch.device('cuda'),
+                          host_pack=(host == 'pull'))
         if host:
             assert eng.cached_inps.is_pinned() and not eng.cached_inps.is_cuda
-            assert eng.h2d_bytes_per_step() == 4 * (inps[:bs].numel() + outs[:bs].numel())
+            dense = 4 * (inps[:bs].numel() + outs[:bs].numel())
+            if host == 'pull':       # zero-packed cache (post-ReLU features): only the non-zero values cross PCIe
+                assert any(isinstance(src, ops.PackedRows) for src, _s, _c in eng._pull_bufs)
+                assert 0.2 * dense < eng.h2d_bytes_per_step() < 0.95 * dense
+            else:
+                assert eng.h2d_bytes_per_step() == dense
         eng.capture()
         eng.enable_loss_readback()
         direct, lagged = [], []
@@ -141,7 +148,7 @@ def test_host_resident_engine_is_bit_identical_and_reads_every_loss(monkeypatch)
         eng.close()
         assert lagged[0] == 0.0 and lagged[1:] == direct[:-1] and last == direct[-1]
         out[host] = ([m.weight_quantizer.alpha.detach().cpu().numpy().copy() for m in mods], direct)
-    for mode in ('pull', 'dma'):
+    for mode in ('pull', 'pull_dense', 'dma'):
         for a, b in zip(out[False][0], out[mode][0]):
             assert_exact(b, a, f"alpha, host-resident ({mode}) vs HBM-resident cache")
         assert out[False][1] == out[mode][1], mode
