@@ -52,7 +52,7 @@ def _run_with_output_affine(unit, modules, cached_inps, cached_outs, *, iters, w
 
 
 def reconstruct_unit(model, unit, cali_data, *, is_block, batch_size, iters, weight, opt_mode, asym, include_act_func,
-                     b_range, warmup, act_quant, lr, p, multi_gpu, eval, bias_cal=False, scaling='weak'):
+                     b_range, warmup, act_quant, lr, p, multi_gpu, eval, bias_cal=False, scaling='weak', host_resident=False):
     """shared body of block_reconstruction (block_recon.py:10-116) and layer_reconstruction (layer_recon.py:10-104)"""
     if eval:
         iters = 0          # structure-only call: swap the quantisers, learn nothing (block_recon.py:36-37)
@@ -85,7 +85,8 @@ def reconstruct_unit(model, unit, cali_data, *, is_block, batch_size, iters, wei
         else:
             engine = ReconEngine(unit, modules, cached_inps, cached_outs, cached_grads, act_quant=act_quant, iters=iters,
                                  weight=weight, b_range=b_range, warmup=warmup, p=p, lr=lr, opt_mode=opt_mode,
-                                 batch_size=batch_size, multi_gpu=multi_gpu, act_quantizers=act_quantizers, scaling=scaling)
+                                 batch_size=batch_size, multi_gpu=multi_gpu, act_quantizers=act_quantizers, scaling=scaling,
+                                 host_resident=host_resident)
             try:
                 engine.run()
             finally:
@@ -103,14 +104,17 @@ def block_reconstruction(model: QuantModel, block: BaseQuantBlock, cali_data: to
                          batch_size: int = 32, iters: int = 20000, weight: float = 0.01, opt_mode: str = 'mse',
                          asym: bool = False, include_act_func: bool = True, b_range: tuple = (20, 2),
                          warmup: float = 0.0, act_quant: bool = False, lr: float = 4e-5, p: float = 2.0,
-                         multi_gpu: bool = False, eval: bool = False, bias_cal: bool = False, scaling: str = 'weak'):
+                         multi_gpu: bool = False, eval: bool = False, bias_cal: bool = False, scaling: str = 'weak',
+                         host_resident: bool = False):
     """Optimise the rounding (or, with act_quant, the activation step sizes) of every layer in `block` so the
     block output matches the FP block output on the calibration data. Arguments as upstream; `bias_cal` (README flag,
     keyword-only in practice) additionally learns every layer's output-channel scale/offset in the weight phase;
-    `scaling` ('weak' | 'strong') picks the multi-GPU partitioning (engine.ReconEngine)."""
+    `scaling` ('weak' | 'strong') picks the multi-GPU partitioning (engine.ReconEngine); `host_resident=True` keeps the cached
+    features in pinned host memory (upstream's keep_gpu=False, quant/data_utils.py:34-36) and pulls every mini-batch over PCIe."""
     reconstruct_unit(model, block, cali_data, is_block=True, batch_size=batch_size, iters=iters, weight=weight,
                      opt_mode=opt_mode, asym=asym, include_act_func=include_act_func, b_range=b_range, warmup=warmup,
-                     act_quant=act_quant, lr=lr, p=p, multi_gpu=multi_gpu, eval=eval, bias_cal=bias_cal, scaling=scaling)
+                     act_quant=act_quant, lr=lr, p=p, multi_gpu=multi_gpu, eval=eval, bias_cal=bias_cal, scaling=scaling,
+                     host_resident=host_resident)
 
 
 class LossFunction:

@@ -154,6 +154,23 @@ def test_host_resident_engine_is_bit_identical_and_reads_every_loss(monkeypatch)
         assert out[False][1] == out[mode][1], mode
 
 
+def test_block_reconstruction_host_resident_keyword(monkeypatch):
+    """public API: block_reconstruction(..., host_resident=True) (upstream's keep_gpu=False cache placement) learns the same
+    alphas as the HBM-resident default, bit for bit, under deterministic cuDNN"""
+    monkeypatch.setattr(torch.backends.cudnn, "deterministic", True)
+    monkeypatch.setattr(torch.backends.cudnn, "benchmark", False)
+    res = []
+    for host in (False, True):
+        Q, qnn, cali = build_qnn()
+        block = qnn.model.layer1[1]
+        torch.manual_seed(11)
+        Q.block_reconstruction(qnn, block, cali_data=cali, iters=24, weight=0.01, asym=True, b_range=(20, 2), warmup=0.2,
+                               act_quant=False, opt_mode='mse', batch_size=16, host_resident=host)
+        res.append([m.weight_quantizer.alpha.detach().cpu().numpy().copy() for m in block.modules() if isinstance(m, Q.QuantModule)])
+    for a, b in zip(*res):
+        assert_exact(b, a, "alpha, host_resident=True vs default")
+
+
 def test_block_reconstruction_weight_then_act_phase():
     Q, qnn, cali = build_qnn()
     dev = torch.device('cuda')
