@@ -5,7 +5,8 @@
 One "step" = one reconstruction iteration (mini-batch 32) on EACH of the 9 reconstructed units of ResNet-18
 (8 residual blocks + fc; the stem is ignore_reconstruction upstream), i.e. 9 iterations of the hot loop of
 quant/block_recon.py:89-105. `value` = iterations/s with the cached features resident in HBM; `e2e` = the same
-through the host-resident cache mode (pinned host features, per-step H2D of the mini-batch, D2H of the loss).
+through the host-resident cache mode (pinned host features — post-ReLU tensors zero-packed —, per-step H2D of the mini-batch,
+D2H of the loss; the mode block_reconstruction(..., host_resident=True) selects).
 The roofline object reports the dominant kernel on DRAM-resident inputs (> L2), next to its in-step share.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
