@@ -7,6 +7,7 @@
 // weight in registers (12 B/elem instead of (S+2)*4 B/elem).
 #include "ssq_common.cuh"
 #include "ssq_fastdiv.h"
+#include "ssq_slab_plan.h"
 
 namespace ssq {
 
@@ -551,21 +552,6 @@ fq_shift_bwd_finish_kernel(const float* __restrict__ partial, float* __restrict_
     }
     s = warp_sum(s);
     if (lane == 0) gp[t] = (float)s;
-}
-
-static inline void slab_plan(int64_t oc, int64_t K, int& nslab, int64_t& rows_per_slab, int vec_ctas = 0) {
-    const bool vec = vec_ctas > 0;
-    int64_t colblocks = ((vec ? K / 4 : K) + SSQ_THREADS - 1) / SSQ_THREADS;
-    // vec: ONE wave of column-block x slab CTAs at the occupancy the launch bounds guarantee (rounding the slab count up
-    // gave 612 CTAs for 592 slots: a second wave of 20 CTAs that cost as much as the first); slabs of at least 4 rows so the
-    // partials stay small
-    int64_t want = vec ? ((int64_t)SSQ_NUM_SMS * vec_ctas) / colblocks
-                       : ((int64_t)SSQ_NUM_SMS * SSQ_CTAS_PER_SM + colblocks - 1) / colblocks;
-    if (vec && want > (oc + 3) / 4) want = (oc + 3) / 4;
-    if (want > oc) want = oc;
-    if (want < 1) want = 1;
-    rows_per_slab = (oc + want - 1) / want;
-    nslab = (int)((oc + rows_per_slab - 1) / rows_per_slab);
 }
 
 static inline unsigned finish_grid(int64_t ic, int nshift) {
