@@ -47,6 +47,8 @@ def main(argv=None):
     # the reference README's flags (README.md:20,33-34)
     flag = lambda v: str(v).lower() in ('1', 'true', 'yes')
     ap.add_argument('--device_gpu', default='cuda:0')
+    ap.add_argument('--host_resident', default=False, type=flag,
+                    help="weight phase: keep the cached features in pinned host memory (upstream's keep_gpu=False) and pull every mini-batch over PCIe")
     ap.add_argument('--bias_cal', default=False, type=flag, help='learn the output-channel scale gamma^z and offset varphi^z')
     ap.add_argument('--bias_ch_quant', default=False, type=flag,
                     help='learn the input-channel group R: shifted-scale ChannelQuant + fused shift/rounding loop on BasicBlock units')
@@ -119,7 +121,8 @@ def main(argv=None):
 
     t0 = time.time()
     recon_model(qnn, cali_data=cali, iters=args.iters_w, weight=args.weight, asym=True, b_range=(args.b_start, args.b_end),
-                warmup=args.warmup, act_quant=False, opt_mode='mse', batch_size=args.batch_size, bias_cal=args.bias_cal)
+                warmup=args.warmup, act_quant=False, opt_mode='mse', batch_size=args.batch_size, bias_cal=args.bias_cal,
+                host_resident=args.host_resident)
     torch.cuda.synchronize()
     print(f'weight reconstruction: {time.time() - t0:.2f}s for {done[0]} units x {args.iters_w} iterations')
     qnn.set_quant_state(weight_quant=True, act_quant=False)
