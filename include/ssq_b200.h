@@ -179,7 +179,10 @@ size_t ssq_shift_bwd_ws_bytes(int64_t oc, int64_t ic, int64_t kk, int nshift, in
  * Outputs per row: delta, zero_point, raw_zero_point (= -new_min), best score and winning
  * index (-1 if no candidate scored below 1e10, i.e. the reference's delta-stays-None case).
  * rows == 1 with large k is the per-tensor activation case (grid-wide variant; needs ws).
- * p_norm is 2.4 in the reference; n_levels = 2^n_bits. */
+ * p_norm is 2.4 in the reference; n_levels = 2^n_bits.
+ * Two passes, identical argmin: all candidates are ranked with a MUFU-based |d|^p, the ones
+ * within 1e-4 of the ranked minimum are settled with libm powf in a fixed summation order
+ * (csrc/scale_search.cu header). Rows shorter than 128 elements get one warp each. */
 int ssq_mse_scale_search(const float* x, int64_t rows, int64_t k, int n_levels, int symmetric,
                          float p_norm, float* delta, float* zero_point, float* raw_zero_point,
                          float* best_score, int32_t* best_index,
@@ -195,12 +198,22 @@ int ssq_row_minmax(const float* x, int64_t rows, int64_t k, float* row_min, floa
  * cand[j], j < level, in the reference's order (descending: level/level ... 1/level, fp32);
  * a column fits candidate c when every row has lo < (w/c/delta + zero)/(L-1) < hi;
  * inp_scale[col] = the LAST fitting candidate, else it keeps its incoming value.
- * zero = rint(raw_zp/delta) per row is computed by the kernel. */
+ * zero = rint(raw_zp/delta) per row is computed by the kernel.
+ * One pass over w (4 B/element, independent of `level`): the predicate is monotone in the
+ * candidate, so each element's fitting prefix is estimated in closed form and settled with
+ * the exact predicate near boundaries; inputs outside the proof's preconditions (a foreign
+ * candidate list, zero outside [0, L-1], lo >= 0, hi <= 1) run the brute-force sweep of all
+ * `level` candidates instead. _ex(force_brute=1) selects the brute force explicitly. */
 int ssq_inp_scale_search(const float* w, const float* delta, const float* raw_zero_point,
                          const float* cand, int level, float x_range, float lo, float hi,
                          float* inp_scale, int64_t oc, int64_t k,
                          void* ws, size_t ws_bytes, void* stream);
-size_t ssq_inp_scale_search_ws_bytes(int64_t k);
+int ssq_inp_scale_search_ex(const float* w, const float* delta, const float* raw_zero_point,
+                            const float* cand, int level, float x_range, float lo, float hi,
+                            float* inp_scale, int64_t oc, int64_t k, int force_brute,
+                            void* ws, size_t ws_bytes, void* stream);
+size_t ssq_inp_scale_search_ws_bytes(int64_t k);              /* sized for oc <= 65536 */
+size_t ssq_inp_scale_search_ws_bytes2(int64_t oc, int64_t k);
 
 /* ---- K3: reconstruction loss -----------------------------------------------------------
  * quant/quant_layer.py:25-32 (lp_loss 'none': sum|d|^p / (numel/C)), quant/block_recon.py:154-162

@@ -58,7 +58,9 @@ PROTOTYPES = {
     "ssq_mse_scale_search_ws_bytes": (_sz, [_i64, _i64]),
     "ssq_row_minmax": (_i32, [_p, _i64, _i64, _p, _p, _p, _sz, _p]),
     "ssq_inp_scale_search": (_i32, [_p, _p, _p, _p, _i32, _f, _f, _f, _p, _i64, _i64, _p, _sz, _p]),
+    "ssq_inp_scale_search_ex": (_i32, [_p, _p, _p, _p, _i32, _f, _f, _f, _p, _i64, _i64, _i32, _p, _sz, _p]),
     "ssq_inp_scale_search_ws_bytes": (_sz, [_i64]),
+    "ssq_inp_scale_search_ws_bytes2": (_sz, [_i64, _i64]),
     "ssq_recon_loss": (_i32, [_p, _p, _p, _p, _p, _p, _i64, _i64, _d, _i32, _f, _p, _p, _sz, _p]),
     "ssq_recon_loss_bwd": (_i32, [_p, _p, _p, _p, _p, _p, _i64, _i64, _d, _i32, _f, _p, _sz, _p]),
     "ssq_chan_affine_fwd": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _p]),

@@ -447,14 +447,15 @@ def row_minmax(x2d):
     return mn, mx
 
 
-def inp_scale_search(w2d, delta, raw_zero_point, cand, x_range: float, lo: float, hi: float, inp_scale):
-    """w2d [oc,k]; updates inp_scale ([k]) in place and returns it."""
+def inp_scale_search(w2d, delta, raw_zero_point, cand, x_range: float, lo: float, hi: float, inp_scale, force_brute=False):
+    """w2d [oc,k]; updates inp_scale ([k]) in place and returns it. force_brute: evaluate every (column, candidate) with
+    the reference expression instead of the one-pass monotone search (cross-check; same result)."""
     w2d = _req(w2d, "w"); delta = _req(delta, "delta"); raw_zero_point = _req(raw_zero_point, "raw_zero_point")
     cand = _req(cand, "cand"); inp_scale = _req(inp_scale, "inp_scale")
     oc, k = w2d.shape
-    ws = workspace(w2d.device, _lib.load().ssq_inp_scale_search_ws_bytes(k), "inpscale")
-    _call("ssq_inp_scale_search", w2d.data_ptr(), delta.data_ptr(), raw_zero_point.data_ptr(), cand.data_ptr(),
-          cand.numel(), float(x_range), float(lo), float(hi), inp_scale.data_ptr(), oc, k,
+    ws = workspace(w2d.device, _lib.load().ssq_inp_scale_search_ws_bytes2(oc, k), "inpscale")
+    _call("ssq_inp_scale_search_ex", w2d.data_ptr(), delta.data_ptr(), raw_zero_point.data_ptr(), cand.data_ptr(),
+          cand.numel(), float(x_range), float(lo), float(hi), inp_scale.data_ptr(), oc, k, int(bool(force_brute)),
           ws.data_ptr(), ws.numel(), _stream(w2d))
     return inp_scale
 
