@@ -349,27 +349,78 @@ def kernel_microbench(dev, peak_gbs):
     return res
 
 
-def scale_search_bench(Q, qnn, dev):
-    """K2a alone: the 80-candidate MSE clip search over every weight tensor of the model (per-channel rows) and over
-    one activation-sized tensor (per-tensor, grid-wide variant); CUDA events, after one warm-up pass"""
+def scale_search_bench(Q, qnn, dev, peak_gbs):
+    """K2a / K2b on the roofline: the 80-candidate MSE clip search over every weight tensor of the model
+    (per-channel rows) and over one activation-sized tensor (grid-wide variant), row shapes k = 9 / 576 / 4608 on their own,
+    and the ChannelQuantMSE input-scale search. CUDA events, after warm-up. K2a is instruction-bound by design (80 candidates
+    x ~14 instructions + 2 MUFU per 4 bytes), so it reports candidate evaluations/s and the fraction of the SM's issue rate
+    beside the (small) HBM fraction; K2b is one pass over the weights and reports the HBM fraction of its 4 B/element."""
     from shiftedscalequantization_b200 import ops
     mods = [m for m in qnn.modules() if isinstance(m, Q.QuantModule)]
     rows = [(m.org_weight.reshape(m.org_weight.shape[0], -1).contiguous(), m.weight_quantizer.n_levels) for m in mods]
+
+    def timeit(fn, reps=5, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps
+
     def run():
         for r, nl in rows:
             ops.mse_scale_search(r, nl, False)
-    run(); torch.cuda.synchronize(dev)
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record(); run(); e1.record(); torch.cuda.synchronize(dev)
-    w_ms = e0.elapsed_time(e1)
+    w_ms = timeit(run, reps=3, warm=1)
     act = torch.relu(torch.randn(64, 64, 112, 112, device=dev)).reshape(1, -1)
-    ops.mse_scale_search(act, 16, False); torch.cuda.synchronize(dev)
-    e0.record(); ops.mse_scale_search(act, 16, False); e1.record(); torch.cuda.synchronize(dev)
-    a_ms = e0.elapsed_time(e1)
-    return {"weights_all_layers_ms": w_ms, "channels": int(sum(r.shape[0] for r, _ in rows)),
-            "weight_elems": int(sum(r.numel() for r, _ in rows)),
-            "activation_tensor_ms": a_ms, "activation_elems": int(act.numel()),
-            "note": "powf-bound (80 x |d|^2.4 per element), not HBM-bound; reference: Python loop, 48.5 s on 8 CPU cores (SURVEY probe)"}
+    a_ms = timeit(lambda: ops.mse_scale_search(act, 16, False), reps=3, warm=1)
+    # issue-rate roof: 148 SMs x 4 schedulers x 1 warp-instruction/clk; the ranking pass costs ~16 warp-instructions per
+    # 32 (element, candidate) pairs, so pairs/s <= SMs*4*32*clk/16
+    sm_clk = 1.9e9
+    pair_roof = 148 * 4 * 32 * sm_clk / 16.0
+
+    def k2a(x2d, nl):
+        ms = timeit(lambda: ops.mse_scale_search(x2d, nl, False))
+        n = x2d.numel()
+        return {"ms": round(ms, 4), "rows": x2d.shape[0], "k": x2d.shape[1], "elems": n, "gbs": round(4 * n / ms / 1e6, 1),
+                "hbm_frac": round(4 * n / ms / 1e6 / peak_gbs, 4), "cand_evals_per_s": round(80 * n / ms * 1e3, 0),
+                "issue_frac_est": round(80 * n / (ms * 1e-3) / pair_roof, 3)}
+    out = {"weights_all_layers_ms": w_ms, "channels": int(sum(r.shape[0] for r, _ in rows)),
+           "weight_elems": int(sum(r.numel() for r, _ in rows)), "activation_tensor_ms": a_ms, "activation_elems": int(act.numel()),
+           "round1_ms": {"weights_all_layers": 4.63, "activation_tensor": 17.07, "source": "BENCH_r01.json extra.scale_search"},
+           "k2a": {}, "k2b": {}}
+    torch.manual_seed(3)
+    out["k2a"]["rows_k9(depthwise)"] = k2a(torch.randn(65536, 9, device=dev) * 0.05, 8)
+    out["k2a"]["rows_k576"] = k2a(torch.randn(16384, 576, device=dev) * 0.05, 4)
+    out["k2a"]["rows_k4608"] = k2a(torch.randn(4096, 4608, device=dev) * 0.05, 4)
+    out["k2a"]["tensor_51M(activations)"] = {**k2a(act, 16)}
+    del act
+
+    def k2b(oc, k, level, bits=2, thr=1.5):
+        w = torch.randn(oc, k, device=dev) * 0.02
+        mn = w.min(1)[0].clamp(max=0); mx = w.max(1)[0].clamp(min=0)
+        L = 2 ** bits
+        d = ((mx - mn) / (L - 1)).contiguous(); raw = (-mn).contiguous()
+        cand = torch.tensor([i / level for i in range(level, 0, -1)], dtype=torch.float32, device=dev)
+        lo = float(torch.tensor(0.0 - 0.5 / (L - 1) * thr, dtype=torch.float32)); hi = float(torch.tensor(1.0 + 0.5 / (L - 1) * thr, dtype=torch.float32))
+        s = torch.ones(k, device=dev)
+        ms = timeit(lambda: ops.inp_scale_search(w, d, raw, cand, L - 1, lo, hi, s))
+        ms_b = timeit(lambda: ops.inp_scale_search(w, d, raw, cand, L - 1, lo, hi, s, force_brute=True), reps=2, warm=1) \
+            if oc * k * level <= 2 ** 31 else None
+        n = oc * k
+        return {"ms": round(ms, 4), "oc": oc, "k": k, "level": level, "gbs": round(4 * n / ms / 1e6, 1),
+                "hbm_frac": round(4 * n / ms / 1e6 / peak_gbs, 3), "brute_force_ms": None if ms_b is None else round(ms_b, 4)}
+    out["k2b"]["[512,256,3,3]_level16"] = k2b(512, 2304, 16)
+    out["k2b"]["[512,256,3,3]_level1024"] = k2b(512, 2304, 1024)
+    out["k2b"]["[4096,4096,3,3]_level16(604MB)"] = k2b(4096, 36864, 16)
+    out["k2b"]["[4096,4096,3,3]_level1024(604MB)"] = k2b(4096, 36864, 1024)
+    torch.cuda.empty_cache()
+    out["note"] = ("K2a: MUFU-ranked candidates, libm-settled survivors (identical argmin); issue_frac_est = candidate evaluations/s over "
+                   "the issue-rate roof at 16 warp-instructions per 32 evaluations and 1.9 GHz; the measured smsp__issue_active is in "
+                   "profiles/r02_k2_ncu.md. K2b: one pass, 4 B/element. Reference: Python loops, 48.5 s for the ResNet-18 weights on 8 CPU cores (SURVEY probe)")
+    return out
 
 
 def shifted_loop_bench(dev, n_images=256):
@@ -496,7 +547,10 @@ def run_ours(args):
         qnn(cali[:64].to(dev))
     torch.cuda.synchronize(dev); scale_search_s = time.perf_counter() - t0
     log(f"[rank {rank}] weight scale search (5800 channels x 80 candidates): {scale_search_s * 1e3:.1f} ms")
-    search = scale_search_bench(Q, qnn, dev) if world == 1 else None
+    search = scale_search_bench(Q, qnn, dev, peak_gbs) if world == 1 else None
+    if args.k2_only:
+        emit(json.dumps({"first_quantised_forward_ms": scale_search_s * 1e3, "scale_search": search}))
+        return
     engines, feats = make_engines(Q, qnn, cali, dev, act_quant=False, multi_gpu=world > 1, scaling=args.scaling)
     setup_s = time.perf_counter() - t_setup
     launches_per_step = sum(e.launches_per_iter for e in engines)
@@ -685,6 +739,7 @@ def main():
     ap.add_argument("--skip-shift", action="store_true", help="no shifted-scale loop timing")
     ap.add_argument("--micro-only", action="store_true", help="only the DRAM-resident kernel microbench")
     ap.add_argument("--skip-micro", action="store_true", help="no roofline microbench (short profiler runs)")
+    ap.add_argument("--k2-only", action="store_true", help="only the scale-search (K2a / K2b) roofline numbers")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

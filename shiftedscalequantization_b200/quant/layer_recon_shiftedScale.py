@@ -223,8 +223,12 @@ def shifted_b_table(loss_func, iters, temp_decay=None, gate_only=False):
     return tab
 
 
-def _shifted_recon(unit, modules, iters, lmda, model, act, adaround, loss_cls, train_target, device):
+def _shifted_recon(unit, modules, iters, lmda, model, act, adaround, loss_cls, train_target, device, loss_off=None):
+    """act: optimise the activation step sizes (block variant, upstream :21-35); loss_off: build the loss with
+    round_loss='none' (defaults to `act`; the layer variant passes act=False, loss_off=<its act flag>: upstream :283
+    switches the regulariser off for act=True but still optimises the weight parameters, :270-279)"""
     from ..engine import cosine_lr_table
+    loss_off = act if loss_off is None else bool(loss_off)
     warmup, p, b_range, lr, batch_size = 0.2, 2.0, (20, 2), 4e-4, 32
     scheduler = None
     if act:
@@ -232,7 +236,7 @@ def _shifted_recon(unit, modules, iters, lmda, model, act, adaround, loss_cls, t
     else:
         slots = _prepare_weight_params(modules, adaround)
         print("number of elements in opt_params: {}".format(sum(getattr(o, a).numel() for o, a in slots)))
-    loss_func = loss_cls(unit, round_loss='none' if act else 'relaxation', lmda=lmda, max_count=iters, b_range=b_range,
+    loss_func = loss_cls(unit, round_loss='none' if loss_off else 'relaxation', lmda=lmda, max_count=iters, b_range=b_range,
                          decay_start=0, warmup=warmup, p=p, adaround=adaround)
     cached_inp = torch.cat(unit.cached_inp_features).to(device)
     cached_out = torch.cat(unit.cached_out_features).to(device)
@@ -240,10 +244,10 @@ def _shifted_recon(unit, modules, iters, lmda, model, act, adaround, loss_cls, t
     if USE_CAPTURED_LOOP and iters >= 8:
         lr_table = cosine_lr_table(lr, iters) if act else torch.full((max(iters, 1),), 1e-3)
         b_tables = [shifted_b_table(loss_func, iters, gate_only=not adaround)]
-        quantizers = loss_func._quantizers() if not act else []
+        quantizers = loss_func._quantizers() if not loss_off else []
 
         def reg_fn(live):
-            if act or not quantizers:
+            if loss_off or not quantizers:
                 return []
             if adaround:
                 return [sum(ops.RoundReg.apply(q.beta, live[0], lmda) for q in quantizers)]
@@ -294,14 +298,13 @@ def block_recon_shiftedScale(block: BaseQuantBlock, iters: int = 20000, lmda: fl
 
 def layer_recon_shiftedScale(layer: QuantModule, iters: int = 20000, lmda: float = 1., model=None, test_loader=None,
                              act=False, adaround=False, useShiftedScale=True):
-    """Single-layer variant. As upstream, the weight parameters are optimised even when act=True is passed, and
-    with adaround the hard switch is written to `layer.hard_round` (not the quantiser's) — quirks kept (:325-326)."""
+    """Single-layer variant. As upstream, the weight parameters are optimised even when act=True is passed (act only
+    switches the regulariser off for the whole loop, :283), and with adaround the hard switch is written to
+    `layer.hard_round` (not the quantiser's) — quirks kept (:325-326). Pinned by tests/golden/layer_shift.npz."""
     model.train()
     device = next(model.parameters()).device
     out, lf, opt, ci, co, s0, bs = _shifted_recon(layer, [layer], iters, lmda, model, False, adaround,
-                                                  ScaleLossFunction, None, device)
-    if act:
-        lf.round_loss = 'none'
+                                                  ScaleLossFunction, None, device, loss_off=bool(act))
     if adaround:
         layer.hard_round = True
     else:

@@ -9,7 +9,9 @@
   long_horizon.npz  the real `block_reconstruction` on ResNet-18 layer1.0 and the real, unmodified `layer_reconstruction`
                     on fc for 2 000 and 20 000 iterations (the north_star horizon): final AdaRound alphas and hard codes.
 
-Run in the build container only:  python tests/golden/make_golden_round2.py [layer_shift] [families] [long_horizon]
+  channelquantact.npz  quant/channelQuantAct.py:45-54, the 'adaround' / 'none' forward modes + autograd of beta.
+
+Run in the build container only:  python tests/golden/make_golden_round2.py [layer_shift] [families] [long_horizon] [channelquantact]
 The vectors are committed; nothing at test/bench time reads /root/reference.
 """
 import os
@@ -190,8 +192,37 @@ def gen_long_horizon():
     save("long_horizon", **out)
 
 
+def gen_channelquantact():
+    """quant/channelQuantAct.py:45-54: the 'adaround' forward of the activation twin (hard rounding only: the soft branch calls
+    an undefined get_soft_round upstream; the caller supplies beta and hard_round, the class never initialises them)"""
+    from quant.quant_layer import UniformAffineQuantizer
+    from quant.channelQuantAct import ChannelQuantAct
+    g = torch.Generator().manual_seed(4242)
+    x = torch.relu(torch.randn(4, 8, 6, 6, generator=g)) * 1.7
+    uaq = UniformAffineQuantizer(n_bits=4, channel_wise=False, scale_method='mse', leaf_param=True)
+    uaq(x)
+    q = ChannelQuantAct(uaq)
+    q.opt_mode = 'adaround'
+    q.beta = torch.nn.Parameter(torch.randn(x.shape, generator=g) * 2.0)
+    out = {"x": npy(x), "delta": npy(uaq.delta), "zp": npy(uaq.zero_point), "beta": npy(q.beta)}
+    q.hard_round = False
+    try:                                   # upstream: the soft branch calls an undefined get_soft_round (:48)
+        q(x)
+        out["soft_raises"] = np.array(False)
+    except AttributeError:
+        out["soft_raises"] = np.array(True)
+    q.hard_round = True
+    with torch.no_grad():
+        out["y_hard"] = npy(q(x))
+    q.opt_mode = 'none'
+    with torch.no_grad():
+        out["y_none"] = npy(q(x))
+    save("channelquantact", **out)
+
+
 if __name__ == "__main__":
     import_reference()
-    todo = sys.argv[1:] or ["layer_shift", "families", "long_horizon"]
+    todo = sys.argv[1:] or ["layer_shift", "families", "long_horizon", "channelquantact"]
     for name in todo:
-        {"layer_shift": gen_layer_shift, "families": gen_families, "long_horizon": gen_long_horizon}[name]()
+        {"layer_shift": gen_layer_shift, "families": gen_families, "long_horizon": gen_long_horizon,
+         "channelquantact": gen_channelquantact}[name]()

@@ -306,6 +306,94 @@ def test_inp_scale_search_oracle_large(ops):
             assert set(np.unique(host(s))).issubset(set(host(cand).tolist()))
 
 
+@pytest.mark.parametrize("level,thr,bits", [(1, 1.0, 2), (2, 1.5, 2), (7, 1.0, 3), (16, 1.5, 2), (333, 2.0, 4), (1024, 1.5, 2), (1024, 0.3, 8)])
+def test_inp_scale_search_one_pass_equals_brute_force(ops, level, thr, bits):
+    """the one-pass monotone-prefix search against the brute-force sweep of every (column, candidate) with the reference
+    expression, on weights salted with the cases the estimate is weakest on: zeros, values sitting exactly on a candidate
+    boundary (w = V * c_j), NaN / Inf, ragged column counts"""
+    r = rng(level * 7 + bits)
+    L = 2 ** bits
+    oc, k = 96, 1000 + (level % 3)                                   # k not a multiple of 4 for some cases
+    w = (r.standard_normal((oc, k)) * 0.03).astype(np.float32)
+    w[r.integers(0, oc, 200), r.integers(0, k, 200)] = 0.0
+    d, z, raw = zip(*[O.max_init(row, bits) for row in w])
+    d = np.array(d, np.float32); raw = np.array(raw, np.float32)
+    cand_np = np.array([i / level for i in range(level, 0, -1)], dtype=np.float32)
+    lo = np.float32(0.0 - 0.5 / (L - 1) * thr); hi = np.float32(1.0 + 0.5 / (L - 1) * thr)
+    # boundary salting: w = fl(vmax * c_j) where vmax ~ delta * ((hi * (L-1)) - zero) is close to the row's interval end
+    zero = np.rint(raw / d)
+    for _ in range(300):
+        i, j, c = r.integers(0, oc), r.integers(0, k), cand_np[r.integers(0, level)]
+        vmax = d[i] * (hi * (L - 1) - zero[i])
+        w[i, j] = np.float32(vmax * c * (1 + (r.integers(-3, 4)) * 6e-8))
+    w[3, 5] = np.nan; w[7, 11] = np.inf; w[9, 13] = -np.inf
+    cand = torch.from_numpy(cand_np).cuda()
+    fast = torch.ones(k, device="cuda"); brute = torch.ones(k, device="cuda")
+    ops.inp_scale_search(dev(w), dev(d), dev(raw), cand, L - 1, float(lo), float(hi), fast)
+    ops.inp_scale_search(dev(w), dev(d), dev(raw), cand, L - 1, float(lo), float(hi), brute, force_brute=True)
+    assert_exact(host(fast), host(brute), f"inp_scale, level {level}")
+    assert host(fast)[5] == 1.0 and host(fast)[11] == 1.0 and host(fast)[13] == 1.0     # NaN / Inf columns never fit: untouched
+    if level <= 16:
+        ref = O.inp_scale_search(w, d.reshape(-1, 1), raw.reshape(-1, 1), L, level, thr)
+        assert_exact(host(fast), ref.reshape(-1), "inp_scale vs oracle")
+
+
+def test_inp_scale_search_falls_back_outside_its_preconditions(ops):
+    """a zero point outside [0, L-1], a foreign candidate list and lo >= 0 take the brute-force path: same answers as the
+    forced brute force, and as the oracle"""
+    r = rng(77)
+    w = (r.standard_normal((40, 260)) * 0.03).astype(np.float32)
+    d = np.full(40, 0.02, np.float32)
+    raw = (r.uniform(-0.2, 0.4, 40)).astype(np.float32)              # zero = rint(raw/d) in [-10, 20]: outside [0, 3]
+    level, L = 16, 4
+    cand_np = np.array([i / level for i in range(level, 0, -1)], dtype=np.float32)
+    for cand_try, lo, hi in ((cand_np, -0.25, 1.25), (cand_np * np.float32(0.97), -0.25, 1.25), (cand_np, 0.01, 1.25)):
+        cand = torch.from_numpy(cand_try.astype(np.float32)).cuda()
+        raw_try = raw if cand_try is cand_np and lo < 0 else np.abs(raw) * 0.1
+        fast = torch.ones(260, device="cuda"); brute = torch.ones(260, device="cuda")
+        ops.inp_scale_search(dev(w), dev(d), dev(raw_try), cand, L - 1, lo, hi, fast)
+        ops.inp_scale_search(dev(w), dev(d), dev(raw_try), cand, L - 1, lo, hi, brute, force_brute=True)
+        assert_exact(host(fast), host(brute), "fallback path")
+
+
+@pytest.mark.parametrize("k", [1, 5, 9, 27, 127, 128, 129, 1023])
+def test_mse_search_row_variants_agree_with_oracle(ops, k):
+    """warp-per-row (k < 128) and CTA-per-row variants, ragged lengths, against the oracle's full 80-candidate libm scan"""
+    r = rng(900 + k)
+    rows = 37
+    x = (r.standard_normal((rows, k)) * 0.05).astype(np.float32)
+    for bits in (2, 4):
+        d, z, raw, score, idx = ops.mse_scale_search(dev(x), 2 ** bits, False)
+        for i in range(rows):
+            res, scores = O.mse_search_row(x[i], bits, return_scores=True)
+            got = int(host(idx)[i])
+            if res is None:                                          # k == 1: delta = 0, every score NaN
+                assert got == -1
+                continue
+            dr, zr, rr, ir = res
+            if got != ir:
+                rel = abs(float(scores[got]) - float(scores[ir])) / max(float(scores[ir]), 1e-30)
+                assert rel < 2e-6, f"k={k} row {i}: picked {got} vs {ir}, score gap {rel:.2e}"
+            else:
+                assert host(d)[i] == dr and host(z)[i] == zr and host(raw)[i] == rr
+
+
+def test_mse_search_two_pass_equals_full_scan_on_hostile_rows(ops):
+    """rows the ranking pass must hand to the settle pass untouched: NaN / Inf / huge elements, p = 2 (no ranking), and
+    plain rows for which every candidate is settled (p = 2.4 vs the same search with the window forced open by p = 2.4000001)"""
+    x = torch.randn(6, 300, device="cuda") * 0.1
+    x[1, 7] = float("nan"); x[2, 9] = float("inf"); x[3, 11] = 1e30
+    d, z, raw, score, idx = ops.mse_scale_search(x, 16, False)
+    hx = host(x)
+    for i in (0, 3, 4, 5):
+        (dr, zr, rr, ir), scores = O.mse_search_row(hx[i], 4, return_scores=True)
+        assert int(host(idx)[i]) == ir and host(d)[i] == dr, i
+    assert int(host(idx)[1]) == -1                                   # NaN poisons every score: delta stays None upstream
+    d2, z2, raw2, score2, idx2 = ops.mse_scale_search(x[:1].repeat(4, 1), 16, False, p_norm=2.0)
+    (dr, zr, rr, ir), _ = O.mse_search_row(hx[0], 4, p=2.0, return_scores=True)
+    assert (host(idx2) == ir).all() and (host(d2) == dr).all()
+
+
 # ------------------------------------------------------------------------------------------- K1c
 @pytest.mark.parametrize("case", golden("channelquant").cases())
 def test_shift_golden(ops, case):
