@@ -96,8 +96,8 @@ class ReconEngine:
         computes (no host work per step); 'dma': one cudaMemcpyAsync per row on a copy stream, issued by the host.
         host_pack (pull mode; default on): cached tensors whose rows are a multiple of 1024 elements and at most 80 % non-zero —
         post-ReLU features — are kept zero-packed on the host (non-zero values only; bit mask and chunk offsets on the device, 3 %
-        of the dense size) and expanded by the pulling kernel, so fewer bytes cross PCIe; lossless, same trajectory."""
-        """scaling (multi_gpu only): 'weak' = every rank draws its own mini-batch of `batch_size` from its shard and the
+        of the dense size) and expanded by the pulling kernel, so fewer bytes cross PCIe; lossless, same trajectory.
+        scaling (multi_gpu only): 'weak' = every rank draws its own mini-batch of `batch_size` from its shard and the
         gradients are SUMMED (the reference's link.allreduce semantics, block_recon.py:100-102; global batch = R x batch);
         'strong' = the ranks split ONE global mini-batch of `batch_size` (every rank holds the whole cache and the same
         index table, rank r takes columns [r*b, (r+1)*b)); the loss gradient is scaled by 1/R and the regulariser counted
@@ -171,12 +171,16 @@ class ReconEngine:
         self._frozen = [(q, q.requires_grad) for q in unit.parameters()]
         for q, _ in self._frozen:
             q.requires_grad_(False)
-        if act_quant:
-            self._setup_act_phase(list(act_quantizers))
-        else:
-            self._setup_weight_phase()
-        self.exp_avg = torch.zeros_like(self.flat)
-        self.exp_avg_sq = torch.zeros_like(self.flat)
+        try:
+            if act_quant:
+                self._setup_act_phase(list(act_quantizers))
+            else:
+                self._setup_weight_phase()
+            self.exp_avg = torch.zeros_like(self.flat)
+            self.exp_avg_sq = torch.zeros_like(self.flat)
+        except BaseException:
+            self.close()                 # a failed set-up must not leave the unit frozen or holding engine weights
+            raise
 
     # ------------------------------------------------------------------------------------------ setup
     def _setup_weight_phase(self):
@@ -418,11 +422,13 @@ class ReconEngine:
         for q, flag in self._frozen:
             q.requires_grad_(flag)
         if self.act_quant:
-            for q in self.act_quantizers:
+            for q in getattr(self, 'act_quantizers', ()):
                 q.delta.requires_grad_(True)
         else:
             for m in self.modules:
-                m.weight_quantizer.alpha.requires_grad_(True)
+                a = getattr(m.weight_quantizer, 'alpha', None)
+                if a is not None:
+                    a.requires_grad_(True)
         self.graph = None
 
 
@@ -581,9 +587,10 @@ class AutogradReconEngine:
             self._iteration()
             self.launches_per_iter = ops.launch_count() - before
 
-    def run(self, every: int = 500, on_report=None):
-        """runs the loop; on_report(i) is called after iteration i whenever i % every == 0 (the reference's read-out
-        cadence) — the only points where the host looks at device values"""
+    def run(self, every: int = 500, on_report=None, report_offset: int = 0):
+        """runs the loop; on_report(i) is called after iteration i whenever (i + report_offset) % every == 0 (the
+        reference's read-out cadences: i % 500 == 0 in the shifted loops, count = i + 1 in LossFunction) — the only
+        points where the host looks at device values"""
         if self.iters <= 0:
             return
         if self.use_graph and self.graph is None:
@@ -592,7 +599,7 @@ class AutogradReconEngine:
         self._t0.record()
         for i in range(self.iters):
             self.step()
-            if on_report is not None and i % every == 0:
+            if on_report is not None and (i + report_offset) % every == 0:
                 on_report(i)
         self._t1.record()
 

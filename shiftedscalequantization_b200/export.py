@@ -78,6 +78,11 @@ def export_int_weights(model: torch.nn.Module) -> Dict[str, dict]:
                  "qmin": float(qmin), "n_bits": int(q.n_bits), "shape": tuple(w.shape)}
         if in_scale is not None:
             entry["in_scale"] = in_scale.detach().clone()
+        # the layer's output affine gamma^z / varphi^z (quant_layer.py:258-259) is part of what the layer computes once
+        # bias_cal has trained it; identity (1, 0) is left out
+        if not m._output_affine_is_identity():
+            entry["out_scale"] = m.alpha_out.detach().reshape(-1).clone()
+            entry["out_offset"] = m.beta_out.detach().reshape(-1).clone()
         out[name] = entry
     return out
 
@@ -92,7 +97,9 @@ def dequantize(entry: dict) -> torch.Tensor:
 @torch.no_grad()
 def import_int_weights(model: torch.nn.Module, blob: Dict[str, dict], strict: bool = True) -> int:
     """write the dequantised weights into the matching Conv2d / Linear / QuantModule `.weight` of `model`
-    (a float model then computes what the quantised model computed). Returns the number of layers written."""
+    (a float model then computes what the quantised model computed). A trained output affine (bias_cal) is restored into
+    alpha_out / beta_out of a QuantModule target, and folded into weight and bias of a plain Conv2d / Linear target
+    (W <- gamma_oc W, b <- gamma b + varphi: equal up to fp32 rounding). Returns the number of layers written."""
     if blob.get("__format__") != FORMAT:
         raise ops._lib.SsqError("not an ssq integer export")
     mods = dict(model.named_modules())
@@ -108,9 +115,21 @@ def import_int_weights(model: torch.nn.Module, blob: Dict[str, dict], strict: bo
         wq = dequantize(entry)
         if tuple(m.weight.shape) != tuple(wq.shape):
             raise ops._lib.SsqError(f"{name}: shape {tuple(m.weight.shape)} vs exported {tuple(wq.shape)}")
-        m.weight.data.copy_(wq)
+        a, b = entry.get("out_scale"), entry.get("out_offset")
         if isinstance(m, QuantModule):
+            m.weight.data.copy_(wq)
             m.org_weight.copy_(wq)
+            if a is not None:
+                m.alpha_out.data.copy_(a.view_as(m.alpha_out)); m.beta_out.data.copy_(b.view_as(m.beta_out))
+                m._affine_key = None
+        else:
+            if a is not None:
+                wq = wq * a.view((-1,) + (1,) * (wq.dim() - 1))
+                if m.bias is None:
+                    m.bias = torch.nn.Parameter(b.clone())
+                else:
+                    m.bias.data.copy_(m.bias.data * a + b)
+            m.weight.data.copy_(wq)
         n += 1
     return n
 

@@ -43,7 +43,7 @@ def _run_with_output_affine(unit, modules, cached_inps, cached_outs, *, iters, w
         print('Total loss:\t{:.3f} (rec:{:.3f}, round:{:.3f})\tb={:.2f}\tcount={}'.format(rec + rnd, rec, rnd, float(eng.live[0]), count))
 
     try:
-        eng.run(every=500, on_report=lambda i: report(i) if i > 0 else None)
+        eng.run(every=500, on_report=report, report_offset=1)      # count % 500 == 0, as upstream's LossFunction (:176)
     finally:
         eng.close()
         for m in modules:
@@ -74,23 +74,29 @@ def reconstruct_unit(model, unit, cali_data, *, is_block, batch_size, iters, wei
             act_quantizers.append(unit.act_quantizer)
         act_quantizers += [m.act_quantizer for m in modules if m.act_quantizer.delta is not None]
 
+    if not eval:
+        # host_resident = upstream's keep_gpu=False: the caches never exist on the device as a whole (data_utils.py:34-36)
+        keep_gpu = not host_resident
+        device = next(model.parameters()).device
+        cached_inps, cached_outs = save_inp_oup_data(model, unit, cali_data, asym, act_quant, batch_size, keep_gpu=keep_gpu)
+        cached_grads = save_grad_data(model, unit, cali_data, act_quant, batch_size=batch_size, keep_gpu=keep_gpu) \
+            if opt_mode != 'mse' else None
     if iters > 0:
-        cached_inps, cached_outs = save_inp_oup_data(model, unit, cali_data, asym, act_quant, batch_size)
-        cached_grads = save_grad_data(model, unit, cali_data, act_quant, batch_size=batch_size) if opt_mode != 'mse' else None
         if bias_cal and not act_quant:
             if opt_mode != 'mse':
                 raise NotImplementedError('bias_cal is defined for the mse reconstruction loss')
-            _run_with_output_affine(unit, modules, cached_inps, cached_outs, iters=iters, weight=weight, b_range=b_range,
+            _run_with_output_affine(unit, modules, cached_inps.to(device), cached_outs.to(device), iters=iters, weight=weight, b_range=b_range,
                                     warmup=warmup, p=p, batch_size=batch_size, multi_gpu=multi_gpu)
         else:
             engine = ReconEngine(unit, modules, cached_inps, cached_outs, cached_grads, act_quant=act_quant, iters=iters,
                                  weight=weight, b_range=b_range, warmup=warmup, p=p, lr=lr, opt_mode=opt_mode,
                                  batch_size=batch_size, multi_gpu=multi_gpu, act_quantizers=act_quantizers, scaling=scaling,
-                                 host_resident=host_resident)
+                                 host_resident=host_resident, device=device)
             try:
                 engine.run()
             finally:
                 engine.close()
+    if not eval:
         del cached_inps, cached_outs, cached_grads
         torch.cuda.empty_cache()
 

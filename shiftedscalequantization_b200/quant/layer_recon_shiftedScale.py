@@ -206,7 +206,8 @@ def _run_loop(unit, loss_func, optimizer, scheduler, cached_inp, cached_out, ite
 def _probe(unit, loss_func, optimizer, cached_inp, cached_out, batch_size):
     """reconstruction loss on the first batch (the 'Soft Round' / 'Hard Round' read-outs, upstream :97-121)"""
     optimizer.zero_grad()
-    loss_func(unit(cached_inp[:batch_size]), cached_out[:batch_size])
+    with torch.no_grad():                   # a read-out: upstream builds (and drops) an autograd graph here
+        loss_func(unit(cached_inp[:batch_size]), cached_out[:batch_size])
     return loss_func.rec_loss
 
 

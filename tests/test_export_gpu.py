@@ -157,3 +157,38 @@ def test_export_shifted_modes():
         packed = ops.export_codes(m.weight.detach(), d_code.contiguous(), zp.detach(), qmin, qmax, q.n_bits, alpha=beta.detach())
         y = ops.import_codes(packed, m.weight.shape, d_deq.contiguous(), zp.detach(), qmin, q.n_bits)
         assert torch.equal(y, q(m.weight)), m.pathName
+
+
+def test_export_carries_the_trained_output_affine():
+    """bias_cal trains alpha_out / beta_out (gamma^z, varphi^z); the export must carry them: a QuantModule target gets
+    them back exactly, a plain float model gets them folded into weight and bias (equal up to fp32 rounding)"""
+    from test_recon_gpu import build_qnn
+    from shiftedscalequantization_b200 import export as E, zoo
+    Q, qnn, cali = build_qnn()
+    block = qnn.model.layer1[0]
+    Q.block_reconstruction(qnn, block, cali_data=cali, iters=20, weight=0.01, asym=True, b_range=(20, 2), warmup=0.2,
+                           act_quant=False, opt_mode='mse', batch_size=16, bias_cal=True)
+    assert not block.conv1._output_affine_is_identity()
+    qnn.set_quant_state(True, False)
+    x = cali[:8].cuda()
+    with torch.no_grad():
+        ref = qnn(x)
+    blob = E.export_int_weights(qnn)
+    assert "out_scale" in blob["model.layer1.0.conv1"] and "out_scale" not in blob["model.layer2.0.conv1"]
+    # (a) back into a fresh QuantModel of the same network: exact
+    torch.manual_seed(1005)
+    Q2, qnn2, _ = build_qnn()
+    E.import_int_weights(qnn2, blob)
+    qnn2.set_quant_state(False, False)
+    with torch.no_grad():
+        assert torch.equal(qnn2(x), ref)
+    # (b) into a plain float network (BN folded the same way): affine folded into weight / bias
+    torch.manual_seed(1005)
+    from shiftedscalequantization_b200.quant.fold_bn import search_fold_and_remove_bn
+    cnn = zoo.resnet18().cuda().eval()
+    search_fold_and_remove_bn(cnn)
+    wrapper = torch.nn.Module(); wrapper.model = cnn
+    E.import_int_weights(wrapper, blob)
+    with torch.no_grad():
+        out = cnn(x)
+    assert torch.allclose(out, ref, rtol=1e-4, atol=1e-4 * float(ref.abs().max()))

@@ -282,3 +282,60 @@ def test_channelquantact_adaround_mode():
     assert_close(host(y), y_ref, what="'adaround' mode, soft rounding vs oracle")
     gb_ref = O.adaround_backward(host(gy), g["x"], g["beta"], np.float32(d), np.float32(z), 0, 15)
     assert_close(host(q.beta.grad), gb_ref, what="d/d beta vs oracle")
+
+
+# ------------------------------------------------------------------------------------------------ feature capture
+@pytest.mark.parametrize("act_quant", [False, True])
+def test_carried_capture_equals_capture_from_the_image(act_quant):
+    """the quantised input and the FP output of every unit carried forward from the previous unit's cached
+    tensors (one unit forward each per mini-batch) are bit-identical to the reference's two prefix forwards per mini-batch —
+    through a sequential calibration of ResNet-18 (stem, 8 blocks, average-pool + flatten into fc), weight phase and
+    activation phase"""
+    from test_recon_gpu import build_qnn
+    from shiftedscalequantization_b200.quant import data_utils as DU
+    Q, qnn, cali = build_qnn(n_cali=64)
+    if act_quant:
+        qnn.set_quant_state(True, True)
+        with torch.no_grad():
+            qnn(cali[:32].cuda())
+        qnn.disable_network_output_quantization()
+    units = [qnn.model.conv1] + [b for l in (qnn.model.layer1, qnn.model.layer2, qnn.model.layer3, qnn.model.layer4) for b in l] + [qnn.model.fc]
+    kw = dict(iters=8, weight=0.01, asym=True, b_range=(20, 2), warmup=0.2, act_quant=act_quant, opt_mode='mse', batch_size=16,
+              lr=4e-4, p=2.4 if act_quant else 2.0)
+    for i, u in enumerate(units):
+        qnn.set_quant_state(False, False); u.set_quant_state(True, act_quant)
+        ci, co = DU.save_inp_oup_data(qnn, u, cali, True, act_quant, 16)
+        mode = DU.capture_stats(qnn).last_mode
+        assert mode == ('from_image' if i == 0 else 'carried'), (i, mode)
+        DU.reset_capture(qnn, enabled=False)
+        ri, ro = DU.save_inp_oup_data(qnn, u, cali, True, act_quant, 16)
+        DU.reset_capture(qnn, enabled=True)
+        assert torch.equal(ci, ri) and torch.equal(co, ro), f"unit {i}"
+        # put the frontier back (the comparison run cleared it), then calibrate the unit as a real run would
+        DU._plan(qnn)["frontier"] = DU._Frontier(u, ci, co, DU._cali_key(cali, 16, True, act_quant))
+        if i in (1, 2):                                        # a real reconstruction in between, on two of the blocks
+            Q.block_reconstruction(qnn, u, cali_data=cali, **kw)
+
+
+def test_public_api_uses_the_carried_capture_and_host_resident_frees_the_device():
+    """block_reconstruction over consecutive units takes the carried path; host_resident=True (upstream keep_gpu=False) keeps
+    the caches in pinned host memory only — peak device memory drops by about the cache size"""
+    from test_recon_gpu import build_qnn
+    from shiftedscalequantization_b200.quant import data_utils as DU
+    kw = dict(iters=8, weight=0.01, asym=True, b_range=(20, 2), warmup=0.2, act_quant=False, opt_mode='mse', batch_size=16)
+    peaks = {}
+    alphas = {}
+    for host in (False, True):
+        Q, qnn, cali = build_qnn(n_cali=256, res=64)
+        torch.cuda.synchronize(); torch.cuda.empty_cache(); torch.cuda.reset_peak_memory_stats()
+        base = torch.cuda.memory_allocated()
+        torch.manual_seed(5)
+        for u in (qnn.model.layer1[0], qnn.model.layer1[1], qnn.model.layer2[0]):
+            Q.block_reconstruction(qnn, u, cali_data=cali, host_resident=host, **kw)
+        peaks[host] = torch.cuda.max_memory_allocated() - base
+        st = DU.capture_stats(qnn)
+        assert st.carried == 2 and st.from_image == 1, (st.carried, st.from_image)
+        alphas[host] = qnn.model.layer2[0].conv1.weight_quantizer.alpha.detach().clone()
+    cache_bytes = 256 * 64 * 16 * 16 * 4 * 2                   # layer1.x: inputs + outputs of 256 images
+    assert peaks[True] < peaks[False] - 0.5 * cache_bytes, peaks
+    assert torch.equal(alphas[True], alphas[False])            # same trajectory either way
