@@ -97,9 +97,9 @@ def dequantize(entry: dict) -> torch.Tensor:
 @torch.no_grad()
 def import_int_weights(model: torch.nn.Module, blob: Dict[str, dict], strict: bool = True) -> int:
     """write the dequantised weights into the matching Conv2d / Linear / QuantModule `.weight` of `model`
-    (a float model then computes what the quantised model computed). A trained output affine (bias_cal) is restored into
-    alpha_out / beta_out of a QuantModule target, and folded into weight and bias of a plain Conv2d / Linear target
-    (W <- gamma_oc W, b <- gamma b + varphi: equal up to fp32 rounding). Returns the number of layers written."""
+    (a float model then computes what the quantised model computed; for a QuantModule that is its quantiser-off path). A
+    trained output affine (bias_cal) is folded into weight and bias (W <- gamma_oc W, b <- gamma b + varphi: equal to the
+    quantised forward up to fp32 rounding; bit-exact when the affine is the identity). Returns the number of layers written."""
     if blob.get("__format__") != FORMAT:
         raise ops._lib.SsqError("not an ssq integer export")
     mods = dict(model.named_modules())
@@ -116,20 +116,22 @@ def import_int_weights(model: torch.nn.Module, blob: Dict[str, dict], strict: bo
         if tuple(m.weight.shape) != tuple(wq.shape):
             raise ops._lib.SsqError(f"{name}: shape {tuple(m.weight.shape)} vs exported {tuple(wq.shape)}")
         a, b = entry.get("out_scale"), entry.get("out_offset")
-        if isinstance(m, QuantModule):
-            m.weight.data.copy_(wq)
+        bias = m.bias.data if getattr(m, "bias", None) is not None else None
+        if a is not None:                   # fold gamma^z / varphi^z: (conv(x, W) + bias) * a + b == conv(x, a W) + (a bias + b)
+            wq = wq * a.view((-1,) + (1,) * (wq.dim() - 1))
+            bias = b.clone() if bias is None else bias * a + b
+            if m.bias is None:
+                m.bias = torch.nn.Parameter(bias.clone())
+            else:
+                m.bias.data.copy_(bias)
+        m.weight.data.copy_(wq)
+        if isinstance(m, QuantModule):      # the FP path of a QuantModule reads org_weight / org_bias
             m.org_weight.copy_(wq)
             if a is not None:
-                m.alpha_out.data.copy_(a.view_as(m.alpha_out)); m.beta_out.data.copy_(b.view_as(m.beta_out))
-                m._affine_key = None
-        else:
-            if a is not None:
-                wq = wq * a.view((-1,) + (1,) * (wq.dim() - 1))
-                if m.bias is None:
-                    m.bias = torch.nn.Parameter(b.clone())
+                if m.org_bias is None:
+                    m.org_bias = bias.clone()
                 else:
-                    m.bias.data.copy_(m.bias.data * a + b)
-            m.weight.data.copy_(wq)
+                    m.org_bias.copy_(bias)
         n += 1
     return n
 

@@ -161,34 +161,44 @@ def hard_codes(m):
     return torch.clamp(x + q.zero_point, 0, q.n_levels - 1).to(torch.uint8)
 
 
+def _long_horizon_run(BR, layer_reconstruction, iters):
+    qnn, cali = build("resnet18", 2, 32, 64)
+    kw = dict(cali_data=cali, iters=iters, weight=0.01, asym=True, b_range=(20, 2), warmup=0.2, act_quant=False,
+              opt_mode='mse', batch_size=32)
+    block = qnn.model.layer1[0]
+    t0 = time.time()
+    torch.manual_seed(377)
+    BR.block_reconstruction(qnn, block, **kw)
+    t_block = time.time() - t0
+    t0 = time.time()
+    torch.manual_seed(378)
+    layer_reconstruction(qnn, qnn.model.fc, **kw)
+    t_fc = time.time() - t0
+    return qnn, cali, {"block.conv1": block.conv1, "block.conv2": block.conv2, "fc": qnn.model.fc}, (t_block, t_fc)
+
+
 def gen_long_horizon():
     BR = _patched_block_recon()
     from quant import layer_reconstruction
     out = {}
     for iters in (2000, 20000):
-        qnn, cali = build("resnet18", 2, 32, 64)
+        qnn, cali, mods, secs = _long_horizon_run(BR, layer_reconstruction, iters)
         if "cali_probe" not in out:
             out["cali_probe"] = npy(cali.reshape(-1)[:64])
             out["probe.conv1_w"] = npy(qnn.model.conv1.org_weight[:4])
-        kw = dict(cali_data=cali, iters=iters, weight=0.01, asym=True, b_range=(20, 2), warmup=0.2, act_quant=False,
-                  opt_mode='mse', batch_size=32)
-        block = qnn.model.layer1[0]
-        t0 = time.time()
-        torch.manual_seed(377)
-        BR.block_reconstruction(qnn, block, **kw)
-        t_block = time.time() - t0
-        for n, m in (("conv1", block.conv1), ("conv2", block.conv2)):
-            out[f"i{iters}.block.{n}.alpha16"] = npy(m.weight_quantizer.alpha).astype(np.float16)
-            out[f"i{iters}.block.{n}.codes"] = npy(hard_codes(m))
-        t0 = time.time()
-        torch.manual_seed(378)
-        layer_reconstruction(qnn, qnn.model.fc, **kw)
-        t_fc = time.time() - t0
-        fc = qnn.model.fc
-        out[f"i{iters}.fc.alpha16"] = npy(fc.weight_quantizer.alpha).astype(np.float16)
-        out[f"i{iters}.fc.codes"] = npy(hard_codes(fc))
-        out[f"i{iters}.cpu_seconds"] = np.array([t_block, t_fc])
-        print(f"iters={iters}: block {t_block:.1f}s fc {t_fc:.1f}s", flush=True)
+        for n, m in mods.items():
+            out[f"i{iters}.{n}.alpha16"] = npy(m.weight_quantizer.alpha).astype(np.float16)
+            out[f"i{iters}.{n}.codes"] = npy(hard_codes(m))
+        out[f"i{iters}.cpu_seconds"] = np.array(secs)
+        print(f"iters={iters}: block {secs[0]:.1f}s fc {secs[1]:.1f}s", flush=True)
+        # the reference against ITSELF with another convolution backend (oneDNN off -> ATen's native CPU kernels): the same
+        # last-bit differences a cuDNN run has, i.e. the noise floor of any code-agreement figure at this horizon
+        with torch.backends.mkldnn.flags(enabled=False):
+            _q2, _c2, mods2, _ = _long_horizon_run(BR, layer_reconstruction, iters)
+        for n, m in mods2.items():
+            same = npy(hard_codes(m)) == out[f"i{iters}.{n}.codes"]
+            out[f"i{iters}.{n}.self_agreement"] = np.array(float(same.mean()))
+            print(f"  reference vs reference (native conv backend) {n}: {same.mean():.6f}", flush=True)
     save("long_horizon", **out)
 
 

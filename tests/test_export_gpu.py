@@ -160,8 +160,8 @@ def test_export_shifted_modes():
 
 
 def test_export_carries_the_trained_output_affine():
-    """bias_cal trains alpha_out / beta_out (gamma^z, varphi^z); the export must carry them: a QuantModule target gets
-    them back exactly, a plain float model gets them folded into weight and bias (equal up to fp32 rounding)"""
+    """bias_cal trains alpha_out / beta_out (gamma^z, varphi^z); the export must carry them: the import folds them into
+    weight and bias of the target (QuantModule FP path or plain float model; equal up to fp32 rounding)"""
     from test_recon_gpu import build_qnn
     from shiftedscalequantization_b200 import export as E, zoo
     Q, qnn, cali = build_qnn()
@@ -175,13 +175,13 @@ def test_export_carries_the_trained_output_affine():
         ref = qnn(x)
     blob = E.export_int_weights(qnn)
     assert "out_scale" in blob["model.layer1.0.conv1"] and "out_scale" not in blob["model.layer2.0.conv1"]
-    # (a) back into a fresh QuantModel of the same network: exact
-    torch.manual_seed(1005)
+    # (a) back into a fresh QuantModel of the same network, quantisers off: the affine is folded into org_weight / org_bias
     Q2, qnn2, _ = build_qnn()
     E.import_int_weights(qnn2, blob)
     qnn2.set_quant_state(False, False)
     with torch.no_grad():
-        assert torch.equal(qnn2(x), ref)
+        out2 = qnn2(x)
+    assert torch.allclose(out2, ref, rtol=1e-4, atol=1e-4 * float(ref.abs().max()))
     # (b) into a plain float network (BN folded the same way): affine folded into weight / bias
     torch.manual_seed(1005)
     from shiftedscalequantization_b200.quant.fold_bn import search_fold_and_remove_bn

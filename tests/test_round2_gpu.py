@@ -317,7 +317,7 @@ def test_carried_capture_equals_capture_from_the_image(act_quant):
             Q.block_reconstruction(qnn, u, cali_data=cali, **kw)
 
 
-def test_public_api_uses_the_carried_capture_and_host_resident_frees_the_device():
+def test_public_api_uses_the_carried_capture_and_host_resident_frees_the_device(monkeypatch):
     """block_reconstruction over consecutive units takes the carried path; host_resident=True (upstream keep_gpu=False) keeps
     the caches in pinned host memory only — peak device memory drops by about the cache size"""
     from test_recon_gpu import build_qnn
@@ -325,6 +325,7 @@ def test_public_api_uses_the_carried_capture_and_host_resident_frees_the_device(
     kw = dict(iters=8, weight=0.01, asym=True, b_range=(20, 2), warmup=0.2, act_quant=False, opt_mode='mse', batch_size=16)
     peaks = {}
     alphas = {}
+    monkeypatch.setattr(torch.backends.cudnn, "deterministic", True)    # as the reference's drivers (common.py:84-85): no atomics in wgrad
     for host in (False, True):
         Q, qnn, cali = build_qnn(n_cali=256, res=64)
         torch.cuda.synchronize(); torch.cuda.empty_cache(); torch.cuda.reset_peak_memory_stats()
