@@ -134,6 +134,43 @@ int ssq_fq_adaround_fwd_mt(const ssq_adaround_desc* table, int count, int64_t to
 int ssq_fq_adaround_bwd_mt(const ssq_adaround_desc* table, int count, int64_t total_tiles,
                            const float* b_dev, float lambda, void* stream);
 
+/* ---- one reconstruction iteration in three launches ----------------------------------------
+ * quant/block_recon.py:89-105 (randperm mini-batch :90-92, block forward :95, LossFunction :97,
+ * backward :99, optimizer.step :103) and the schedules it reads (LinearTempDecay :185-202,
+ * CosineAnnealingLR :72-73). Device-side iteration state: *step = iterations COMPLETED so far
+ * (only read during an iteration; the launch that applies Adam increments it when its last CTA
+ * retires), idx_table [n_steps, batch] = the reference's CPU torch.randperm(N)[:B] stream
+ * consumed up front, b_table / lr_table [n_steps]. Rows past n_steps-1 repeat the last row.
+ * ssq_iter_prologue  = bookkeeping (idx_live/b_live/lr_live <- row *step, for the kernels that
+ *   follow) + gather of the mini-batch's cached input rows (cache == NULL: skipped) + soft
+ *   forward of every quantised layer of the unit with the regulariser (count == 0: skipped).
+ *   Same arithmetic and the same fixed-order regulariser sum as ssq_fq_adaround_fwd_mt.
+ * ssq_fq_adaround_bwd_adam_mt = ssq_fq_adaround_bwd_mt + ssq_adam_step on the alphas it just
+ *   differentiated (flat/exp_avg/exp_avg_sq are the unit's flat buffers; every table[i].alpha
+ *   points into flat), t = *step + 1, then ends the iteration. store_grad != 0 also writes
+ *   table[i].galpha. Bit-identical to the two separate launches.
+ * ssq_adam_step_end_iteration = ssq_adam_step with t = *step + 1, then ends the iteration
+ *   (multi-GPU: after the all-reduce; activation phase). */
+typedef struct ssq_iter_state {
+    const int64_t* step;
+    const int64_t* idx_table;
+    int64_t* idx_live;        /* nullable */
+    const float* b_table;     /* nullable */
+    float* b_live;            /* nullable */
+    const float* lr_table;    /* nullable */
+    float* lr_live;           /* nullable */
+    int64_t n_steps;
+    int batch;
+} ssq_iter_state;
+int ssq_iter_prologue(const ssq_iter_state* st, const float* cache, float* cur_inp, int64_t per_sample,
+                      const ssq_adaround_desc* table, int count, int64_t total_tiles,
+                      float lambda, float* reg_out, void* ws, size_t ws_bytes, void* stream);
+int ssq_fq_adaround_bwd_adam_mt(const ssq_adaround_desc* table, int count, int64_t total_tiles,
+                                const float* b_dev, float lambda,
+                                float* flat, float* exp_avg, float* exp_avg_sq, const float* lr_dev,
+                                int64_t* step_dev, double beta1, double beta2, double eps, int store_grad,
+                                void* ws, size_t ws_bytes, void* stream);
+
 /* ---- K1c: shifted-scale ChannelQuant ------------------------------------------------
  * quant/channelQuant.py:49-127. Conv weights [OC,IC,kh,kw] (kk = kh*kw) carry one
  * group-probability row per INPUT channel: alpha [IC,S]; FC weights [OC,IC] carry one per
@@ -265,6 +302,30 @@ int ssq_chan_affine_bwd(const float* gy, const float* x, const float* a, float* 
 int ssq_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                   const float* lr_dev, double beta1, double beta2, double eps,
                   const int64_t* step_dev, void* stream);
+/* the same with t = *step_dev + 1 (step_dev = iterations completed), incrementing *step_dev when the last CTA retires */
+int ssq_adam_step_end_iteration(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                const float* lr_dev, double beta1, double beta2, double eps,
+                                int64_t* step_dev, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- the exchange step: gradient SUM over the ranks + Adam, one kernel over peer memory ----
+ * reference intent: link.allreduce(p.grad) for every optimised parameter, then optimizer.step
+ * (quant/block_recon.py:100-103). flat_ptrs[r] / grad_ptrs[r] / pad_ptrs[r] (HOST arrays of `world`
+ * DEVICE pointers) are rank r's parameter buffer, gradient buffer and flag pad in symmetric
+ * memory (same layout on every rank; pad = ssq_exchange_pad_bytes() zeroed bytes). Rank `rank`
+ * sums elements [rank*S, (rank+1)*S), S = ssq_exchange_shard_elems(n, world), of all gradient
+ * buffers in rank order, applies Adam (t = *step_dev + 1) to that shard — exp_avg_shard /
+ * exp_avg_sq_shard hold S floats — and stores the new parameters into EVERY rank's parameter
+ * buffer; then it ends the iteration (*step_dev += 1). n must be a multiple of 4. Every rank must
+ * launch it with the same n and world. reduced_shard_out (nullable): the summed gradient shard.
+ * *timeouts is incremented if a peer does not arrive within ~2^25 polls (results are then
+ * undefined; the caller raises instead of hanging the device). */
+size_t ssq_exchange_pad_bytes(void);
+int64_t ssq_exchange_shard_elems(int64_t n, int world);
+int ssq_grad_exchange_adam(float* const* flat_ptrs, const float* const* grad_ptrs, uint32_t* const* pad_ptrs,
+                           int rank, int world, int64_t n,
+                           float* exp_avg_shard, float* exp_avg_sq_shard,
+                           const float* lr_dev, int64_t* step_dev, double beta1, double beta2, double eps,
+                           float* reduced_shard_out, unsigned int* timeouts, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- calibration loop plumbing -----------------------------------------------------------
  * gather rows of a cached feature tensor: dst[n] = src[index[n]] (quant/block_recon.py:91) */

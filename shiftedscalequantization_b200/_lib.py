@@ -35,6 +35,14 @@ class AdaRoundDesc(C.Structure):
     ]
 
 
+class IterState(C.Structure):
+    """mirror of ssq_iter_state"""
+    _fields_ = [
+        ("step", _p), ("idx_table", _p), ("idx_live", _p), ("b_table", _p), ("b_live", _p),
+        ("lr_table", _p), ("lr_live", _p), ("n_steps", _i64), ("batch", _i32),
+    ]
+
+
 # name -> (restype, argtypes); must list every function of include/ssq_b200.h
 PROTOTYPES = {
     "ssq_abi_version": (_i32, []),
@@ -66,6 +74,12 @@ PROTOTYPES = {
     "ssq_chan_affine_fwd": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _p]),
     "ssq_chan_affine_bwd": (_i32, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p, _sz, _p]),
     "ssq_adam_step": (_i32, [_p, _p, _p, _p, _i64, _p, _d, _d, _d, _p, _p]),
+    "ssq_adam_step_end_iteration": (_i32, [_p, _p, _p, _p, _i64, _p, _d, _d, _d, _p, _p, _sz, _p]),
+    "ssq_iter_prologue": (_i32, [C.POINTER(IterState), _p, _p, _i64, C.POINTER(AdaRoundDesc), _i32, _i64, _f, _p, _p, _sz, _p]),
+    "ssq_fq_adaround_bwd_adam_mt": (_i32, [C.POINTER(AdaRoundDesc), _i32, _i64, _p, _f, _p, _p, _p, _p, _p, _d, _d, _d, _i32, _p, _sz, _p]),
+    "ssq_exchange_pad_bytes": (_sz, []),
+    "ssq_exchange_shard_elems": (_i64, [_i64, _i32]),
+    "ssq_grad_exchange_adam": (_i32, [_p, _p, _p, _i32, _i32, _i64, _p, _p, _p, _p, _d, _d, _d, _p, _p, _p, _sz, _p]),
     "ssq_gather_rows": (_i32, [_p, _p, _p, _i64, _i64, _p]),
     "ssq_packed_row_bytes": (_i64, [_i64, _i32]),
     "ssq_export_codes": (_i32, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _f, _f, _i32, _p]),

@@ -15,7 +15,7 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = CSRC / "libssq_b200.so"
 STAMP = CSRC / ".libssq_b200.stamp"
-SOURCES = ["fq_affine.cu", "fq_adaround.cu", "fq_shift.cu", "scale_search.cu", "recon_loss.cu", "loop.cu", "export_codes.cu"]
+SOURCES = ["fq_affine.cu", "fq_adaround.cu", "fq_shift.cu", "scale_search.cu", "recon_loss.cu", "loop.cu", "export_codes.cu", "exchange.cu"]
 HEADERS = [CSRC / "ssq_common.cuh", CSRC / "ssq_fastdiv.h", CSRC / "ssq_slab_plan.h", PKG_DIR.parent / "include" / "ssq_b200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -330,6 +330,204 @@ ada_bwd_mt_kernel(const __grid_constant__ MtTable table, int count, int64_t tota
     }
 }
 
+// ---- one reconstruction iteration in three launches -------------------------------------------------------
+// (quant/block_recon.py:89-105). Launch 1 = this prologue: the iteration's bookkeeping (mini-batch row of the index table,
+// temperature b, learning rate — all read through the device iteration counter), the gather of the mini-batch's cached input
+// rows, and the soft forward of every quantised layer of the unit + the regulariser. The counter `*step` = iterations completed
+// so far is only READ during an iteration; the fused Adam of launch 3 (or ssq_adam_step_ex) increments it when its last CTA
+// retires. CTAs [0, gather_tiles) copy rows, CTAs [gather_tiles, gather_tiles + ada_ctas) walk the AdaRound tiles.
+struct IterState {
+    const int64_t* step; const int64_t* idx_table; int64_t* idx_live;
+    const float* b_table; float* b_live; const float* lr_table; float* lr_live;
+    int64_t n_steps; int batch;
+};
+__device__ __forceinline__ int64_t iter_row(const IterState& S) {
+    int64_t s = *S.step;
+    if (s >= S.n_steps) s = S.n_steps - 1;          // replays past the schedule keep the last row
+    return s < 0 ? 0 : s;
+}
+
+__global__ void __launch_bounds__(SSQ_THREADS, 4)
+iter_prologue_kernel(const __grid_constant__ IterState S, const float* __restrict__ cache, float* __restrict__ cur,
+                     int64_t per_sample, int gather_tiles, bool gvec,
+                     const __grid_constant__ MtTable table, int count, int64_t total_tiles, int ada_ctas,
+                     float lambda, float* __restrict__ reg_out, WsView ws) {
+    __shared__ double smem[32];
+    __shared__ int s_which;
+    const int64_t s = iter_row(S);
+    if (blockIdx.x == 0) {                           // publish the live row for the kernels that follow
+        if (S.idx_live) for (int j = threadIdx.x; j < S.batch; j += blockDim.x) S.idx_live[j] = S.idx_table[s * S.batch + j];
+        if (threadIdx.x == 0) {
+            if (S.b_live) *S.b_live = S.b_table ? S.b_table[s] : 0.f;
+            if (S.lr_live && S.lr_table) *S.lr_live = S.lr_table[s];
+        }
+    }
+    if ((int)blockIdx.x < gather_tiles) {
+        constexpr int U = 4;
+        const int64_t* __restrict__ rows = S.idx_table + s * S.batch;
+        TileWalk tw;
+        const int64_t i0 = (int64_t)blockIdx.x * (SSQ_THREADS * U) + threadIdx.x;
+        if (gvec) {
+            const int64_t ps4 = per_sample >> 2, total4 = (int64_t)S.batch * ps4;
+            tw.init((uint64_t)i0, (uint64_t)ps4, (uint64_t)S.batch);
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t i = i0 + (int64_t)u * SSQ_THREADS;
+                if (i < total4) v[u] = ld_stream4(cache + (__ldg(rows + tw.c) * ps4 + tw.col) * 4);
+                tw.step(SSQ_THREADS);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t i = i0 + (int64_t)u * SSQ_THREADS;
+                if (i < total4) st_stream4(cur + i * 4, v[u]);
+            }
+        } else {
+            const int64_t total = (int64_t)S.batch * per_sample;
+            tw.init((uint64_t)i0, (uint64_t)per_sample, (uint64_t)S.batch);
+            for (int u = 0; u < U; ++u) {
+                const int64_t i = i0 + (int64_t)u * SSQ_THREADS;
+                if (i < total) cur[i] = cache[__ldg(rows + tw.c) * per_sample + tw.col];
+                tw.step(SSQ_THREADS);
+            }
+        }
+        return;
+    }
+    if (count == 0) return;
+    const int slot = (int)blockIdx.x - gather_tiles;
+    const float b = S.b_table ? S.b_table[s] : 0.f;
+    const bool reg_on = reg_out && (b > 0.f);
+    double acc[1] = {0.0};
+    for (int64_t tile = slot; tile < total_tiles; tile += ada_ctas) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_which = find_desc(table, count, tile);
+        __syncthreads();
+        const ssq_adaround_desc& D = table.d[s_which];
+        const int64_t e0 = (tile - D.tile_begin) * SSQ_MT_TILE;
+        const int64_t e1 = e0 + SSQ_MT_TILE < D.n ? e0 + SSQ_MT_TILE : D.n;
+        const bool vec = desc_vec(D, false);
+        acc[0] += reg_on ? ada_fwd_span<true, true>(D.w, D.alpha, D.delta, D.zero_point, D.wq, nullptr, e0, e1, D.inner, D.nchan,
+                                                    D.qmin, D.qmax, b, threadIdx.x, blockDim.x, vec)
+                         : ada_fwd_span<true, false>(D.w, D.alpha, D.delta, D.zero_point, D.wq, nullptr, e0, e1, D.inner, D.nchan,
+                                                     D.qmin, D.qmax, b, threadIdx.x, blockDim.x, vec);
+    }
+    if (!reg_out) return;
+    block_sum<1>(acc, smem);
+    if (grid_finish<1>(acc, ws, 0, slot, ada_ctas, smem) && threadIdx.x == 0)
+        reg_out[0] = reg_on ? (float)((double)lambda * acc[0]) : 0.f;
+}
+
+// Launch 3: gradient of every alpha (reconstruction + regulariser) AND its Adam step in one pass over (g_wq, w, alpha, m, v):
+// the gradient never goes to memory (unless galpha is wanted), torch.optim.Adam's arithmetic as in loop.cu. t = *step + 1;
+// the last CTA to retire increments *step.
+struct AdamArgs {
+    float* flat; float* m; float* v;               // alpha lives at flat + off, its moments at m + off, v + off
+    const float* lr; int64_t* step; unsigned int* ticket;
+    double beta1, beta2, eps;
+    int store_grad;
+};
+__global__ void __launch_bounds__(SSQ_THREADS)
+ada_bwd_adam_mt_kernel(const __grid_constant__ MtTable table, int count, int64_t total_tiles,
+                       const float* __restrict__ b_dev, float lambda, const __grid_constant__ AdamArgs A) {
+    __shared__ int s_which;
+    __shared__ float s_step_size, s_bc2_sqrt;
+    const float b = b_dev ? __ldg(b_dev) : 0.f;
+    const bool reg_on = b_dev && (b > 0.f);
+    const float lam_g = reg_on ? lambda : 0.f;
+    if (threadIdx.x == 0) {
+        const double t = (double)(*A.step + 1);
+        s_step_size = (float)((double)__ldg(A.lr) / (1.0 - pow(A.beta1, t)));
+        s_bc2_sqrt = (float)sqrt(1.0 - pow(A.beta2, t));
+    }
+    const float w1 = (float)(1.0 - A.beta1), w2 = (float)(1.0 - A.beta2), beta2 = (float)A.beta2, eps = (float)A.eps;
+    __syncthreads();
+    const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+    auto adam = [&](float& p, float g, float& mm, float& vv) {
+        mm = mm + w1 * (g - mm);
+        vv = vv * beta2 + w2 * g * g;
+        const float denom = sqrtf(vv) / bc2_sqrt + eps;
+        p = p - step_size * (mm / denom);
+    };
+    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_which = find_desc(table, count, tile);
+        __syncthreads();
+        const ssq_adaround_desc& D = table.d[s_which];
+        const int64_t e0 = (tile - D.tile_begin) * SSQ_MT_TILE;
+        const int64_t e1 = e0 + SSQ_MT_TILE < D.n ? e0 + SSQ_MT_TILE : D.n;
+        const int64_t off = D.alpha - A.flat;
+        float* __restrict__ pa = A.flat + off;
+        float* __restrict__ pm = A.m + off;
+        float* __restrict__ pv = A.v + off;
+        ChanWalk cw;
+        if (desc_vec(D, true) && aligned16(pm) && aligned16(pv)) {
+            const uint32_t n4 = (uint32_t)((e1 - e0) >> 2);
+            cw.init((uint64_t)(e0 >> 2) + threadIdx.x, blockDim.x, D.inner >> 2, D.nchan);
+            // 4 vectors per thread (SSQ_MT_TILE / 4 / SSQ_THREADS), loads of all of them issued first
+            constexpr int NV = SSQ_MT_TILE / 4 / SSQ_THREADS;
+            float4 wv[NV], av[NV], gv[NV], mv[NV], vv[NV];
+#pragma unroll
+            for (int u = 0; u < NV; ++u) {
+                const uint32_t j = threadIdx.x + u * SSQ_THREADS;
+                if (j < n4) {
+                    const int64_t e = e0 + 4 * (int64_t)j;
+                    wv[u] = ld_stream4(D.w + e); gv[u] = ld_stream4(D.gwq + e);
+                    av[u] = *reinterpret_cast<const float4*>(pa + e);
+                    mv[u] = *reinterpret_cast<const float4*>(pm + e);
+                    vv[u] = *reinterpret_cast<const float4*>(pv + e);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < NV; ++u) {
+                const uint32_t j = threadIdx.x + u * SSQ_THREADS;
+                if (j < n4) {
+                    const int64_t e = e0 + 4 * (int64_t)j;
+                    const Recip R = make_recip(__ldg(D.delta + cw.c));
+                    const float z = __ldg(D.zero_point + cw.c);
+                    const float4 t = div4_exact(wv[u], R);
+                    float4 g;
+                    if (reg_on) {
+                        g.x = ada_bwd_one<true, true>(gv[u].x, t.x, av[u].x, R, z, D.qmin, D.qmax, b, lam_g);
+                        g.y = ada_bwd_one<true, true>(gv[u].y, t.y, av[u].y, R, z, D.qmin, D.qmax, b, lam_g);
+                        g.z = ada_bwd_one<true, true>(gv[u].z, t.z, av[u].z, R, z, D.qmin, D.qmax, b, lam_g);
+                        g.w = ada_bwd_one<true, true>(gv[u].w, t.w, av[u].w, R, z, D.qmin, D.qmax, b, lam_g);
+                    } else {
+                        g.x = ada_bwd_one<true, false>(gv[u].x, t.x, av[u].x, R, z, D.qmin, D.qmax, b, lam_g);
+                        g.y = ada_bwd_one<true, false>(gv[u].y, t.y, av[u].y, R, z, D.qmin, D.qmax, b, lam_g);
+                        g.z = ada_bwd_one<true, false>(gv[u].z, t.z, av[u].z, R, z, D.qmin, D.qmax, b, lam_g);
+                        g.w = ada_bwd_one<true, false>(gv[u].w, t.w, av[u].w, R, z, D.qmin, D.qmax, b, lam_g);
+                    }
+                    if (A.store_grad) st_stream4(D.galpha + e, g);
+                    adam(av[u].x, g.x, mv[u].x, vv[u].x); adam(av[u].y, g.y, mv[u].y, vv[u].y);
+                    adam(av[u].z, g.z, mv[u].z, vv[u].z); adam(av[u].w, g.w, mv[u].w, vv[u].w);
+                    *reinterpret_cast<float4*>(pa + e) = av[u];
+                    *reinterpret_cast<float4*>(pm + e) = mv[u];
+                    *reinterpret_cast<float4*>(pv + e) = vv[u];
+                }
+                cw.next();
+            }
+        } else {
+            cw.init(e0 + threadIdx.x, blockDim.x, D.inner, D.nchan);
+            for (int64_t i = e0 + threadIdx.x; i < e1; i += blockDim.x) {
+                const Recip R = make_recip(__ldg(D.delta + cw.c));
+                const float z = __ldg(D.zero_point + cw.c);
+                const float u = div_exact(D.w[i], R);
+                const float g = reg_on ? ada_bwd_one<true, true>(D.gwq[i], u, pa[i], R, z, D.qmin, D.qmax, b, lam_g)
+                                       : ada_bwd_one<true, false>(D.gwq[i], u, pa[i], R, z, D.qmin, D.qmax, b, lam_g);
+                if (A.store_grad) D.galpha[i] = g;
+                adam(pa[i], g, pm[i], pv[i]);
+                cw.next();
+            }
+        }
+    }
+    // every CTA has read *step (thread 0, before the barrier above); the last one to arrive bumps it
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(A.ticket, 1u) == gridDim.x - 1) { *A.step = *A.step + 1; *A.ticket = 0u; __threadfence(); }
+    }
+}
+
 static inline int check_layout(int64_t n, int64_t inner, int64_t nchan) {
     if (n < 0 || inner <= 0 || nchan <= 0 || n % inner != 0 || (n / inner) % nchan != 0) return SSQ_ERR_SIZE;
     return SSQ_OK;
@@ -437,5 +635,53 @@ extern "C" int ssq_fq_adaround_bwd_mt(const ssq_adaround_desc* table, int count,
     MtTable t;
     for (int i = 0; i < count; ++i) t.d[i] = table[i];
     ada_bwd_mt_kernel<<<grid, SSQ_THREADS, 0, (cudaStream_t)stream>>>(t, count, total_tiles, b_dev, lambda);
+    return launch_status();
+}
+
+
+extern "C" int ssq_iter_prologue(const ssq_iter_state* st, const float* cache, float* cur_inp, int64_t per_sample,
+                                 const ssq_adaround_desc* table, int count, int64_t total_tiles,
+                                 float lambda, float* reg_out, void* ws, size_t ws_bytes, void* stream) {
+    if (!st || !st->step || !st->idx_table) return SSQ_ERR_NULL;
+    if (st->n_steps <= 0 || st->batch < 0 || count < 0 || count > SSQ_MT_MAX || total_tiles < 0 || per_sample < 0) return SSQ_ERR_SIZE;
+    if ((cache != nullptr) != (cur_inp != nullptr)) return SSQ_ERR_NULL;
+    if (count > 0 && !table) return SSQ_ERR_NULL;
+    if (reg_out && (!ws || ws_bytes < ssq_ws_bytes(1))) return SSQ_ERR_WORKSPACE;
+    if (reg_out && !st->b_table) return SSQ_ERR_MODE;
+    IterState S{st->step, st->idx_table, st->idx_live, st->b_table, st->b_live, st->lr_table, st->lr_live, st->n_steps, st->batch};
+    const bool gvec = cache && (per_sample % 4 == 0) && aligned16(cache) && aligned16(cur_inp);
+    int64_t gt = 0;
+    if (cache) {
+        const int64_t units = gvec ? (int64_t)st->batch * (per_sample >> 2) : (int64_t)st->batch * per_sample;
+        gt = (units + SSQ_THREADS * 4 - 1) / (SSQ_THREADS * 4);
+    }
+    if (gt > 0x3fffffff) return SSQ_ERR_SIZE;
+    const int ada_ctas = count > 0 ? (int)tile_grid(total_tiles, reg_out != nullptr) : 0;
+    int64_t grid = gt + ada_ctas;
+    if (grid < 1) grid = 1;
+    MtTable t;
+    for (int i = 0; i < count; ++i) t.d[i] = table[i];
+    iter_prologue_kernel<<<(unsigned)grid, SSQ_THREADS, 0, (cudaStream_t)stream>>>(S, cache, cur_inp, per_sample, (int)gt, gvec, t, count,
+                                                                                   total_tiles, ada_ctas, lambda, reg_out, ws_view(ws, 1));
+    return launch_status();
+}
+
+extern "C" int ssq_fq_adaround_bwd_adam_mt(const ssq_adaround_desc* table, int count, int64_t total_tiles,
+                                           const float* b_dev, float lambda,
+                                           float* flat, float* exp_avg, float* exp_avg_sq, const float* lr_dev,
+                                           int64_t* step_dev, double beta1, double beta2, double eps, int store_grad,
+                                           void* ws, size_t ws_bytes, void* stream) {
+    if (count == 0 || total_tiles == 0) return SSQ_OK;
+    if (!table || !flat || !exp_avg || !exp_avg_sq || !lr_dev || !step_dev) return SSQ_ERR_NULL;
+    if (count < 0 || count > SSQ_MT_MAX || total_tiles < 0) return SSQ_ERR_SIZE;
+    if (!ws || ws_bytes < ssq_ws_bytes(1)) return SSQ_ERR_WORKSPACE;
+    for (int i = 0; i < count; ++i) if (!table[i].gwq || (store_grad && !table[i].galpha)) return SSQ_ERR_NULL;
+    MtTable t;
+    for (int i = 0; i < count; ++i) t.d[i] = table[i];
+    // the last ticket of the fixed header is reserved for the iteration counter's hand-over
+    AdamArgs A{flat, exp_avg, exp_avg_sq, lr_dev, step_dev, reinterpret_cast<unsigned int*>(ws) + (SSQ_WS_TICKETS - 1),
+               beta1, beta2, eps, store_grad};
+    const unsigned grid = tile_grid(total_tiles, false);
+    ada_bwd_adam_mt_kernel<<<grid, SSQ_THREADS, 0, (cudaStream_t)stream>>>(t, count, total_tiles, b_dev, lambda, A);
     return launch_status();
 }

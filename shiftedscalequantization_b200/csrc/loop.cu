@@ -11,7 +11,7 @@ namespace ssq {
 __global__ void __launch_bounds__(SSQ_THREADS)
 adam_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,
             int64_t n, const float* __restrict__ lr_dev, double beta1d, double beta2d, double epsd,
-            const int64_t* __restrict__ step_dev) {
+            int64_t* step_dev, unsigned int* ticket /* nullable: non-null = *step_dev counts COMPLETED iterations */) {
     // Python-double scalars, cast to fp32 by ATen when they meet an fp32 tensor
     const float w1 = (float)(1.0 - beta1d);   // lerp weight (< 0.5 => m + w*(g-m))
     const float w2 = (float)(1.0 - beta2d);
@@ -37,7 +37,7 @@ adam_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __
     // evaluated by one thread per CTA while the tile's loads are in flight
     __shared__ float s_step_size, s_bc2_sqrt;
     if (threadIdx.x == 0) {
-        const double t = (double)(*step_dev);
+        const double t = (double)(*step_dev + (ticket ? 1 : 0));
         const double bc1 = 1.0 - pow(beta1d, t);
         const double bc2 = 1.0 - pow(beta2d, t);
         s_step_size = (float)((double)__ldg(lr_dev) / bc1);
@@ -65,6 +65,13 @@ adam_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __
     // tail (n % 4 elements, or everything when a pointer is not 16-byte aligned): grid-stride, scalar
     for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
         one(param[i], grad[i], m[i], v[i]);
+    if (ticket) {            // every CTA read *step_dev before the barrier above; the last one to retire ends the iteration
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(ticket, 1u) == gridDim.x - 1) { *step_dev = *step_dev + 1; *ticket = 0u; __threadfence(); }
+        }
+    }
 }
 
 __global__ void loop_advance_kernel(int64_t* step_dev, const int64_t* __restrict__ idx_table, int64_t* idx_live, int batch,
@@ -225,17 +232,32 @@ pull_rows_packed_kernel(const uint32_t* __restrict__ mask, const float* __restri
 
 using namespace ssq;
 
+static int adam_launch(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                       const float* lr_dev, double beta1, double beta2, double eps,
+                       int64_t* step_dev, unsigned int* ticket, void* stream) {
+    if (!param || !grad || !exp_avg || !exp_avg_sq || !lr_dev || !step_dev) return SSQ_ERR_NULL;
+    if (n < 0) return SSQ_ERR_SIZE;
+    const bool vec = aligned16(param) && aligned16(grad) && aligned16(exp_avg) && aligned16(exp_avg_sq);
+    unsigned grid = vec ? tile_grid(((n >> 2) + SSQ_THREADS * 2 - 1) / (SSQ_THREADS * 2), false)
+                        : (unsigned)grid_for((n + SSQ_THREADS - 1) / SSQ_THREADS);
+    if (grid < 1) grid = 1;
+    adam_kernel<<<grid, SSQ_THREADS, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr_dev, beta1, beta2, eps, step_dev, ticket);
+    return launch_status();
+}
+
 extern "C" int ssq_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                              const float* lr_dev, double beta1, double beta2, double eps,
                              const int64_t* step_dev, void* stream) {
     if (n == 0) return SSQ_OK;
-    if (!param || !grad || !exp_avg || !exp_avg_sq || !lr_dev || !step_dev) return SSQ_ERR_NULL;
-    if (n < 0) return SSQ_ERR_SIZE;
-    const bool vec = aligned16(param) && aligned16(grad) && aligned16(exp_avg) && aligned16(exp_avg_sq);
-    const unsigned grid = vec ? tile_grid(((n >> 2) + SSQ_THREADS * 2 - 1) / (SSQ_THREADS * 2), false)
-                              : (unsigned)grid_for((n + SSQ_THREADS - 1) / SSQ_THREADS);
-    adam_kernel<<<grid, SSQ_THREADS, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr_dev, beta1, beta2, eps, step_dev);
-    return launch_status();
+    return adam_launch(param, grad, exp_avg, exp_avg_sq, n, lr_dev, beta1, beta2, eps, const_cast<int64_t*>(step_dev), nullptr, stream);
+}
+
+extern "C" int ssq_adam_step_end_iteration(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                           const float* lr_dev, double beta1, double beta2, double eps,
+                                           int64_t* step_dev, void* ws, size_t ws_bytes, void* stream) {
+    if (!ws || ws_bytes < ssq_ws_bytes(1)) return SSQ_ERR_WORKSPACE;
+    return adam_launch(param, grad, exp_avg, exp_avg_sq, n, lr_dev, beta1, beta2, eps, step_dev,
+                       reinterpret_cast<unsigned int*>(ws) + (SSQ_WS_TICKETS - 1), stream);
 }
 
 extern "C" int ssq_loop_advance(int64_t* step_dev, const int64_t* idx_table, int64_t* idx_live, int batch,

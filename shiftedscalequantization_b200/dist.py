@@ -106,3 +106,60 @@ def all_gather_rows(local: torch.Tensor, n_total: int) -> torch.Tensor:
     out = [torch.empty_like(pad) for _ in range(w)]
     td.all_gather(out, pad)
     return torch.cat([o[:hi - lo] for o, (lo, hi) in zip(out, sizes)])
+
+
+# ------------------------------------------------------------------------------------------- symmetric memory
+EXCHANGE = os.environ.get("SSQ_EXCHANGE", "p2p")     # "p2p": the fused peer-memory kernel (csrc/exchange.cu); "nccl": all-reduce + Adam
+
+
+class SymmetricUnit:
+    """The flat parameter / gradient buffers of one reconstruction unit in symmetric memory, plus the flag pad the
+    exchange kernel synchronises through: one allocation per rank at the same offset everywhere, peer pointers exchanged
+    once (torch.distributed._symmetric_memory — plumbing only; the data path is ssq_grad_exchange_adam)."""
+
+    def __init__(self, n_floats: int, device: torch.device):
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        lib = _lib.load()
+        self.n = int(n_floats)
+        assert self.n % 4 == 0
+        pad_floats = int(lib.ssq_exchange_pad_bytes()) // 4
+        self.world, self.rank = world_size(), rank()
+        total = 2 * self.n + pad_floats
+        self.buf = symm.empty(total, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        torch.cuda.synchronize(device)
+        self.handle = symm.rendezvous(self.buf, td.group.WORLD)
+        self.flat = self.buf[:self.n]
+        self.gflat = self.buf[self.n:2 * self.n]
+        bases = [self.handle.get_buffer(r, (total,), torch.float32, 0).data_ptr() for r in range(self.world)]
+        import ctypes as C
+        arr = C.c_void_p * self.world
+        self.flat_ptrs = arr(*bases)
+        self.grad_ptrs = arr(*[b + 4 * self.n for b in bases])
+        self.pad_ptrs = arr(*[b + 8 * self.n for b in bases])
+        self.shard = int(lib.ssq_exchange_shard_elems(self.n, self.world))
+        self.timeouts = torch.zeros(1, dtype=torch.int32, device=device)
+        td.barrier()                                   # every rank has zeroed its pad before anybody polls it
+
+    def check(self):
+        """raise if a rendezvous of the exchange kernel ever timed out (one device read; call after a run)"""
+        if int(self.timeouts) != 0:
+            raise RuntimeError("gradient exchange: a peer rank did not arrive at a rendezvous (results are invalid)")
+
+
+def symmetric_unit_or_none(n_floats: int, device: torch.device):
+    """a SymmetricUnit when the peer-memory exchange is selected AND available on every rank, else None (NCCL path)"""
+    if world_size() <= 1 or EXCHANGE != "p2p":
+        return None
+    unit, ok = None, 1
+    try:
+        unit = SymmetricUnit(n_floats, device)
+    except Exception as e:             # symmetric memory unsupported here (no P2P, fabric handles unavailable, ...)
+        ok = 0
+        if rank() == 0:
+            import sys
+            print(f"[ssq] symmetric memory unavailable ({type(e).__name__}: {e}); the gradient exchange uses NCCL", file=sys.stderr)
+    flag = torch.tensor([ok], dtype=torch.int32, device=device)
+    td.all_reduce(flag, op=td.ReduceOp.MIN)
+    return unit if int(flag) == 1 else None

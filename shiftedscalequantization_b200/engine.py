@@ -10,8 +10,10 @@ re-designed for B200:
   * the reconstruction loss reads the cached FP outputs in place through the index (no gathered copy), writes
     d(loss)/d(pred) in the same pass, and the regulariser and its gradient ride inside the fake-quant kernels.
 
-Per-iteration launches of ours (weight phase): loop_advance, gather_rows, adaround_fwd_mt, recon_loss,
-adaround_bwd_mt, adam_step = 6, against ~530 ATen dispatches upstream.
+Per-iteration launches of ours (weight phase, one GPU): iter_prologue (schedules + mini-batch gather + all layers' soft
+weights + regulariser), recon_loss (+ dpred), adaround_bwd_adam_mt (alpha gradients + Adam + end of iteration) = 3, against
+~530 ATen dispatches upstream. With several GPUs the last one splits into adaround_bwd_mt, the gradient
+exchange and adam_step_end_iteration.
 """
 from __future__ import annotations
 
@@ -104,6 +106,7 @@ class ReconEngine:
         once, so the summed gradient equals the single-GPU gradient up to summation order and the trajectory is the
         1-GPU trajectory."""
         self.unit, self.modules = unit, list(modules)
+        self.sym = None
         self.host_resident = bool(host_resident)
         if scaling not in ('weak', 'strong'):
             raise ValueError('scaling must be "weak" or "strong"')
@@ -130,6 +133,7 @@ class ReconEngine:
         self.verbose = verbose
         self.launches_per_iter = 0
         self.graph = None
+        self.keep_grad = False          # True: the fused backward also writes the alpha gradients to gflat (inspection)
         n = self.cached_inps.shape[0]
         # ---- device-side schedules -------------------------------------------------------------------
         tab = idx_table if idx_table is not None else index_table(n, self.batch, self.iters)
@@ -155,6 +159,8 @@ class ReconEngine:
         self.idx_live = torch.zeros(self.batch, dtype=torch.int64, device=self.dev)
         self.b_live = torch.zeros(1, device=self.dev)
         self.lr_live = torch.zeros(1, device=self.dev)
+        self.state = ops.IterationState(self.step_dev, self.idx_table, self.idx_live, self.b_table, self.b_live,
+                                        self.lr_table, self.lr_live, max(self.iters, 1))
         self.cur_inp = torch.empty((self.batch,) + tuple(self.cached_inps.shape[1:]), device=self.dev)
         self.cur_out = torch.empty((self.batch,) + tuple(self.cached_outs.shape[1:]), device=self.dev) if self.host_resident else None
         self.cur_grad = torch.empty((self.batch,) + tuple(self.cached_grads.shape[1:]), device=self.dev) \
@@ -176,8 +182,10 @@ class ReconEngine:
                 self._setup_act_phase(list(act_quantizers))
             else:
                 self._setup_weight_phase()
-            self.exp_avg = torch.zeros_like(self.flat)
-            self.exp_avg_sq = torch.zeros_like(self.flat)
+            # the peer-memory exchange keeps Adam's moments for this rank's shard only
+            n_state = self.sym.shard if getattr(self, 'sym', None) is not None else self.flat.numel()
+            self.exp_avg = torch.zeros(n_state, device=self.dev)
+            self.exp_avg_sq = torch.zeros(n_state, device=self.dev)
         except BaseException:
             self.close()                 # a failed set-up must not leave the unit frozen or holding engine weights
             raise
@@ -186,8 +194,13 @@ class ReconEngine:
     def _setup_weight_phase(self):
         qs = [m.weight_quantizer for m in self.modules]
         sizes = [_pad4(q.alpha.numel()) for q in qs]
-        self.flat = torch.zeros(sum(sizes), device=self.dev)
-        self.gflat = torch.zeros_like(self.flat)
+        # several GPUs: parameter and gradient buffers in symmetric memory, exchanged by one peer-memory kernel
+        self.sym = ssq_dist.symmetric_unit_or_none(sum(sizes), self.dev) if self.multi_gpu else None
+        if self.sym is not None:
+            self.flat, self.gflat = self.sym.flat, self.sym.gflat
+        else:
+            self.flat = torch.zeros(sum(sizes), device=self.dev)
+            self.gflat = torch.zeros_like(self.flat)
         entries, self.wq_leaves, off = [], [], 0
         for m, q, sz in zip(self.modules, qs, sizes):
             n = q.alpha.numel()
@@ -221,20 +234,21 @@ class ReconEngine:
 
     # ------------------------------------------------------------------------------------------ one iteration
     def _iteration(self):
-        ops.loop_advance(self.step_dev, self.idx_table, self.idx_live, self.b_table, self.b_live,
-                         self.lr_table, self.lr_live, max(self.iters, 1))
+        """one iteration; *step_dev (iterations completed) is read by every kernel and incremented by the last one"""
+        table = None if self.act_quant else self.table
+        reg = None if self.act_quant else self.reg_dev
         if not self.host_resident:
-            ops.gather_rows(self.cached_inps, self.idx_live, out=self.cur_inp)
-        elif self.host_pull:
-            # the rows pulled during the previous iteration become current (HBM->HBM); then fork: the SMs pull the
-            # next mini-batch (row *step_dev of the table, already advanced) over PCIe beside this iteration's kernels
-            main = torch.cuda.current_stream(self.dev)
-            for _src, stage, cur in self._pull_bufs:
-                cur.copy_(stage, non_blocking=True)
-            self._pull_stream.wait_stream(main)
-            self._pull(0)
-        if not self.act_quant:
-            self.table.forward(True, self.b_live, self.weight, self.reg_dev)
+            ops.iter_prologue(self.state, self.cached_inps, self.cur_inp, table, self.weight, reg)
+        else:
+            ops.iter_prologue(self.state, None, None, table, self.weight, reg)
+            if self.host_pull:
+                # the rows pulled during the previous iteration become current (HBM->HBM); then fork: the SMs pull the
+                # NEXT mini-batch (row *step_dev + 1 of the table) over PCIe beside this iteration's kernels
+                main = torch.cuda.current_stream(self.dev)
+                for _src, stage, cur in self._pull_bufs:
+                    cur.copy_(stage, non_blocking=True)
+                self._pull_stream.wait_stream(main)
+                self._pull(1)
         with torch.enable_grad():
             out = self.unit(self.cur_inp)
         if self.host_resident:
@@ -254,10 +268,18 @@ class ReconEngine:
                 self.gflat[:packed.numel()].copy_(packed)
         else:
             gwqs = torch.autograd.grad([out], self.wq_leaves, [dpred.view_as(out)])
-            self.table.backward(gwqs, self.b_live, self.weight * self.reg_share)
-        if self.multi_gpu:
-            ssq_dist.all_reduce_sum_(self.gflat)                     # SUM, as link.allreduce at block_recon.py:100-102
-        ops.adam_step(self.flat, self.gflat, self.exp_avg, self.exp_avg_sq, self.lr_live, self.step_dev)
+            if not self.multi_gpu:
+                self.table.backward_adam(gwqs, self.b_live, self.weight * self.reg_share, self.flat, self.exp_avg,
+                                         self.exp_avg_sq, self.lr_live, self.step_dev, store_grad=self.keep_grad)
+            else:
+                self.table.backward(gwqs, self.b_live, self.weight * self.reg_share)
+        if self.multi_gpu and getattr(self, 'sym', None) is not None:
+            # SUM over the ranks (link.allreduce, block_recon.py:100-102) + Adam + hand-out of the new alphas: one kernel
+            ops.grad_exchange_adam(self.sym, self.exp_avg, self.exp_avg_sq, self.lr_live, self.step_dev)
+        elif self.act_quant or self.multi_gpu:
+            if self.multi_gpu:
+                ssq_dist.all_reduce_sum_(self.gflat)                 # NCCL path (activation step sizes; SSQ_EXCHANGE=nccl)
+            ops.adam_step_end_iteration(self.flat, self.gflat, self.exp_avg, self.exp_avg_sq, self.lr_live, self.step_dev)
         if self.host_pull:
             torch.cuda.current_stream(self.dev).wait_stream(self._pull_stream)      # join the prefetch branch
 
@@ -417,6 +439,8 @@ class ReconEngine:
                     rec + rnd, rec, rnd, float(self.b_live), count))
 
     def close(self):
+        if getattr(self, 'sym', None) is not None and self.graph is not None:
+            self.sym.check()
         for m in self.modules:
             m._engine_weight = None
         for q, flag in self._frozen:

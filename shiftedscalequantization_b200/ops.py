@@ -7,10 +7,12 @@ from __future__ import annotations
 
 from typing import Optional, Sequence, Tuple
 
+import ctypes as C
+
 import torch
 
 from . import _lib
-from ._lib import AdaRoundDesc, MT_MAX, MT_TILE, SHIFT_ADASHIFT, SHIFT_DEQUANT
+from ._lib import AdaRoundDesc, IterState, MT_MAX, MT_TILE, SHIFT_ADASHIFT, SHIFT_DEQUANT
 
 # --------------------------------------------------------------------------------------- plumbing
 _launch_count = 0          # kernels launched through this module (bench.py reports it)
@@ -300,6 +302,38 @@ class AdaRoundTable:
             self.table[i].gwq = _req(g, "gwq").data_ptr()
         _call("ssq_fq_adaround_bwd_mt", self.table, self.count, self.total_tiles, _ptr(b_dev), float(lam),
               torch.cuda.current_stream(self.device).cuda_stream)
+
+    def backward_adam(self, gwqs: Sequence[torch.Tensor], b_dev, lam: float, flat, exp_avg, exp_avg_sq, lr_dev, step_dev,
+                      betas=(0.9, 0.999), eps=1e-8, store_grad=False):
+        """gradient of every alpha + its Adam step + end of the iteration (*step_dev += 1) in one launch"""
+        for i, g in enumerate(gwqs):
+            self.table[i].gwq = _req(g, "gwq").data_ptr()
+        ws = workspace(self.device, _lib.load().ssq_ws_bytes(1), "mt")
+        _call("ssq_fq_adaround_bwd_adam_mt", self.table, self.count, self.total_tiles, _ptr(b_dev), float(lam),
+              flat.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), lr_dev.data_ptr(), step_dev.data_ptr(),
+              float(betas[0]), float(betas[1]), float(eps), int(bool(store_grad)), ws.data_ptr(), ws.numel(),
+              torch.cuda.current_stream(self.device).cuda_stream)
+
+
+class IterationState:
+    """device-side iteration state of one reconstruction loop (include/ssq_b200.h, ssq_iter_state)"""
+
+    def __init__(self, step_dev, idx_table, idx_live, b_table, b_live, lr_table, lr_live, n_steps: int):
+        self.keep = (step_dev, idx_table, idx_live, b_table, b_live, lr_table, lr_live)
+        self.c = IterState(step_dev.data_ptr(), idx_table.data_ptr(), _ptr(idx_live), _ptr(b_table), _ptr(b_live),
+                           _ptr(lr_table), _ptr(lr_live), int(n_steps), int(idx_table.shape[-1]))
+        self.device = step_dev.device
+
+
+def iter_prologue(state: IterationState, cache, cur_inp, table: Optional[AdaRoundTable], lam: float = 0.0, reg_out=None):
+    """launch 1 of an iteration: bookkeeping + mini-batch gather (cache None: skipped) + multi-tensor soft forward with the
+    regulariser (table None: skipped)"""
+    per_sample = 0 if cache is None else cache.numel() // cache.shape[0]
+    ws = workspace(state.device, _lib.load().ssq_ws_bytes(1), "mt") if reg_out is not None else None
+    _call("ssq_iter_prologue", C.byref(state.c), _ptr(cache), _ptr(cur_inp) if cache is not None else None, per_sample,
+          table.table if table is not None else None, table.count if table is not None else 0,
+          table.total_tiles if table is not None else 0, float(lam), _ptr(reg_out), _ptr(ws), 0 if ws is None else ws.numel(),
+          torch.cuda.current_stream(state.device).cuda_stream)
 
 
 # --------------------------------------------------------------------------------------- K1c
@@ -606,6 +640,24 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, lr_dev, step_dev, betas=(0.9, 0.
         return
     _call("ssq_adam_step", param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel(),
           lr_dev.data_ptr(), float(betas[0]), float(betas[1]), float(eps), step_dev.data_ptr(), _stream(param))
+
+
+def adam_step_end_iteration(param, grad, exp_avg, exp_avg_sq, lr_dev, step_dev, betas=(0.9, 0.999), eps=1e-8):
+    """adam_step with t = *step_dev + 1 that also ends the iteration (*step_dev += 1 once every CTA has retired)"""
+    ws = workspace(param.device, _lib.load().ssq_ws_bytes(1), "mt")
+    _call("ssq_adam_step_end_iteration", param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel(),
+          lr_dev.data_ptr(), float(betas[0]), float(betas[1]), float(eps), step_dev.data_ptr(), ws.data_ptr(), ws.numel(), _stream(param))
+
+
+def grad_exchange_adam(sym, exp_avg_shard, exp_avg_sq_shard, lr_dev, step_dev, betas=(0.9, 0.999), eps=1e-8, reduced_out=None):
+    """the multi-GPU exchange step as ONE kernel over peer memory: reduce-scatter of the symmetric gradient buffers, Adam on
+    this rank's shard, all-gather of the new parameters into every rank's buffer, end of iteration (include/ssq_b200.h)"""
+    dev = sym.flat.device
+    ws = workspace(dev, _lib.load().ssq_ws_bytes(1), "mt")
+    _call("ssq_grad_exchange_adam", sym.flat_ptrs, sym.grad_ptrs, sym.pad_ptrs, sym.rank, sym.world, sym.n,
+          exp_avg_shard.data_ptr(), exp_avg_sq_shard.data_ptr(), lr_dev.data_ptr(), step_dev.data_ptr(),
+          float(betas[0]), float(betas[1]), float(eps), _ptr(reduced_out), sym.timeouts.data_ptr(), ws.data_ptr(), ws.numel(),
+          torch.cuda.current_stream(dev).cuda_stream)
 
 
 def gather_rows(src, index, out=None):

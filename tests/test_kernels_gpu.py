@@ -553,6 +553,76 @@ def test_adam_and_loop_advance(ops):
         assert_close(host(p), g[f"p{s}"], rtol=2e-6, what=f"adam step {s} vs torch.optim.Adam")
 
 
+def test_fused_iteration_kernels_equal_the_separate_launches(ops):
+    """ssq_iter_prologue == loop_advance + gather_rows + fq_adaround_fwd_mt and ssq_fq_adaround_bwd_adam_mt ==
+    fq_adaround_bwd_mt + adam_step, bit for bit, over several iterations of a two-layer unit (one layer with a ragged,
+    non-vector size); the iteration counter ends every iteration one higher"""
+    r = rng(2024)
+    dev_ = torch.device("cuda")
+    shapes = [(64, 32, 3, 3), (7, 5, 3, 3)]
+    iters, batch, n_img = 6, 8, 20
+    cache = dev(r.standard_normal((n_img, 4, 6, 6)))
+    idx_table = torch.stack([torch.randperm(n_img)[:batch] for _ in range(iters)]).cuda()
+    b_table = torch.tensor([0.0, 0.0, 20.0, 14.0, 8.0, 2.0], device=dev_)
+    lr_table = torch.full((iters,), 1e-3, device=dev_)
+
+    def unit():
+        torch.manual_seed(3)
+        sizes = [int(np.prod(s)) for s in shapes]
+        pad = [(n + 3) // 4 * 4 for n in sizes]
+        flat = torch.zeros(sum(pad), device=dev_); gflat = torch.zeros_like(flat)
+        entries, off = [], 0
+        for shp, n, pn in zip(shapes, sizes, pad):
+            w = torch.randn(shp, device=dev_) * 0.05
+            d = (w.abs().amax(dim=(1, 2, 3), keepdim=True) / 1.5).contiguous(); z = torch.full_like(d, 2.0)
+            a = flat[off:off + n].view(shp); a.copy_(ops.adaround_init_alpha(w, d))
+            entries.append(dict(w=w, alpha=a, delta=d, zero_point=z, wq=torch.empty_like(w), galpha=gflat[off:off + n].view(shp),
+                                qmin=0.0, qmax=3.0))
+            off += pn
+        return flat, gflat, entries, ops.AdaRoundTable(entries)
+
+    res = {}
+    for fused in (False, True):
+        flat, gflat, entries, table = unit()
+        m, v = torch.zeros_like(flat), torch.zeros_like(flat)
+        step = torch.zeros(1, dtype=torch.int64, device=dev_)
+        idx_live = torch.zeros(batch, dtype=torch.int64, device=dev_); b_live = torch.zeros(1, device=dev_); lr_live = torch.zeros(1, device=dev_)
+        cur = torch.empty((batch,) + tuple(cache.shape[1:]), device=dev_); reg = torch.zeros(1, device=dev_)
+        state = ops.IterationState(step, idx_table, idx_live, b_table, b_live, lr_table, lr_live, iters)
+        trace = []
+        for it in range(iters + 2):                                  # two replays past the schedule: last row repeats
+            if fused:
+                ops.iter_prologue(state, cache, cur, table, 0.01, reg)
+                assert int(step) == it
+            else:
+                ops.loop_advance(step, idx_table, idx_live, b_table, b_live, lr_table, lr_live, iters)
+                ops.gather_rows(cache, idx_live, out=cur)
+                table.forward(True, b_live, 0.01, reg)
+            row = min(it, iters - 1)
+            assert torch.equal(idx_live, idx_table[row]) and float(b_live) == float(b_table[row]) and torch.equal(cur, cache[idx_table[row]])
+            gwqs = [torch.randn_like(e["w"]) * (1 + it) for e in entries] if it == 0 else gwqs
+            if fused:
+                table.backward_adam(gwqs, b_live, 0.01, flat, m, v, lr_live, step, store_grad=True)
+            else:
+                table.backward(gwqs, b_live, 0.01)
+                ops.adam_step(flat, gflat, m, v, lr_live, step)
+            assert int(step) == it + 1
+            trace.append([reg.clone(), flat.clone(), m.clone(), v.clone(), gflat.clone()] + [e["wq"].clone() for e in entries])
+        res[fused] = trace
+    for a, b in zip(res[False], res[True]):
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+    # the un-fused Adam that ends an iteration (multi-GPU / activation phase): same numbers, counter handed over
+    p0 = dev(golden("adam")["p0"]); g1 = dev(golden("adam")["g1"])
+    pa, ma, va = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    pb, mb, vb = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    sa = torch.ones(1, dtype=torch.int64, device=dev_); sb = torch.zeros(1, dtype=torch.int64, device=dev_)
+    lr = ops.scalar_dev(1e-3, dev_)
+    ops.adam_step(pa, g1, ma, va, lr, sa)
+    ops.adam_step_end_iteration(pb, g1, mb, vb, lr, sb)
+    assert torch.equal(pa, pb) and torch.equal(ma, mb) and torch.equal(va, vb) and int(sb) == 1
+
+
 def test_chan_affine(ops):
     r = rng(3)
     x = r.standard_normal((4, 6, 5, 5)).astype(np.float32)

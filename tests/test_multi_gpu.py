@@ -42,10 +42,40 @@ def run(mode):
     eng = ReconEngine(block, mods, inps, outs, None, act_quant=False, iters=iters, weight=0.01, b_range=(20, 2), warmup=0.2,
                       p=2.0, batch_size=bs, use_graph=True, idx_table=tab, verbose=False, multi_gpu=(mode != 'single'),
                       scaling='strong' if mode == 'strong' else 'weak')
+    assert (eng.sym is not None) == (mode != 'single' and D.EXCHANGE == 'p2p'), "symmetric memory must be available on a multi-GPU box"
     eng.run(); eng.close()
     return torch.cat([m.weight_quantizer.alpha.detach().reshape(-1) for m in mods])
 
+# the exchange step itself: reduce-scatter + Adam + all-gather in one peer-memory kernel against torch / NCCL
+from shiftedscalequantization_b200 import ops
+n = 4 * 1037                                                     # not a multiple of the world size or of the tile
+sym = D.SymmetricUnit(n, torch.device("cuda", local))
+torch.manual_seed(11)
+p0 = torch.randn(n, device="cuda")                               # same on every rank
+sym.flat.copy_(p0)
+shard = sym.shard
+m = torch.zeros(shard, device="cuda"); v = torch.zeros(shard, device="cuda"); red = torch.zeros(shard, device="cuda")
+step = torch.zeros(1, dtype=torch.int64, device="cuda"); lr = ops.scalar_dev(1e-3, "cuda")
+pr, mr, vr = p0.clone(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+sr = torch.zeros(1, dtype=torch.int64, device="cuda")
+for it in range(4):
+    torch.manual_seed(100 * it + rk)
+    g = torch.randn(n, device="cuda")                            # a different gradient on every rank
+    sym.gflat.copy_(g)
+    ops.grad_exchange_adam(sym, m, v, lr, step, reduced_out=red)
+    gs = g.clone(); td.all_reduce(gs)                            # world == 2: a + b in either order is the same float
+    ops.adam_step_end_iteration(pr, gs, mr, vr, lr, sr)
+    torch.cuda.synchronize(); td.barrier()
+    lo = rk * shard; hi = min(lo + shard, n)
+    assert torch.equal(red[:hi - lo], gs[lo:hi]), f"iteration {it}: reduced shard"
+    assert torch.equal(sym.flat, pr), f"iteration {it}: parameters after the fused exchange vs all-reduce + Adam"
+    assert int(step) == it + 1
+sym.check()
+
 single = run('single')
+D.EXCHANGE = 'nccl'
+weak_nccl = run('weak')
+D.EXCHANGE = 'p2p'
 for mode in ('strong', 'weak'):
     a = run(mode)
     both = [torch.empty_like(a) for _ in range(world)]
@@ -58,6 +88,7 @@ for mode in ('strong', 'weak'):
         assert float((torch.sign(a) == torch.sign(single)).float().mean()) > 0.9995
     else:
         assert not torch.equal(a, single)                                       # other mini-batches: a different trajectory
+        assert torch.equal(a, weak_nccl), "peer-memory exchange vs NCCL all-reduce + Adam (two ranks: identical sums)"
 td.barrier()
 sys.stdout.write(f"rank {rk} ok\n"); sys.stdout.flush()
 td.destroy_process_group()
@@ -71,6 +102,6 @@ def test_two_gpu_strong_matches_single_and_replicas_identical(tmp_path):
     env = dict(os.environ, SSQ_ROOT=ROOT)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29621", str(script)]
-    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout
