@@ -188,7 +188,9 @@ def test_export_carries_the_trained_output_affine():
     cnn = zoo.resnet18().cuda().eval()
     search_fold_and_remove_bn(cnn)
     wrapper = torch.nn.Module(); wrapper.model = cnn
-    E.import_int_weights(wrapper, blob)
+    # the FP network keeps the shortcut as Sequential(conv, folded bn): the quantised block's `downsample` layer is its `.0`
+    plain = {(k + ".0" if k.endswith(".downsample") else k): v for k, v in blob.items()}
+    E.import_int_weights(wrapper, plain)
     with torch.no_grad():
         out = cnn(x)
     assert torch.allclose(out, ref, rtol=1e-4, atol=1e-4 * float(ref.abs().max()))

@@ -25,6 +25,7 @@ from test_recon_gpu import build_qnn
 rk, local, world = D.init_from_env()
 torch.cuda.set_device(local)
 torch.backends.cudnn.allow_tf32 = False
+torch.backends.cudnn.deterministic = True          # as the reference's drivers (common.py:84-85): runs are comparable bit for bit
 iters, bs = 20, 16
 
 def run(mode):
