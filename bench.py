@@ -96,12 +96,17 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------- reference arm
-def cpu_reference(steps: int, warmup: int, sample_images: int = 64, units=None):
-    """The reference's CPU path (oracle/ref_loop_torch.py: the same ATen-CPU op chain as quant/block_recon.py:89-105,
-    pinned to the real reference loops by tests/golden/recon_loop.npz) on all host cores. One step = one iteration on
-    each of the 9 units at batch 32; features are synthetic relu(randn) of the real shapes, `sample_images` per unit."""
+def reference_loop(steps: int, warmup: int, sample_images: int = 64, units=None, device: str = "cpu"):
+    """The reference's own op chain (oracle/ref_loop_torch.py: the ATen ops of quant/block_recon.py:89-105 in the same order,
+    torch.optim.Adam — ONE optimizer per unit, built before the timed loop as block_recon.py:60 does —, pinned to the real
+    reference loops by tests/golden/recon_loop.npz). device='cpu': all host cores = the CPU baseline / `--impl reference`
+    arm. device='cuda': the same chain on ATen's CUDA kernels + cuDNN, i.e. what the unmodified reference does on this
+    GPU (extra.gpu_reference; TF32 off like the headline). One step = one iteration on each of the 9 units at batch 32;
+    features are synthetic relu(randn) of the real shapes, `sample_images` per unit."""
     from oracle import ref_loop_torch as R
-    torch.set_num_threads(os.cpu_count() or 1)
+    on_gpu = device != "cpu"
+    if not on_gpu:
+        torch.set_num_threads(os.cpu_count() or 1)
     cores = torch.get_num_threads()
     torch.manual_seed(1005)
     built = []
@@ -116,24 +121,30 @@ def cpu_reference(steps: int, warmup: int, sample_images: int = 64, units=None):
             x = torch.relu(torch.randn(sample_images, cin, hw, hw))
         y = R.fp_unit_outputs(unit, x)
         tab = torch.stack([torch.randperm(sample_images)[:BATCH] for _ in range(total)])
-        built.append((unit, x, y, tab))
-    times = []
-    state = [None] * len(built)
+        if on_gpu:
+            unit, x, y, tab = R.unit_to(unit, device), x.to(device), y.to(device), tab.to(device)
+        built.append((unit, x, y, tab, {}))
+    alphas = [None] * len(built)
+    sync = (lambda: torch.cuda.synchronize()) if on_gpu else (lambda: None)
+    t_timed = 0.0
     for s in range(total):
-        t0 = time.perf_counter()
-        for u, (unit, x, y, tab) in enumerate(built):
+        if s == warmup:
+            sync(); t0 = time.perf_counter()
+        for u, (unit, x, y, tab, state) in enumerate(built):
             # one iteration at the right point of the 20k schedule is what matters for cost: regulariser on
-            alphas, _ = R.recon_weight_loop(unit, x, y, tab[s:s + 1], 1, weight=RECON['weight'], b_range=RECON['b_range'],
-                                            warmup=RECON['warmup'], p=RECON['p'], alphas=state[u],
-                                            start_count=SCHED_ITERS // 2 + s, t_max=SCHED_ITERS)
-            state[u] = alphas
-        dt = time.perf_counter() - t0
-        if s >= warmup:
-            times.append(dt)
-    ms = 1e3 * sum(times) / max(len(times), 1)
+            alphas[u], _ = R.recon_weight_loop(unit, x, y, tab[s:s + 1], 1, weight=RECON['weight'], b_range=RECON['b_range'],
+                                               warmup=RECON['warmup'], p=RECON['p'], alphas=alphas[u],
+                                               start_count=SCHED_ITERS // 2 + s, t_max=SCHED_ITERS, state=state)
+    sync(); t_timed = time.perf_counter() - t0
+    ms = 1e3 * t_timed / max(steps, 1)
     return {"iters_per_s": len(built) / (ms / 1e3), "ms_per_step": ms, "cores": cores,
-            "sample": f"{len(times)} steps x {len(built)} units, batch {BATCH}, {sample_images} synthetic feature images per unit "
-                      f"(real ResNet-18 224x224 unit shapes), torch {torch.__version__} CPU, Adam state rebuilt per step"}
+            "sample": f"{steps} steps x {len(built)} units, batch {BATCH}, {sample_images} synthetic feature images per unit "
+                      f"(real ResNet-18 224x224 unit shapes), torch {torch.__version__} {'CUDA (ATen + cuDNN fp32)' if on_gpu else 'CPU'}, "
+                      "one Adam per unit built outside the timed loop"}
+
+
+def cpu_reference(steps: int, warmup: int, sample_images: int = 64, units=None):
+    return reference_loop(steps, warmup, sample_images, units, "cpu")
 
 
 def run_reference(args):
@@ -144,11 +155,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "recon iters/s (ResNet-18 W2A4, 1024 calib imgs)", "value": r["iters_per_s"],
             "unit": "iters/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "calib_images": args.images, "per_rank_batch": BATCH, "global_batch": BATCH,
-                       "step": "one iteration on each of the 9 units",
-                       "arm": "reference CPU path (oracle/ref_loop_torch.py: the ATen-CPU op chain of quant/block_recon.py:89-105, pinned to the "
-                              "real reference loops by tests/golden/recon_loop.npz) on all host cores; rank 0 only",
-                       "conv_math": "fp32"},
+            "config": bench_config(args, args.gpus),
+            "reference_arm": "reference CPU path (oracle/ref_loop_torch.py: the ATen-CPU op chain of quant/block_recon.py:89-105, pinned to the "
+                             "real reference loops by tests/golden/recon_loop.npz) on all host cores; rank 0 only; a bounded sample of the "
+                             "workload in `config`: " + r["sample"],
             "cpu_baseline": {"value": r["iters_per_s"], "unit": "iters/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["iters_per_s"], "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -312,6 +322,12 @@ def kernel_microbench(dev, peak_gbs):
     m = torch.zeros_like(w); v = torch.zeros_like(w)
     step = torch.ones(1, dtype=torch.int64, device=dev); lr = ops.scalar_dev(1e-3, dev)
     res["adam_step"] = timeit(lambda: ops.adam_step(alpha, g, m, v, lr, step), 28 * n)
+    # launch 3 of an iteration: alpha gradient + Adam in one pass (read g_wq, w, alpha, m, v; write alpha, m, v = 32 B/element)
+    a2 = alpha.clone()
+    tab = ops.AdaRoundTable([dict(w=w, alpha=a2, delta=d, zero_point=z, wq=ga, galpha=None, qmin=0.0, qmax=3.0)])
+    lr0 = ops.scalar_dev(0.0, dev)                               # lr = 0: the timed launches leave alpha where it is
+    res["fq_adaround_bwd_adam(+reg grad)"] = timeit(lambda: tab.backward_adam([g], bdev, 0.01, a2, m, v, lr0, step), 32 * n)
+    del a2, tab
     # K1c: shifted-scale mixture, S = 3 shifts, one group per input channel (alpha [IC,3]); candidates recomputed from w
     shifts = [0.96875, 1.03125, 1.0]
     sd = torch.stack([(d * st).reshape(-1) for st in shifts]).contiguous()
@@ -482,6 +498,8 @@ def shifted_loop_bench(dev, n_images=256):
 
 
 ENTRY_TO_MICRO = {"ssq_recon_loss": "recon_loss(fwd+dpred)", "ssq_gather_rows": "gather_rows", "ssq_adam_step": "adam_step",
+                  "ssq_adam_step_end_iteration": "adam_step", "ssq_iter_prologue": "fq_adaround_fwd(+reg)",
+                  "ssq_fq_adaround_bwd_adam_mt": "fq_adaround_bwd_adam(+reg grad)",
                   "ssq_fq_adaround_fwd_mt": "fq_adaround_fwd(+reg)", "ssq_fq_adaround_bwd_mt": "fq_adaround_bwd(+reg grad)",
                   "ssq_fq_affine_fwd": "fq_affine_fwd(acts,per-tensor)", "ssq_fq_affine_bwd": "fq_affine_bwd(acts,per-tensor)"}
 
@@ -507,6 +525,130 @@ def in_step_profile(engines, dev):
     for e, g in zip(engines, graphs):
         e.graph = g
     return prof, total
+
+
+def public_api_bench(dev, n_images, iters=600):
+    """the call a user makes: Q.block_reconstruction / Q.layer_reconstruction on fresh units (feature capture, engine set-up,
+    graph capture, `iters` iterations, hard rounding) — wall time of the whole call and the loop-only rate, to be read beside
+    the per-unit engine numbers (they must agree: it is the same engine)"""
+    from shiftedscalequantization_b200.quant import block_recon as BR
+    Q, qnn, cali = build_model(dev, n_images)
+    qnn.set_quant_state(True, False)
+    with torch.no_grad():
+        qnn(cali[:64].to(dev))
+    kw = dict(cali_data=cali, iters=iters, weight=RECON['weight'], asym=True, b_range=RECON['b_range'], warmup=RECON['warmup'],
+              act_quant=False, opt_mode='mse', batch_size=BATCH)
+    out = {}
+    for name, unit, fn in (("layer1.0", qnn.model.layer1[0], Q.block_reconstruction), ("layer1.1", qnn.model.layer1[1], Q.block_reconstruction),
+                           ("layer2.0", qnn.model.layer2[0], Q.block_reconstruction)):
+        torch.cuda.synchronize(dev); t0 = time.perf_counter()
+        fn(qnn, unit, **kw)
+        torch.cuda.synchronize(dev); wall = time.perf_counter() - t0
+        st = dict(BR.LAST_RUN_STATS)
+        out[name] = {"call_s": round(wall, 3), "loop_iters_per_s": round(st["iters"] / (st["loop_ms"] * 1e-3), 1), "iters": st["iters"],
+                     "capture_s": round(st.get("capture_s", 0.0), 3), "capture_mode": st.get("capture_mode"),
+                     "ssq_launches_per_iter": st["launches_per_iter"]}
+    del qnn
+    torch.cuda.empty_cache()
+    return out
+
+
+def readme_flags_bench(dev, n_images, iters=300):
+    """configs[1] as written: `--bias_cal --bias_ch_quant` (README.md:20,33-34; no code upstream, semantics in DESIGN.md §6) on
+    all nine units through the public functions: bias_cal alone = block/layer_reconstruction(bias_cal=True) (gamma^z, varphi^z
+    learned with the AdaRound alphas); with bias_ch_quant the BasicBlock units go through ChannelQuant +
+    block_recon_fused_shiftedScale(bias_cal=True) (input-channel group R). Loop-only iterations/s per unit."""
+    from shiftedscalequantization_b200.quant import block_recon as BR
+    from shiftedscalequantization_b200.quant import layer_recon_shiftedScale as LS
+    from shiftedscalequantization_b200.quant.channelQuant import ChannelQuant
+    from shiftedscalequantization_b200.quant.layer_recon_fused_shiftedScale import block_recon_fused_shiftedScale
+    import contextlib
+    import io
+    out = {}
+    for flags in ("bias_cal", "bias_cal+bias_ch_quant"):
+        Q, qnn, cali = build_model(dev, n_images)
+        qnn.set_quant_state(True, False)
+        with torch.no_grad():
+            qnn(cali[:64].to(dev))
+        kw = dict(cali_data=cali, iters=iters, weight=RECON['weight'], asym=True, b_range=RECON['b_range'], warmup=RECON['warmup'],
+                  act_quant=False, opt_mode='mse', batch_size=BATCH, bias_cal=True)
+        rates = {}
+        for unit in recon_units(Q, qnn):
+            name = getattr(unit, "pathName", "") or "fc"
+            with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+                if isinstance(unit, Q.BaseQuantBlock) and "ch_quant" in flags:
+                    for m in unit.modules():
+                        if isinstance(m, Q.QuantModule):
+                            m.weight_quantizer = ChannelQuant(1.0, uaq=m.weight_quantizer, weight_tensor=m.org_weight.data,
+                                                              shiftTarget=[0.96875, 1.03125, 1.0], name=m.pathName)
+                    unit.clear_cached_features()
+                    for mode, wq_on in (('if', True), ('of', False)):
+                        qnn.set_quant_state(wq_on, False)
+                        unit.cache_features = mode
+                        with torch.no_grad():
+                            for i in range(0, cali.shape[0], BATCH):
+                                qnn(cali[i:i + BATCH].to(dev))
+                        unit.cache_features = 'none'
+                    qnn.set_quant_state(False, False)
+                    unit.set_quant_state(True, False)
+                    block_recon_fused_shiftedScale(unit, iters=iters, lmda=[RECON['weight'], RECON['weight']], model=qnn, bias_cal=True)
+                    unit.clear_cached_features()
+                    st = dict(LS.LAST_LOOP_STATS)
+                elif isinstance(unit, Q.BaseQuantBlock):
+                    Q.block_reconstruction(qnn, unit, **kw)
+                    st = dict(BR.LAST_RUN_STATS)
+                else:
+                    Q.layer_reconstruction(qnn, unit, **kw)
+                    st = dict(BR.LAST_RUN_STATS)
+            rates[name] = {"iters_per_s": round(st["iters"] / (st["loop_ms"] * 1e-3), 1), "ssq_launches_per_iter": st["launches_per_iter"]}
+        hm = len(rates) / sum(1.0 / v["iters_per_s"] for v in rates.values())
+        out[flags] = {"per_unit": rates, "harmonic_mean_iters_per_s": round(hm, 1), "iters_per_unit": iters}
+        del qnn
+        torch.cuda.empty_cache()
+    return out
+
+
+def code_agreement_bench(dev):
+    """north_star: hard integer codes vs the REAL reference after a long loop. tests/golden/long_horizon.npz holds the codes the
+    reference produced on the CPU (block_reconstruction on layer1.0, layer_reconstruction on fc of a seeded ResNet-18, 64 randn
+    32x32 images, 2 000 iterations; tests/golden/make_golden_round2.py); the same flow runs here through the public API and
+    the fraction of identical codes is reported next to the reference's agreement with ITSELF under another CPU convolution
+    backend (the noise floor: cuDNN and CPU convolutions differ in the last bits, Adam amplifies that)."""
+    import numpy as np
+    from shiftedscalequantization_b200 import ops, quant as Q, zoo
+    path = os.path.join(ROOT, "tests", "golden", "long_horizon.npz")
+    if not os.path.exists(path):
+        return None
+    g = np.load(path)
+    out = {}
+    for iters in (2000,):
+        torch.manual_seed(1005)
+        cnn = zoo.resnet18(num_classes=10).to(dev).eval()
+        qnn = Q.QuantModel(cnn, {'n_bits': 2, 'channel_wise': True, 'scale_method': 'max'}, dict(AQ)).to(dev).eval()
+        qnn.set_first_last_layer_to_8bit()
+        cali = torch.randn(64, 3, 32, 32)
+        qnn.set_quant_state(True, False)
+        with torch.no_grad():
+            qnn(cali[:32].to(dev))
+        kw = dict(cali_data=cali, iters=iters, weight=0.01, asym=True, b_range=(20, 2), warmup=0.2, act_quant=False, opt_mode='mse', batch_size=32)
+        block = qnn.model.layer1[0]
+        torch.manual_seed(377)
+        Q.block_reconstruction(qnn, block, **kw)
+        torch.manual_seed(378)
+        Q.layer_reconstruction(qnn, qnn.model.fc, **kw)
+        rep = {}
+        for name, m in (("block.conv1", block.conv1), ("block.conv2", block.conv2), ("fc", qnn.model.fc)):
+            q = m.weight_quantizer
+            _, codes = ops.adaround_fwd(m.org_weight.detach(), q.alpha.detach(), q.delta.detach(), q.zero_point.detach(), 0.0,
+                                        float(q.n_levels - 1), soft=False, want_codes=True)
+            same = codes.cpu().numpy().astype(np.uint8) == g[f"i{iters}.{name}.codes"]
+            key = f"i{iters}.{name}.self_agreement"
+            rep[name] = {"identical_codes": float(same.mean()), "codes": int(same.size),
+                         "reference_vs_itself": float(g[key]) if key in g.files else None}
+        out[f"{iters}_iterations"] = rep
+    out["note"] = ("fraction of hard integer codes identical to the real reference's (CPU) after the loop; 20 000 iterations: "
+                   "tests/test_round2_gpu.py::test_long_horizon_code_agreement, numbers in profiles/r02_parity_report.json")
+    return out
 
 
 def run_ours(args):
@@ -578,15 +720,17 @@ def run_ours(args):
             torch.cuda.synchronize(dev)
             t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
             t0.record()
-            for _ in range(max(args.steps, 20)):
+            n_unit_iters = max(args.steps, 500)                  # >= 500 timed iterations per unit
+            for _ in range(n_unit_iters):
                 e.step()
             t1.record(); torch.cuda.synchronize(dev)
-            us = 1e3 * t0.elapsed_time(t1) / max(args.steps, 20)
+            us = 1e3 * t0.elapsed_time(t1) / n_unit_iters
             name = getattr(e.unit, "pathName", "") or f"unit{ui}"
             per_unit[name] = {"us_per_iter": round(us, 1), "iters_per_s": round(1e6 / us, 1),
                               "alpha_elems": int(e.flat.numel()), "ssq_launches": e.launches_per_iter}
         hm = len(per_unit) / sum(1.0 / v["iters_per_s"] for v in per_unit.values())
         per_unit["harmonic_mean_iters_per_s"] = round(hm, 1)
+        per_unit["timed_iterations_per_unit"] = max(args.steps, 500)
         prof, eager_ms = in_step_profile(engines, dev)
     release(engines)
     e2e = None
@@ -655,12 +799,21 @@ def run_ours(args):
     del engines, qnn
     torch.cuda.empty_cache()
     shifted = shifted_loop_bench(dev) if not args.skip_shift else None
+    more = {}
+    if not args.skip_extras:
+        more["public_api"] = public_api_bench(dev, min(n_total, 256))
+        more["readme_flags"] = readme_flags_bench(dev, min(n_total, 256))
+        more["code_agreement"] = code_agreement_bench(dev)
+        g = reference_loop(steps=5, warmup=2, device=str(dev))
+        more["gpu_reference"] = {"iters_per_s": g["iters_per_s"], "ms_per_step": g["ms_per_step"], "sample": g["sample"],
+                                 "note": "the reference's own op chain (~530 ATen launches per iteration) on this B200, fp32 cuDNN: "
+                                         "separates 'B200 vs host CPU' from '3 launches vs 530'"}
 
     # ---- roofline: DRAM-resident microbench of every kernel + in-step shares
     if args.skip_micro:
         line = base_line(args, value, ms_step, world, clocks, launches_per_step, e2e, peak_src)
         line["extra"] = {"first_quantised_forward_ms": scale_search_s * 1e3, "scale_search": search, "setup_s": setup_s, "act_phase": act,
-                         "shifted_loops": shifted, "per_unit": per_unit}
+                         "shifted_loops": shifted, "per_unit": per_unit, **more}
         emit(json.dumps(line))
         return
     micro = kernel_microbench(dev, peak_gbs)
@@ -671,7 +824,12 @@ def run_ours(args):
     traffic = None
     try:    # dram__bytes_read+write of one launch at this microbench shape, from the committed ncu --set full capture
         prof = json.load(open(os.path.join(ROOT, "profiles", "r01_kernels_ncu_full.json")))
+        try:
+            prof.update(json.load(open(os.path.join(ROOT, "profiles", "r02_kernels_ncu_full.json"))))
+        except Exception:
+            pass
         key = {"fq_adaround_fwd(+reg)": "ada_fwd_kernel", "fq_adaround_bwd(+reg grad)": "ada_bwd_kernel", "adam_step": "adam_kernel",
+               "fq_adaround_bwd_adam(+reg grad)": "ada_bwd_adam_mt_kernel",
                "recon_loss(fwd+dpred)": "recon_loss_kernel", "gather_rows": "gather_rows_kernel",
                "fq_affine_fwd(weights,per-channel)": "fq_affine_fwd_vec",
                "fq_affine_bwd(weights,per-channel)": "fq_affine_bwd_kernel"}.get(mk)    # captures taken at exactly these shapes
@@ -697,8 +855,26 @@ def run_ours(args):
                      "tf32": tf32_extra, "shifted_loops": shifted, "per_unit": per_unit,
                      "feature_capture_s": {"per_unit": [round(c, 3) for c in capture_s], "total": round(sum(capture_s), 3),
                                            "note": "save_inp_oup_data (quant/data_utils.py:8-37), 1024 images, batch 32, asym=True: excluded from iters/s"},
-                     "projected_full_run_s": (9 * 20000) / value + ((9 * 5000) / act["iters_per_s"] if act else 0)}
+                     "projected_full_run_s": (9 * 20000) / value + ((9 * 5000) / act["iters_per_s"] if act else 0), **more}
     emit(json.dumps(line))
+
+
+def bench_config(args, world):
+    """the workload description; identical keys and values in both arms (`--impl ours` / `--impl reference`)"""
+    strong = world > 1 and args.scaling == "strong"
+    return {"workload": WORKLOAD,
+            "calib_images": args.images, "per_rank_batch": BATCH // world if strong else BATCH,
+            "global_batch": BATCH if strong else BATCH * world,
+            "step": "one iteration on each of the 9 units",
+            "conv_math": "tf32" if args.tf32 else "fp32", "cudnn_benchmark": bool(args.cudnn_benchmark),
+            "l2": "inputs larger than L2: one step streams ~215 MB of mini-batch features (random rows of the 6.4 GB cache) plus the "
+                  "weights / alpha / Adam state of all 9 units (~230 MB), so nothing a unit touches survives in the 126 MB L2 until its "
+                  "next iteration; the roofline kernels are timed on 0.6-0.8 GB tensors",
+            "multi_gpu": ("single GPU" if world == 1 else
+                          "strong: every rank holds the cache, the ranks split one global mini-batch of 32, SUM of the flat "
+                          "alpha gradient (= the 1-GPU gradient) every iteration" if strong else
+                          "weak: calibration images sharded by rank, each rank draws its own mini-batch of 32, SUM of the "
+                          "flat alpha gradient every iteration")}
 
 
 def base_line(args, value, ms_step, world, clocks, launches_per_step, e2e, peak_src):
@@ -706,19 +882,7 @@ def base_line(args, value, ms_step, world, clocks, launches_per_step, e2e, peak_
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": args.scaling if world > 1 else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD,
-                       "calib_images": args.images, "per_rank_batch": BATCH // world if (world > 1 and args.scaling == "strong") else BATCH,
-                       "global_batch": BATCH if (world > 1 and args.scaling == "strong") else BATCH * world,
-                       "step": "one iteration on each of the 9 units (CUDA-graph replay per unit)",
-                       "conv_math": "tf32" if args.tf32 else "fp32", "cudnn_benchmark": bool(args.cudnn_benchmark),
-                       "l2": "inputs larger than L2: one step streams ~215 MB of mini-batch features (random rows of the 6.4 GB cache) plus the "
-                             "weights / alpha / Adam state of all 9 units (~230 MB), so nothing a unit touches survives in the 126 MB L2 until its "
-                             "next iteration; the roofline kernels are timed on 0.6-0.8 GB tensors",
-                       "multi_gpu": ("single GPU" if world == 1 else
-                                     "strong: every rank holds the cache, the ranks split one global mini-batch of 32, SUM all-reduce of the flat "
-                                     "alpha gradient (= the 1-GPU gradient) every iteration" if args.scaling == "strong" else
-                                     "weak: calibration images sharded by rank, each rank draws its own mini-batch of 32, SUM all-reduce of the "
-                                     "flat alpha gradient every iteration")},
+            "config": bench_config(args, world),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * (args.steps + args.warmup)}
 
 
@@ -740,6 +904,7 @@ def main():
     ap.add_argument("--micro-only", action="store_true", help="only the DRAM-resident kernel microbench")
     ap.add_argument("--skip-micro", action="store_true", help="no roofline microbench (short profiler runs)")
     ap.add_argument("--k2-only", action="store_true", help="only the scale-search (K2a / K2b) roofline numbers")
+    ap.add_argument("--skip-extras", action="store_true", help="no public-API / README-flags / code-agreement / GPU-reference extras")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -105,14 +105,19 @@ def unit_forward(unit, x, wqs, act_state=None):
 
 
 def recon_weight_loop(unit, cached_inps, cached_outs, idx_table, iters, weight=0.01, b_range=(20, 2), warmup=0.2,
-                      p=2.0, alphas=None, start_count=0, t_max=None):
+                      p=2.0, alphas=None, start_count=0, t_max=None, state=None):
     """the weight-rounding loop: returns (alphas, losses). `idx_table[i]` is the mini-batch of iteration i.
     t_max/start_count let a caller run a slice of a longer schedule (the CPU baseline times iterations from the
-    middle of the 20 000-iteration schedule, where the regulariser is live and b is non-integer)."""
+    middle of the 20 000-iteration schedule, where the regulariser is live and b is non-integer); `state` (a dict) keeps
+    the optimizer between such slices, as the reference keeps ONE torch.optim.Adam for the whole loop (block_recon.py:60)."""
     L = unit["layers"]
     if alphas is None:
         alphas = {n: init_alpha(s["weight"].detach(), s["delta"].detach()).requires_grad_(True) for n, s in L.items()}
-    opt = torch.optim.Adam(list(alphas.values()))
+    opt = state.get("opt") if state is not None else None
+    if opt is None:
+        opt = torch.optim.Adam(list(alphas.values()))
+        if state is not None:
+            state["opt"] = opt
     t_max = iters if t_max is None else t_max
     loss_start = t_max * warmup
     losses, count = [], start_count
@@ -210,6 +215,19 @@ def synthetic_fc_unit(cin=512, cout=1000, n_bits=8, seed=0):
     return {"kind": "layer", "layers": {"fc": _as_reference_parameters(dict(
         weight=w, bias=torch.zeros(cout), conv=None, act=None, delta=d, zero_point=z, n_levels=2 ** n_bits,
         alpha_out=torch.ones(1, cout), beta_out=torch.zeros(1, cout)))}}
+
+
+def unit_to(unit, device):
+    """the same functional unit with its tensors on `device` (leaf-ness and requires_grad preserved): the GPU-reference leg of
+    bench.py runs this very op chain with ATen's CUDA kernels, as the reference does on a GPU"""
+    def mv(v):
+        if torch.is_tensor(v):
+            t = v.detach().to(device)
+            return t.requires_grad_(True) if v.requires_grad else t
+        return v
+    out = {k: v for k, v in unit.items() if k != "layers"}
+    out["layers"] = {n: {k: mv(v) for k, v in s.items()} for n, s in unit["layers"].items()}
+    return out
 
 
 def fp_unit_outputs(unit, x):

@@ -430,6 +430,8 @@ class ReconEngine:
             return
         if self.use_graph and self.graph is None:
             self.capture()
+        self._t0, self._t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self._t0.record()
         for i in range(self.iters):
             self.step()
             count = i + 1
@@ -437,6 +439,12 @@ class ReconEngine:
                 rec, rnd = float(self.loss_dev), float(self.reg_dev)
                 print('Total loss:\t{:.3f} (rec:{:.3f}, round:{:.3f})\tb={:.2f}\tcount={}'.format(
                     rec + rnd, rec, rnd, float(self.b_live), count))
+        self._t1.record()
+
+    def loop_ms(self) -> float:
+        """device time of the last run()'s iteration loop (capture excluded); synchronises"""
+        self._t1.synchronize()
+        return self._t0.elapsed_time(self._t1)
 
     def close(self):
         if getattr(self, 'sym', None) is not None and self.graph is not None:

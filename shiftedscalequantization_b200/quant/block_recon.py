@@ -16,6 +16,9 @@ from .quant_layer import QuantModule, StraightThrough, lp_loss
 from .quant_model import QuantModel
 
 
+LAST_RUN_STATS = {}      # {'iters', 'loop_ms', 'launches_per_iter', 'capture_s', 'capture_mode'} of the most recent call (bench.py reads it)
+
+
 def _quant_modules(unit):
     return [m for _n, m in unit.named_modules() if isinstance(m, QuantModule)]
 
@@ -44,6 +47,7 @@ def _run_with_output_affine(unit, modules, cached_inps, cached_outs, *, iters, w
 
     try:
         eng.run(every=500, on_report=report, report_offset=1)      # count % 500 == 0, as upstream's LossFunction (:176)
+        LAST_RUN_STATS.update(iters=iters, loop_ms=eng.loop_ms(), launches_per_iter=eng.launches_per_iter)
     finally:
         eng.close()
         for m in modules:
@@ -78,7 +82,12 @@ def reconstruct_unit(model, unit, cali_data, *, is_block, batch_size, iters, wei
         # host_resident = upstream's keep_gpu=False: the caches never exist on the device as a whole (data_utils.py:34-36)
         keep_gpu = not host_resident
         device = next(model.parameters()).device
+        import time
+        from .data_utils import capture_stats
+        torch.cuda.synchronize(device); t_cap = time.perf_counter()
         cached_inps, cached_outs = save_inp_oup_data(model, unit, cali_data, asym, act_quant, batch_size, keep_gpu=keep_gpu)
+        torch.cuda.synchronize(device)
+        LAST_RUN_STATS.update(capture_s=time.perf_counter() - t_cap, capture_mode=capture_stats(model).last_mode)
         cached_grads = save_grad_data(model, unit, cali_data, act_quant, batch_size=batch_size, keep_gpu=keep_gpu) \
             if opt_mode != 'mse' else None
     if iters > 0:
@@ -94,6 +103,7 @@ def reconstruct_unit(model, unit, cali_data, *, is_block, batch_size, iters, wei
                                  host_resident=host_resident, device=device)
             try:
                 engine.run()
+                LAST_RUN_STATS.update(iters=iters, loop_ms=engine.loop_ms(), launches_per_iter=engine.launches_per_iter)
             finally:
                 engine.close()
     if not eval:
