@@ -162,14 +162,33 @@ typedef struct ssq_iter_state {
     int64_t n_steps;
     int batch;
 } ssq_iter_state;
+/* The layers' output affine gamma^z / varphi^z (alpha_out / beta_out, quant/quant_layer.py:231-238,258-259; README
+ * --bias_cal) FOLDED into the launches above: `aff` (nullable; parallel to `table`, per-output-channel layers only) makes
+ * the prologue emit W_eff = gamma_oc * W_q into table[i].wq and b_eff = gamma*bias + varphi into aff[i].beff, so that
+ * conv(x, W_eff) + b_eff == (conv(x, W_q) + bias) * gamma + varphi up to fp32 rounding and no activation-sized pass is
+ * needed; the backward scales g_wq by gamma_oc. ssq_affine_grad_mt gives the affine's own gradients from the weight and bias
+ * gradients of that folded layer: ggamma[c] = sum_k gwq[c,k] * W_q[c,k] + gbeff[c] * bias[c], gphi[c] = gbeff[c]
+ * (one warp per output channel, fixed summation order; W_q re-evaluated from (w, alpha) as the forward did). */
+typedef struct ssq_affine_desc {
+    const float* gamma;      /* [OC] */
+    const float* phi;        /* [OC] */
+    const float* bias;       /* [OC] or NULL */
+    float* beff;             /* [OC] out (prologue) */
+    const float* gbeff;      /* [OC] in  (ssq_affine_grad_mt): gradient of the folded bias */
+    float* ggamma;           /* [OC] out */
+    float* gphi;             /* [OC] out */
+    int64_t row_begin;       /* sum of OC over the layers before this one */
+} ssq_affine_desc;
 int ssq_iter_prologue(const ssq_iter_state* st, const float* cache, float* cur_inp, int64_t per_sample,
-                      const ssq_adaround_desc* table, int count, int64_t total_tiles,
+                      const ssq_adaround_desc* table, const ssq_affine_desc* aff, int count, int64_t total_tiles,
                       float lambda, float* reg_out, void* ws, size_t ws_bytes, void* stream);
-int ssq_fq_adaround_bwd_adam_mt(const ssq_adaround_desc* table, int count, int64_t total_tiles,
+/* apply_adam == 0: gradients only (store_grad must be set), the iteration is ended by whoever applies Adam */
+int ssq_fq_adaround_bwd_adam_mt(const ssq_adaround_desc* table, const ssq_affine_desc* aff, int count, int64_t total_tiles,
                                 const float* b_dev, float lambda,
                                 float* flat, float* exp_avg, float* exp_avg_sq, const float* lr_dev,
-                                int64_t* step_dev, double beta1, double beta2, double eps, int store_grad,
+                                int64_t* step_dev, double beta1, double beta2, double eps, int store_grad, int apply_adam,
                                 void* ws, size_t ws_bytes, void* stream);
+int ssq_affine_grad_mt(const ssq_adaround_desc* table, const ssq_affine_desc* aff, int count, void* stream);
 
 /* ---- K1c: shifted-scale ChannelQuant ------------------------------------------------
  * quant/channelQuant.py:49-127. Conv weights [OC,IC,kh,kw] (kk = kh*kw) carry one
@@ -302,6 +321,10 @@ int ssq_chan_affine_bwd(const float* gy, const float* x, const float* a, float* 
 int ssq_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                   const float* lr_dev, double beta1, double beta2, double eps,
                   const int64_t* step_dev, void* stream);
+/* t = *step_dev + 1 without ending the iteration (a second parameter group stepped before the launch that ends it) */
+int ssq_adam_step_pending(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                          const float* lr_dev, double beta1, double beta2, double eps,
+                          const int64_t* step_dev, void* stream);
 /* the same with t = *step_dev + 1 (step_dev = iterations completed), incrementing *step_dev when the last CTA retires */
 int ssq_adam_step_end_iteration(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                                 const float* lr_dev, double beta1, double beta2, double eps,

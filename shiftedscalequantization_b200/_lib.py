@@ -35,6 +35,14 @@ class AdaRoundDesc(C.Structure):
     ]
 
 
+class AffineDesc(C.Structure):
+    """mirror of ssq_affine_desc"""
+    _fields_ = [
+        ("gamma", _p), ("phi", _p), ("bias", _p), ("beff", _p), ("gbeff", _p), ("ggamma", _p), ("gphi", _p),
+        ("row_begin", _i64),
+    ]
+
+
 class IterState(C.Structure):
     """mirror of ssq_iter_state"""
     _fields_ = [
@@ -75,8 +83,10 @@ PROTOTYPES = {
     "ssq_chan_affine_bwd": (_i32, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p, _sz, _p]),
     "ssq_adam_step": (_i32, [_p, _p, _p, _p, _i64, _p, _d, _d, _d, _p, _p]),
     "ssq_adam_step_end_iteration": (_i32, [_p, _p, _p, _p, _i64, _p, _d, _d, _d, _p, _p, _sz, _p]),
-    "ssq_iter_prologue": (_i32, [C.POINTER(IterState), _p, _p, _i64, C.POINTER(AdaRoundDesc), _i32, _i64, _f, _p, _p, _sz, _p]),
-    "ssq_fq_adaround_bwd_adam_mt": (_i32, [C.POINTER(AdaRoundDesc), _i32, _i64, _p, _f, _p, _p, _p, _p, _p, _d, _d, _d, _i32, _p, _sz, _p]),
+    "ssq_adam_step_pending": (_i32, [_p, _p, _p, _p, _i64, _p, _d, _d, _d, _p, _p]),
+    "ssq_iter_prologue": (_i32, [C.POINTER(IterState), _p, _p, _i64, C.POINTER(AdaRoundDesc), C.POINTER(AffineDesc), _i32, _i64, _f, _p, _p, _sz, _p]),
+    "ssq_fq_adaround_bwd_adam_mt": (_i32, [C.POINTER(AdaRoundDesc), C.POINTER(AffineDesc), _i32, _i64, _p, _f, _p, _p, _p, _p, _p, _d, _d, _d, _i32, _i32, _p, _sz, _p]),
+    "ssq_affine_grad_mt": (_i32, [C.POINTER(AdaRoundDesc), C.POINTER(AffineDesc), _i32, _p]),
     "ssq_exchange_pad_bytes": (_sz, []),
     "ssq_exchange_shard_elems": (_i64, [_i64, _i32]),
     "ssq_grad_exchange_adam": (_i32, [_p, _p, _p, _i32, _i32, _i64, _p, _p, _p, _p, _d, _d, _d, _p, _p, _p, _sz, _p]),

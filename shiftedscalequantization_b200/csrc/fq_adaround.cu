@@ -60,7 +60,8 @@ __device__ __forceinline__ double ada_fwd_span(const float* __restrict__ w, cons
                                                const float* __restrict__ delta, const float* __restrict__ zp,
                                                float* __restrict__ wq, float* __restrict__ codes, int64_t e0, int64_t e1,
                                                int64_t inner, int64_t nchan, float qmin, float qmax, float b,
-                                               int64_t tid, int64_t nthr, bool vec) {
+                                               int64_t tid, int64_t nthr, bool vec,
+                                               const float* __restrict__ gamma = nullptr /* [nchan] output-channel scale folded into wq */) {
     double acc = 0.0;
     ChanWalk cw;
     if (vec) {
@@ -71,9 +72,9 @@ __device__ __forceinline__ double ada_fwd_span(const float* __restrict__ w, cons
         float4* __restrict__ c4 = codes ? reinterpret_cast<float4*>(codes + e0) : nullptr;
         const uint32_t n4 = (uint32_t)((e1 - e0) >> 2), step = (uint32_t)nthr;
         cw.init((uint64_t)(e0 >> 2) + (uint64_t)tid, nthr, inner >> 2, nchan);
-        Recip R; float z = 0.f; uint32_t c_have = 0xffffffffu;      // channel constants: recomputed only when the channel changes
+        Recip R; float z = 0.f, gm = 1.f; uint32_t c_have = 0xffffffffu;      // channel constants: recomputed only when the channel changes
         auto body = [&](uint32_t j, const float4& wv, const float4& av) {
-            if (cw.c != c_have) { R = make_recip(__ldg(delta + cw.c)); z = __ldg(zp + cw.c); c_have = cw.c; }
+            if (cw.c != c_have) { R = make_recip(__ldg(delta + cw.c)); z = __ldg(zp + cw.c); if (gamma) gm = __ldg(gamma + cw.c); c_have = cw.c; }
             float4 y, q;
             AdaOut o;
             float rsum = 0.f;
@@ -86,6 +87,7 @@ __device__ __forceinline__ double ada_fwd_span(const float* __restrict__ w, cons
                 ONE(x) ONE(y) ONE(z) ONE(w)
 #undef ONE
             }
+            if (gamma) { y.x = __fmul_rn(y.x, gm); y.y = __fmul_rn(y.y, gm); y.z = __fmul_rn(y.z, gm); y.w = __fmul_rn(y.w, gm); }
             st_stream4(reinterpret_cast<float*>(y4 + j), y);
             if (c4) st_stream4(reinterpret_cast<float*>(c4 + j), q);
             if (REGON) acc += (double)rsum;
@@ -104,7 +106,7 @@ __device__ __forceinline__ double ada_fwd_span(const float* __restrict__ w, cons
         for (int64_t i = e0 + tid; i < e1; i += nthr) {
             const Recip R = make_recip(__ldg(delta + cw.c));
             const AdaOut o = ada_fwd_one<SOFT, REGON>(div_exact(w[i], R), alpha[i], R, __ldg(zp + cw.c), qmin, qmax, b);
-            wq[i] = o.y;
+            wq[i] = gamma ? __fmul_rn(o.y, __ldg(gamma + cw.c)) : o.y;
             if (codes) codes[i] = o.q;
             if (REGON) acc += (double)o.reg;
             cw.next();
@@ -268,6 +270,7 @@ round_reg_bwd_kernel(const float* __restrict__ v, int64_t n, const float* __rest
 
 // ---- multi-tensor ----------------------------------------------------------------------------
 struct MtTable { ssq_adaround_desc d[SSQ_MT_MAX]; };   // lives in kernel parameter space
+struct AffTable { ssq_affine_desc d[SSQ_MT_MAX]; };    // the layers' output affines (gamma^z, varphi^z), parallel to MtTable
 
 __device__ __forceinline__ int find_desc(const MtTable& table, int count, int64_t tile) {
     int lo = 0;
@@ -350,7 +353,8 @@ __device__ __forceinline__ int64_t iter_row(const IterState& S) {
 __global__ void __launch_bounds__(SSQ_THREADS, 4)
 iter_prologue_kernel(const __grid_constant__ IterState S, const float* __restrict__ cache, float* __restrict__ cur,
                      int64_t per_sample, int gather_tiles, bool gvec,
-                     const __grid_constant__ MtTable table, int count, int64_t total_tiles, int ada_ctas,
+                     const __grid_constant__ MtTable table, const __grid_constant__ AffTable aff, bool has_aff,
+                     int count, int64_t total_tiles, int ada_ctas,
                      float lambda, float* __restrict__ reg_out, WsView ws) {
     __shared__ double smem[32];
     __shared__ int s_which;
@@ -406,15 +410,62 @@ iter_prologue_kernel(const __grid_constant__ IterState S, const float* __restric
         const int64_t e0 = (tile - D.tile_begin) * SSQ_MT_TILE;
         const int64_t e1 = e0 + SSQ_MT_TILE < D.n ? e0 + SSQ_MT_TILE : D.n;
         const bool vec = desc_vec(D, false);
+        const float* gamma = has_aff ? aff.d[s_which].gamma : nullptr;
+        if (has_aff && tile == D.tile_begin) {          // the layer's first tile also folds the bias: b_eff = gamma*b + phi
+            const ssq_affine_desc& F = aff.d[s_which];
+            for (int64_t c = threadIdx.x; c < D.nchan; c += blockDim.x) {
+                const float bb = F.bias ? __ldg(F.bias + c) : 0.f;
+                F.beff[c] = __fadd_rn(__fmul_rn(bb, __ldg(F.gamma + c)), __ldg(F.phi + c));
+            }
+        }
         acc[0] += reg_on ? ada_fwd_span<true, true>(D.w, D.alpha, D.delta, D.zero_point, D.wq, nullptr, e0, e1, D.inner, D.nchan,
-                                                    D.qmin, D.qmax, b, threadIdx.x, blockDim.x, vec)
+                                                    D.qmin, D.qmax, b, threadIdx.x, blockDim.x, vec, gamma)
                          : ada_fwd_span<true, false>(D.w, D.alpha, D.delta, D.zero_point, D.wq, nullptr, e0, e1, D.inner, D.nchan,
-                                                     D.qmin, D.qmax, b, threadIdx.x, blockDim.x, vec);
+                                                     D.qmin, D.qmax, b, threadIdx.x, blockDim.x, vec, gamma);
     }
     if (!reg_out) return;
     block_sum<1>(acc, smem);
     if (grid_finish<1>(acc, ws, 0, slot, ada_ctas, smem) && threadIdx.x == 0)
         reg_out[0] = reg_on ? (float)((double)lambda * acc[0]) : 0.f;
+}
+
+// gradients of the folded output affine (quant_layer.py:258-259 under autograd): for layer l, output channel c
+//   d/d gamma = sum_k g_Weff[c,k] * W_q[c,k] + g_beff[c] * bias[c],   d/d phi = g_beff[c]
+// (W_eff = gamma W_q, b_eff = gamma bias + phi; g_beff = the bias gradient = sum over N,H,W of d loss / d out).
+// One warp per (layer, output channel); W_q is re-evaluated from (w, alpha) exactly as the forward did; fixed summation order.
+__global__ void __launch_bounds__(SSQ_THREADS)
+affine_grad_mt_kernel(const __grid_constant__ MtTable table, const __grid_constant__ AffTable aff, int count, int64_t total_rows,
+                      const float* __restrict__ b_dev) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (SSQ_THREADS / 32) + (threadIdx.x >> 5);
+    if (row >= total_rows) return;
+    int l = 0;
+    for (int i = 1; i < count; ++i) if (aff.d[i].row_begin <= row) l = i;
+    const ssq_adaround_desc& D = table.d[l];
+    const ssq_affine_desc& F = aff.d[l];
+    const int64_t c = row - F.row_begin, k = D.inner;       // channel-wise layers: inner = elements per output channel
+    const Recip R = make_recip(__ldg(D.delta + c));
+    const float z = __ldg(D.zero_point + c);
+    const float* __restrict__ w = D.w + c * k;
+    const float* __restrict__ a = D.alpha + c * k;
+    const float* __restrict__ g = D.gwq + c * k;
+    double acc = 0.0;
+    for (int64_t j0 = lane; j0 < k; j0 += 32 * 8) {
+        float sdot = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int64_t j = j0 + e * 32;
+            if (j < k) sdot = fmaf(g[j], ada_fwd_one<true, false>(div_exact(w[j], R), a[j], R, z, D.qmin, D.qmax, 0.f).y, sdot);
+        }
+        acc += (double)sdot;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+        const float gb = __ldg(F.gbeff + c);
+        F.ggamma[c] = (float)acc + (F.bias ? gb * __ldg(F.bias + c) : 0.f);
+        F.gphi[c] = gb;
+    }
+    (void)b_dev;
 }
 
 // Launch 3: gradient of every alpha (reconstruction + regulariser) AND its Adam step in one pass over (g_wq, w, alpha, m, v):
@@ -424,10 +475,11 @@ struct AdamArgs {
     float* flat; float* m; float* v;               // alpha lives at flat + off, its moments at m + off, v + off
     const float* lr; int64_t* step; unsigned int* ticket;
     double beta1, beta2, eps;
-    int store_grad;
+    int store_grad, apply_adam;                    // apply_adam == 0: gradients only (several GPUs: the exchange kernel steps)
 };
-__global__ void __launch_bounds__(SSQ_THREADS)
-ada_bwd_adam_mt_kernel(const __grid_constant__ MtTable table, int count, int64_t total_tiles,
+__global__ void __launch_bounds__(SSQ_THREADS, 4)
+ada_bwd_adam_mt_kernel(const __grid_constant__ MtTable table, const __grid_constant__ AffTable aff, bool has_aff,
+                       int count, int64_t total_tiles,
                        const float* __restrict__ b_dev, float lambda, const __grid_constant__ AdamArgs A) {
     __shared__ int s_which;
     __shared__ float s_step_size, s_bc2_sqrt;
@@ -457,34 +509,43 @@ ada_bwd_adam_mt_kernel(const __grid_constant__ MtTable table, int count, int64_t
         const int64_t e1 = e0 + SSQ_MT_TILE < D.n ? e0 + SSQ_MT_TILE : D.n;
         const int64_t off = D.alpha - A.flat;
         float* __restrict__ pa = A.flat + off;
-        float* __restrict__ pm = A.m + off;
-        float* __restrict__ pv = A.v + off;
+        float* __restrict__ pm = A.apply_adam ? A.m + off : pa;          // moments are untouched without the Adam step
+        float* __restrict__ pv = A.apply_adam ? A.v + off : pa;
         ChanWalk cw;
         if (desc_vec(D, true) && aligned16(pm) && aligned16(pv)) {
             const uint32_t n4 = (uint32_t)((e1 - e0) >> 2);
             cw.init((uint64_t)(e0 >> 2) + threadIdx.x, blockDim.x, D.inner >> 2, D.nchan);
-            // 4 vectors per thread (SSQ_MT_TILE / 4 / SSQ_THREADS), loads of all of them issued first
-            constexpr int NV = SSQ_MT_TILE / 4 / SSQ_THREADS;
+            // 4 vectors per thread (SSQ_MT_TILE / 4 / SSQ_THREADS), taken two at a time: 10 loads in flight per thread at 64
+            // registers / 4 resident CTAs (all 20 at once cost 128 registers, 2 CTAs: 0.67 of the HBM peak)
+            constexpr int NV = 2;
+#pragma unroll 1
+            for (int h = 0; h < SSQ_MT_TILE / 4 / SSQ_THREADS / NV; ++h) {
             float4 wv[NV], av[NV], gv[NV], mv[NV], vv[NV];
 #pragma unroll
             for (int u = 0; u < NV; ++u) {
-                const uint32_t j = threadIdx.x + u * SSQ_THREADS;
+                const uint32_t j = threadIdx.x + (h * NV + u) * SSQ_THREADS;
                 if (j < n4) {
                     const int64_t e = e0 + 4 * (int64_t)j;
                     wv[u] = ld_stream4(D.w + e); gv[u] = ld_stream4(D.gwq + e);
                     av[u] = *reinterpret_cast<const float4*>(pa + e);
-                    mv[u] = *reinterpret_cast<const float4*>(pm + e);
-                    vv[u] = *reinterpret_cast<const float4*>(pv + e);
+                    if (A.apply_adam) {
+                        mv[u] = *reinterpret_cast<const float4*>(pm + e);
+                        vv[u] = *reinterpret_cast<const float4*>(pv + e);
+                    }
                 }
             }
 #pragma unroll
             for (int u = 0; u < NV; ++u) {
-                const uint32_t j = threadIdx.x + u * SSQ_THREADS;
+                const uint32_t j = threadIdx.x + (h * NV + u) * SSQ_THREADS;
                 if (j < n4) {
                     const int64_t e = e0 + 4 * (int64_t)j;
                     const Recip R = make_recip(__ldg(D.delta + cw.c));
                     const float z = __ldg(D.zero_point + cw.c);
                     const float4 t = div4_exact(wv[u], R);
+                    if (has_aff) {                      // W_eff = gamma W_q: d loss / d W_q = gamma * g_Weff
+                        const float gm = __ldg(aff.d[s_which].gamma + cw.c);
+                        gv[u].x *= gm; gv[u].y *= gm; gv[u].z *= gm; gv[u].w *= gm;
+                    }
                     float4 g;
                     if (reg_on) {
                         g.x = ada_bwd_one<true, true>(gv[u].x, t.x, av[u].x, R, z, D.qmin, D.qmax, b, lam_g);
@@ -498,13 +559,16 @@ ada_bwd_adam_mt_kernel(const __grid_constant__ MtTable table, int count, int64_t
                         g.w = ada_bwd_one<true, false>(gv[u].w, t.w, av[u].w, R, z, D.qmin, D.qmax, b, lam_g);
                     }
                     if (A.store_grad) st_stream4(D.galpha + e, g);
-                    adam(av[u].x, g.x, mv[u].x, vv[u].x); adam(av[u].y, g.y, mv[u].y, vv[u].y);
-                    adam(av[u].z, g.z, mv[u].z, vv[u].z); adam(av[u].w, g.w, mv[u].w, vv[u].w);
-                    *reinterpret_cast<float4*>(pa + e) = av[u];
-                    *reinterpret_cast<float4*>(pm + e) = mv[u];
-                    *reinterpret_cast<float4*>(pv + e) = vv[u];
+                    if (A.apply_adam) {
+                        adam(av[u].x, g.x, mv[u].x, vv[u].x); adam(av[u].y, g.y, mv[u].y, vv[u].y);
+                        adam(av[u].z, g.z, mv[u].z, vv[u].z); adam(av[u].w, g.w, mv[u].w, vv[u].w);
+                        *reinterpret_cast<float4*>(pa + e) = av[u];
+                        *reinterpret_cast<float4*>(pm + e) = mv[u];
+                        *reinterpret_cast<float4*>(pv + e) = vv[u];
+                    }
                 }
                 cw.next();
+            }
             }
         } else {
             cw.init(e0 + threadIdx.x, blockDim.x, D.inner, D.nchan);
@@ -512,14 +576,16 @@ ada_bwd_adam_mt_kernel(const __grid_constant__ MtTable table, int count, int64_t
                 const Recip R = make_recip(__ldg(D.delta + cw.c));
                 const float z = __ldg(D.zero_point + cw.c);
                 const float u = div_exact(D.w[i], R);
-                const float g = reg_on ? ada_bwd_one<true, true>(D.gwq[i], u, pa[i], R, z, D.qmin, D.qmax, b, lam_g)
-                                       : ada_bwd_one<true, false>(D.gwq[i], u, pa[i], R, z, D.qmin, D.qmax, b, lam_g);
+                const float gin = has_aff ? D.gwq[i] * __ldg(aff.d[s_which].gamma + cw.c) : D.gwq[i];
+                const float g = reg_on ? ada_bwd_one<true, true>(gin, u, pa[i], R, z, D.qmin, D.qmax, b, lam_g)
+                                       : ada_bwd_one<true, false>(gin, u, pa[i], R, z, D.qmin, D.qmax, b, lam_g);
                 if (A.store_grad) D.galpha[i] = g;
-                adam(pa[i], g, pm[i], pv[i]);
+                if (A.apply_adam) adam(pa[i], g, pm[i], pv[i]);
                 cw.next();
             }
         }
     }
+    if (!A.apply_adam) return;
     // every CTA has read *step (thread 0, before the barrier above); the last one to arrive bumps it
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -639,8 +705,17 @@ extern "C" int ssq_fq_adaround_bwd_mt(const ssq_adaround_desc* table, int count,
 }
 
 
+static int fill_aff(AffTable& a, const ssq_affine_desc* aff, const ssq_adaround_desc* table, int count) {
+    for (int i = 0; i < count; ++i) {
+        if (!aff[i].gamma || !aff[i].phi || !aff[i].beff) return SSQ_ERR_NULL;
+        if (table[i].n % table[i].nchan != 0 || table[i].inner * table[i].nchan != table[i].n) return SSQ_ERR_MODE;   // per-output-channel layers only
+        a.d[i] = aff[i];
+    }
+    return SSQ_OK;
+}
+
 extern "C" int ssq_iter_prologue(const ssq_iter_state* st, const float* cache, float* cur_inp, int64_t per_sample,
-                                 const ssq_adaround_desc* table, int count, int64_t total_tiles,
+                                 const ssq_adaround_desc* table, const ssq_affine_desc* aff, int count, int64_t total_tiles,
                                  float lambda, float* reg_out, void* ws, size_t ws_bytes, void* stream) {
     if (!st || !st->step || !st->idx_table) return SSQ_ERR_NULL;
     if (st->n_steps <= 0 || st->batch < 0 || count < 0 || count > SSQ_MT_MAX || total_tiles < 0 || per_sample < 0) return SSQ_ERR_SIZE;
@@ -661,27 +736,50 @@ extern "C" int ssq_iter_prologue(const ssq_iter_state* st, const float* cache, f
     if (grid < 1) grid = 1;
     MtTable t;
     for (int i = 0; i < count; ++i) t.d[i] = table[i];
-    iter_prologue_kernel<<<(unsigned)grid, SSQ_THREADS, 0, (cudaStream_t)stream>>>(S, cache, cur_inp, per_sample, (int)gt, gvec, t, count,
-                                                                                   total_tiles, ada_ctas, lambda, reg_out, ws_view(ws, 1));
+    AffTable a;
+    if (aff) { if (int e = fill_aff(a, aff, table, count)) return e; }
+    iter_prologue_kernel<<<(unsigned)grid, SSQ_THREADS, 0, (cudaStream_t)stream>>>(S, cache, cur_inp, per_sample, (int)gt, gvec, t, a, aff != nullptr,
+                                                                                   count, total_tiles, ada_ctas, lambda, reg_out, ws_view(ws, 1));
     return launch_status();
 }
 
-extern "C" int ssq_fq_adaround_bwd_adam_mt(const ssq_adaround_desc* table, int count, int64_t total_tiles,
+extern "C" int ssq_fq_adaround_bwd_adam_mt(const ssq_adaround_desc* table, const ssq_affine_desc* aff, int count, int64_t total_tiles,
                                            const float* b_dev, float lambda,
                                            float* flat, float* exp_avg, float* exp_avg_sq, const float* lr_dev,
-                                           int64_t* step_dev, double beta1, double beta2, double eps, int store_grad,
+                                           int64_t* step_dev, double beta1, double beta2, double eps, int store_grad, int apply_adam,
                                            void* ws, size_t ws_bytes, void* stream) {
     if (count == 0 || total_tiles == 0) return SSQ_OK;
-    if (!table || !flat || !exp_avg || !exp_avg_sq || !lr_dev || !step_dev) return SSQ_ERR_NULL;
+    if (!table || !flat || !lr_dev || !step_dev || (apply_adam && (!exp_avg || !exp_avg_sq))) return SSQ_ERR_NULL;
+    if (!apply_adam && !store_grad) return SSQ_ERR_MODE;
     if (count < 0 || count > SSQ_MT_MAX || total_tiles < 0) return SSQ_ERR_SIZE;
     if (!ws || ws_bytes < ssq_ws_bytes(1)) return SSQ_ERR_WORKSPACE;
     for (int i = 0; i < count; ++i) if (!table[i].gwq || (store_grad && !table[i].galpha)) return SSQ_ERR_NULL;
     MtTable t;
     for (int i = 0; i < count; ++i) t.d[i] = table[i];
     // the last ticket of the fixed header is reserved for the iteration counter's hand-over
+    AffTable a;
+    if (aff) { if (int e = fill_aff(a, aff, table, count)) return e; }
     AdamArgs A{flat, exp_avg, exp_avg_sq, lr_dev, step_dev, reinterpret_cast<unsigned int*>(ws) + (SSQ_WS_TICKETS - 1),
-               beta1, beta2, eps, store_grad};
+               beta1, beta2, eps, store_grad, apply_adam};
     const unsigned grid = tile_grid(total_tiles, false);
-    ada_bwd_adam_mt_kernel<<<grid, SSQ_THREADS, 0, (cudaStream_t)stream>>>(t, count, total_tiles, b_dev, lambda, A);
+    ada_bwd_adam_mt_kernel<<<grid, SSQ_THREADS, 0, (cudaStream_t)stream>>>(t, a, aff != nullptr, count, total_tiles, b_dev, lambda, A);
+    return launch_status();
+}
+
+extern "C" int ssq_affine_grad_mt(const ssq_adaround_desc* table, const ssq_affine_desc* aff, int count, void* stream) {
+    if (count == 0) return SSQ_OK;
+    if (!table || !aff) return SSQ_ERR_NULL;
+    if (count < 0 || count > SSQ_MT_MAX) return SSQ_ERR_SIZE;
+    MtTable t; AffTable a;
+    for (int i = 0; i < count; ++i) t.d[i] = table[i];
+    if (int e = fill_aff(a, aff, table, count)) return e;
+    int64_t rows = 0;
+    for (int i = 0; i < count; ++i) {
+        if (!table[i].gwq || !aff[i].gbeff || !aff[i].ggamma || !aff[i].gphi) return SSQ_ERR_NULL;
+        if (aff[i].row_begin != rows) return SSQ_ERR_SIZE;
+        rows += table[i].nchan;
+    }
+    const int wpc = SSQ_THREADS / 32;
+    affine_grad_mt_kernel<<<(unsigned)((rows + wpc - 1) / wpc), SSQ_THREADS, 0, (cudaStream_t)stream>>>(t, a, count, rows, nullptr);
     return launch_status();
 }

@@ -11,7 +11,7 @@ namespace ssq {
 __global__ void __launch_bounds__(SSQ_THREADS)
 adam_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,
             int64_t n, const float* __restrict__ lr_dev, double beta1d, double beta2d, double epsd,
-            int64_t* step_dev, unsigned int* ticket /* nullable: non-null = *step_dev counts COMPLETED iterations */) {
+            int64_t* step_dev, unsigned int* ticket /* nullable: non-null = end the iteration */, int t_offset) {
     // Python-double scalars, cast to fp32 by ATen when they meet an fp32 tensor
     const float w1 = (float)(1.0 - beta1d);   // lerp weight (< 0.5 => m + w*(g-m))
     const float w2 = (float)(1.0 - beta2d);
@@ -37,7 +37,7 @@ adam_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __
     // evaluated by one thread per CTA while the tile's loads are in flight
     __shared__ float s_step_size, s_bc2_sqrt;
     if (threadIdx.x == 0) {
-        const double t = (double)(*step_dev + (ticket ? 1 : 0));
+        const double t = (double)(*step_dev + t_offset);
         const double bc1 = 1.0 - pow(beta1d, t);
         const double bc2 = 1.0 - pow(beta2d, t);
         s_step_size = (float)((double)__ldg(lr_dev) / bc1);
@@ -234,14 +234,14 @@ using namespace ssq;
 
 static int adam_launch(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                        const float* lr_dev, double beta1, double beta2, double eps,
-                       int64_t* step_dev, unsigned int* ticket, void* stream) {
+                       int64_t* step_dev, unsigned int* ticket, int t_offset, void* stream) {
     if (!param || !grad || !exp_avg || !exp_avg_sq || !lr_dev || !step_dev) return SSQ_ERR_NULL;
     if (n < 0) return SSQ_ERR_SIZE;
     const bool vec = aligned16(param) && aligned16(grad) && aligned16(exp_avg) && aligned16(exp_avg_sq);
     unsigned grid = vec ? tile_grid(((n >> 2) + SSQ_THREADS * 2 - 1) / (SSQ_THREADS * 2), false)
                         : (unsigned)grid_for((n + SSQ_THREADS - 1) / SSQ_THREADS);
     if (grid < 1) grid = 1;
-    adam_kernel<<<grid, SSQ_THREADS, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr_dev, beta1, beta2, eps, step_dev, ticket);
+    adam_kernel<<<grid, SSQ_THREADS, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr_dev, beta1, beta2, eps, step_dev, ticket, t_offset);
     return launch_status();
 }
 
@@ -249,7 +249,14 @@ extern "C" int ssq_adam_step(float* param, const float* grad, float* exp_avg, fl
                              const float* lr_dev, double beta1, double beta2, double eps,
                              const int64_t* step_dev, void* stream) {
     if (n == 0) return SSQ_OK;
-    return adam_launch(param, grad, exp_avg, exp_avg_sq, n, lr_dev, beta1, beta2, eps, const_cast<int64_t*>(step_dev), nullptr, stream);
+    return adam_launch(param, grad, exp_avg, exp_avg_sq, n, lr_dev, beta1, beta2, eps, const_cast<int64_t*>(step_dev), nullptr, 0, stream);
+}
+
+extern "C" int ssq_adam_step_pending(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                     const float* lr_dev, double beta1, double beta2, double eps,
+                                     const int64_t* step_dev, void* stream) {
+    if (n == 0) return SSQ_OK;
+    return adam_launch(param, grad, exp_avg, exp_avg_sq, n, lr_dev, beta1, beta2, eps, const_cast<int64_t*>(step_dev), nullptr, 1, stream);
 }
 
 extern "C" int ssq_adam_step_end_iteration(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
@@ -257,7 +264,7 @@ extern "C" int ssq_adam_step_end_iteration(float* param, const float* grad, floa
                                            int64_t* step_dev, void* ws, size_t ws_bytes, void* stream) {
     if (!ws || ws_bytes < ssq_ws_bytes(1)) return SSQ_ERR_WORKSPACE;
     return adam_launch(param, grad, exp_avg, exp_avg_sq, n, lr_dev, beta1, beta2, eps, step_dev,
-                       reinterpret_cast<unsigned int*>(ws) + (SSQ_WS_TICKETS - 1), stream);
+                       reinterpret_cast<unsigned int*>(ws) + (SSQ_WS_TICKETS - 1), 1, stream);
 }
 
 extern "C" int ssq_loop_advance(int64_t* step_dev, const int64_t* idx_table, int64_t* idx_live, int batch,

@@ -90,7 +90,7 @@ class ReconEngine:
                  act_quantizers: Sequence[nn.Module] = (), use_graph: Optional[bool] = None,
                  idx_table: Optional[torch.Tensor] = None, verbose: bool = True,
                  host_resident: bool = False, device: Optional[torch.device] = None, host_stage: str = 'pull',
-                 scaling: str = 'weak', host_pack: Optional[bool] = None):
+                 scaling: str = 'weak', host_pack: Optional[bool] = None, fold_output_affine: bool = False):
         """host_resident=True keeps the cached features in (pinned) host memory, as the reference does with
         keep_gpu=False (quant/data_utils.py:34-36, `cached_inps[idx].to(device)` at block_recon.py:91-92): every
         step moves its mini-batch rows host->device. host_stage='pull' (default): a kernel inside the captured
@@ -104,8 +104,13 @@ class ReconEngine:
         'strong' = the ranks split ONE global mini-batch of `batch_size` (every rank holds the whole cache and the same
         index table, rank r takes columns [r*b, (r+1)*b)); the loss gradient is scaled by 1/R and the regulariser counted
         once, so the summed gradient equals the single-GPU gradient up to summation order and the trajectory is the
-        1-GPU trajectory."""
+        1-GPU trajectory.
+        fold_output_affine (weight phase; README --bias_cal): every layer's output-channel scale gamma^z (alpha_out) and
+        offset varphi^z (beta_out) is learned with the alphas, FOLDED into the weight launch: W_eff = gamma_oc W_q,
+        b_eff = gamma b + varphi (quant_layer.py:258-259 up to fp32 rounding; no activation-sized pass), their gradients
+        from the weight / bias gradients of the folded layer (ssq_affine_grad_mt)."""
         self.unit, self.modules = unit, list(modules)
+        self.fold_affine = bool(fold_output_affine) and not act_quant
         self.sym = None
         self.host_resident = bool(host_resident)
         if scaling not in ('weak', 'strong'):
@@ -194,15 +199,20 @@ class ReconEngine:
     def _setup_weight_phase(self):
         qs = [m.weight_quantizer for m in self.modules]
         sizes = [_pad4(q.alpha.numel()) for q in qs]
+        n_alpha = sum(sizes)
+        ocs = [_pad4(m.weight.shape[0]) for m in self.modules] if self.fold_affine else []
+        total = n_alpha + 2 * sum(ocs)                  # [alphas | gammas | varphis]
         # several GPUs: parameter and gradient buffers in symmetric memory, exchanged by one peer-memory kernel
-        self.sym = ssq_dist.symmetric_unit_or_none(sum(sizes), self.dev) if self.multi_gpu else None
+        self.sym = ssq_dist.symmetric_unit_or_none(total, self.dev) if self.multi_gpu else None
         if self.sym is not None:
             self.flat, self.gflat = self.sym.flat, self.sym.gflat
         else:
-            self.flat = torch.zeros(sum(sizes), device=self.dev)
+            self.flat = torch.zeros(total, device=self.dev)
             self.gflat = torch.zeros_like(self.flat)
-        entries, self.wq_leaves, off = [], [], 0
-        for m, q, sz in zip(self.modules, qs, sizes):
+        self.n_alpha = n_alpha
+        entries, self.wq_leaves, self.bias_leaves, off = [], [], [], 0
+        g_off, p_off = n_alpha, n_alpha + sum(ocs)
+        for i, (m, q, sz) in enumerate(zip(self.modules, qs, sizes)):
             n = q.alpha.numel()
             view = self.flat[off:off + n].view(q.alpha.shape)
             view.copy_(q.alpha.detach())
@@ -210,10 +220,23 @@ class ReconEngine:
             wq = torch.empty_like(m.weight, memory_format=torch.contiguous_format).requires_grad_(True)
             self.wq_leaves.append(wq)
             m._engine_weight = wq
-            entries.append(dict(w=m.weight.detach(), alpha=view, delta=q.delta.detach(),
-                                zero_point=ops.match_param(q.zero_point.detach(), q.delta.detach()), wq=wq.detach(),
-                                galpha=self.gflat[off:off + n].view(q.alpha.shape),
-                                qmin=0.0, qmax=float(q.n_levels - 1)))
+            e = dict(w=m.weight.detach(), alpha=view, delta=q.delta.detach(),
+                     zero_point=ops.match_param(q.zero_point.detach(), q.delta.detach()), wq=wq.detach(),
+                     galpha=self.gflat[off:off + n].view(q.alpha.shape),
+                     qmin=0.0, qmax=float(q.n_levels - 1))
+            if self.fold_affine:
+                oc = m.weight.shape[0]
+                gam, phi = self.flat[g_off:g_off + oc], self.flat[p_off:p_off + oc]
+                gam.copy_(m.alpha_out.detach().reshape(-1)); phi.copy_(m.beta_out.detach().reshape(-1))
+                m.alpha_out = nn.Parameter(gam.view(m.alpha_out.shape), requires_grad=False)
+                m.beta_out = nn.Parameter(phi.view(m.beta_out.shape), requires_grad=False)
+                beff = torch.empty(oc, device=self.dev).requires_grad_(True)
+                self.bias_leaves.append(beff)
+                m._engine_bias = beff
+                e.update(gamma=gam, phi=phi, bias=None if m.bias is None else m.bias.detach().contiguous(), beff=beff.detach(),
+                         ggamma=self.gflat[g_off:g_off + oc], gphi=self.gflat[p_off:p_off + oc])
+                g_off += ocs[i]; p_off += ocs[i]
+            entries.append(e)
             off += sz
         self.table = ops.AdaRoundTable(entries)
 
@@ -267,10 +290,19 @@ class ReconEngine:
                 packed = torch.stack([torch.zeros((), device=self.dev) if g is None else g.reshape(()) for g in grads])
                 self.gflat[:packed.numel()].copy_(packed)
         else:
-            gwqs = torch.autograd.grad([out], self.wq_leaves, [dpred.view_as(out)])
+            grads = torch.autograd.grad([out], self.wq_leaves + self.bias_leaves, [dpred.view_as(out)])
+            gwqs = grads[:len(self.wq_leaves)]
+            if self.fold_affine:                         # d/d gamma, d/d varphi: needs the alphas the forward used
+                self.table.affine_grad(gwqs, grads[len(self.wq_leaves):])
             if not self.multi_gpu:
+                na = self.n_alpha
                 self.table.backward_adam(gwqs, self.b_live, self.weight * self.reg_share, self.flat, self.exp_avg,
                                          self.exp_avg_sq, self.lr_live, self.step_dev, store_grad=self.keep_grad)
+                if self.fold_affine:                     # second parameter group; the counter already reads t (1-based)
+                    ops.adam_step(self.flat[na:], self.gflat[na:], self.exp_avg[na:], self.exp_avg_sq[na:], self.lr_live, self.step_dev)
+            elif self.sym is not None or self.fold_affine:
+                self.table.backward_adam(gwqs, self.b_live, self.weight * self.reg_share, self.flat, None, None,
+                                         self.lr_live, self.step_dev, apply_adam=False)
             else:
                 self.table.backward(gwqs, self.b_live, self.weight * self.reg_share)
         if self.multi_gpu and getattr(self, 'sym', None) is not None:
@@ -451,6 +483,11 @@ class ReconEngine:
             self.sym.check()
         for m in self.modules:
             m._engine_weight = None
+            m._engine_bias = None
+            if self.fold_affine:
+                m._affine_key = None                     # gamma / varphi moved: re-derive "is identity"
+                for name in ('alpha_out', 'beta_out'):
+                    getattr(m, name).requires_grad_(True)
         for q, flag in self._frozen:
             q.requires_grad_(flag)
         if self.act_quant:

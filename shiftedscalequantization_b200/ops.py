@@ -12,7 +12,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import AdaRoundDesc, IterState, MT_MAX, MT_TILE, SHIFT_ADASHIFT, SHIFT_DEQUANT
+from ._lib import AdaRoundDesc, AffineDesc, IterState, MT_MAX, MT_TILE, SHIFT_ADASHIFT, SHIFT_DEQUANT
 
 # --------------------------------------------------------------------------------------- plumbing
 _launch_count = 0          # kernels launched through this module (bench.py reports it)
@@ -290,6 +290,22 @@ class AdaRoundTable:
             tile += (w.numel() + MT_TILE - 1) // MT_TILE
         self.total_tiles = tile
         self.device = entries[0]["w"].device
+        # folded output affine (gamma^z / varphi^z): every entry then carries gamma, phi, bias (or None), beff, ggamma, gphi
+        self.aff = None
+        if entries[0].get("gamma") is not None:
+            self.aff = (AffineDesc * self.count)()
+            rows = 0
+            for i, e in enumerate(entries):
+                f = self.aff[i]
+                f.gamma, f.phi = _req(e["gamma"], "gamma").data_ptr(), _req(e["phi"], "phi").data_ptr()
+                f.bias = _ptr(e.get("bias"))
+                f.beff = e["beff"].data_ptr()
+                f.gbeff = 0
+                f.ggamma, f.gphi = e["ggamma"].data_ptr(), e["gphi"].data_ptr()
+                f.row_begin = rows
+                rows += self.table[i].nchan
+                if self.table[i].nchan != e["gamma"].numel():
+                    raise _lib.SsqError("the folded output affine needs per-output-channel weight quantisers")
 
     def forward(self, soft: bool, b_dev=None, lam: float = 0.0, reg_out=None):
         ws = workspace(self.device, _lib.load().ssq_ws_bytes(1), "mt") if reg_out is not None else None
@@ -304,15 +320,23 @@ class AdaRoundTable:
               torch.cuda.current_stream(self.device).cuda_stream)
 
     def backward_adam(self, gwqs: Sequence[torch.Tensor], b_dev, lam: float, flat, exp_avg, exp_avg_sq, lr_dev, step_dev,
-                      betas=(0.9, 0.999), eps=1e-8, store_grad=False):
-        """gradient of every alpha + its Adam step + end of the iteration (*step_dev += 1) in one launch"""
+                      betas=(0.9, 0.999), eps=1e-8, store_grad=False, apply_adam=True):
+        """gradient of every alpha + its Adam step + end of the iteration (*step_dev += 1) in one launch;
+        apply_adam=False: gradients only (written to galpha), for the multi-GPU exchange"""
         for i, g in enumerate(gwqs):
             self.table[i].gwq = _req(g, "gwq").data_ptr()
         ws = workspace(self.device, _lib.load().ssq_ws_bytes(1), "mt")
-        _call("ssq_fq_adaround_bwd_adam_mt", self.table, self.count, self.total_tiles, _ptr(b_dev), float(lam),
-              flat.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), lr_dev.data_ptr(), step_dev.data_ptr(),
-              float(betas[0]), float(betas[1]), float(eps), int(bool(store_grad)), ws.data_ptr(), ws.numel(),
-              torch.cuda.current_stream(self.device).cuda_stream)
+        _call("ssq_fq_adaround_bwd_adam_mt", self.table, self.aff, self.count, self.total_tiles, _ptr(b_dev), float(lam),
+              flat.data_ptr(), _ptr(exp_avg), _ptr(exp_avg_sq), lr_dev.data_ptr(), step_dev.data_ptr(),
+              float(betas[0]), float(betas[1]), float(eps), int(bool(store_grad) or not apply_adam), int(bool(apply_adam)),
+              ws.data_ptr(), ws.numel(), torch.cuda.current_stream(self.device).cuda_stream)
+
+    def affine_grad(self, gwqs: Sequence[torch.Tensor], gbeffs: Sequence[torch.Tensor]):
+        """gradients of the folded gamma / varphi from the folded layer's weight and bias gradients (before alpha moves)"""
+        for i, (g, gb) in enumerate(zip(gwqs, gbeffs)):
+            self.table[i].gwq = _req(g, "gwq").data_ptr()
+            self.aff[i].gbeff = _req(gb, "gbeff").data_ptr()
+        _call("ssq_affine_grad_mt", self.table, self.aff, self.count, torch.cuda.current_stream(self.device).cuda_stream)
 
 
 class IterationState:
@@ -331,7 +355,8 @@ def iter_prologue(state: IterationState, cache, cur_inp, table: Optional[AdaRoun
     per_sample = 0 if cache is None else cache.numel() // cache.shape[0]
     ws = workspace(state.device, _lib.load().ssq_ws_bytes(1), "mt") if reg_out is not None else None
     _call("ssq_iter_prologue", C.byref(state.c), _ptr(cache), _ptr(cur_inp) if cache is not None else None, per_sample,
-          table.table if table is not None else None, table.count if table is not None else 0,
+          table.table if table is not None else None, table.aff if table is not None else None,
+          table.count if table is not None else 0,
           table.total_tiles if table is not None else 0, float(lam), _ptr(reg_out), _ptr(ws), 0 if ws is None else ws.numel(),
           torch.cuda.current_stream(state.device).cuda_stream)
 
@@ -639,6 +664,14 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, lr_dev, step_dev, betas=(0.9, 0.
     if param.numel() == 0:
         return
     _call("ssq_adam_step", param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel(),
+          lr_dev.data_ptr(), float(betas[0]), float(betas[1]), float(eps), step_dev.data_ptr(), _stream(param))
+
+
+def adam_step_pending(param, grad, exp_avg, exp_avg_sq, lr_dev, step_dev, betas=(0.9, 0.999), eps=1e-8):
+    """adam_step with t = *step_dev + 1 that leaves the iteration open (a parameter group stepped before the launch that ends it)"""
+    if param.numel() == 0:
+        return
+    _call("ssq_adam_step_pending", param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel(),
           lr_dev.data_ptr(), float(betas[0]), float(betas[1]), float(eps), step_dev.data_ptr(), _stream(param))
 
 

@@ -91,7 +91,10 @@ def reconstruct_unit(model, unit, cali_data, *, is_block, batch_size, iters, wei
         cached_grads = save_grad_data(model, unit, cali_data, act_quant, batch_size=batch_size, keep_gpu=keep_gpu) \
             if opt_mode != 'mse' else None
     if iters > 0:
-        if bias_cal and not act_quant:
+        foldable = all(m.weight_quantizer.delta.numel() == m.weight.shape[0] and m.se_module is None for m in modules) \
+            if (bias_cal and not act_quant) else False
+        if bias_cal and not act_quant and (bias_cal == 'exact' or not foldable):
+            # the reference expression itself, out*alpha_out + beta_out on the activation (two roundings), under autograd
             if opt_mode != 'mse':
                 raise NotImplementedError('bias_cal is defined for the mse reconstruction loss')
             _run_with_output_affine(unit, modules, cached_inps.to(device), cached_outs.to(device), iters=iters, weight=weight, b_range=b_range,
@@ -100,7 +103,7 @@ def reconstruct_unit(model, unit, cali_data, *, is_block, batch_size, iters, wei
             engine = ReconEngine(unit, modules, cached_inps, cached_outs, cached_grads, act_quant=act_quant, iters=iters,
                                  weight=weight, b_range=b_range, warmup=warmup, p=p, lr=lr, opt_mode=opt_mode,
                                  batch_size=batch_size, multi_gpu=multi_gpu, act_quantizers=act_quantizers, scaling=scaling,
-                                 host_resident=host_resident, device=device)
+                                 host_resident=host_resident, device=device, fold_output_affine=bool(bias_cal) and not act_quant)
             try:
                 engine.run()
                 LAST_RUN_STATS.update(iters=iters, loop_ms=engine.loop_ms(), launches_per_iter=engine.launches_per_iter)
@@ -124,7 +127,9 @@ def block_reconstruction(model: QuantModel, block: BaseQuantBlock, cali_data: to
                          host_resident: bool = False):
     """Optimise the rounding (or, with act_quant, the activation step sizes) of every layer in `block` so the
     block output matches the FP block output on the calibration data. Arguments as upstream; `bias_cal` (README flag,
-    keyword-only in practice) additionally learns every layer's output-channel scale/offset in the weight phase;
+    keyword-only in practice) additionally learns every layer's output-channel scale/offset in the weight phase — True: folded
+    into the weight launch of the 3-launch engine (W_eff = gamma W_q, b_eff = gamma b + varphi; equal to the reference
+    expression up to fp32 rounding), 'exact': the reference's out*alpha_out+beta_out on the activation under autograd;
     `scaling` ('weak' | 'strong') picks the multi-GPU partitioning (engine.ReconEngine); `host_resident=True` keeps the cached
     features in pinned host memory (upstream's keep_gpu=False, quant/data_utils.py:34-36) and pulls every mini-batch over PCIe."""
     reconstruct_unit(model, block, cali_data, is_block=True, batch_size=batch_size, iters=iters, weight=weight,

@@ -210,6 +210,7 @@ class QuantModule(nn.Module):
         self._affine_identity = True
         self.train_output_affine = False    # True while gamma^z / varphi^z are being learned: always apply the affine
         self._engine_weight = None      # set by ReconEngine: weight already produced by a multi-tensor launch
+        self._engine_bias = None        # set by ReconEngine when the output affine is folded: gamma*bias + varphi
         self.selection = None
         self.selectionInited = False
         self.pathName = ''
@@ -230,13 +231,15 @@ class QuantModule(nn.Module):
         if self.cache_features == 'if':
             self.cached_inp_features += [input.cpu().clone().detach()]
         quantized = self.use_weight_quant and self.cache_features == 'none'
+        folded = False
         if quantized:
             weight = self._engine_weight if self._engine_weight is not None else self.weight_quantizer(self.weight)
-            bias = self.bias
+            folded = self._engine_weight is not None and self._engine_bias is not None
+            bias = self._engine_bias if folded else self.bias      # folded: W_eff = gamma W_q, b_eff = gamma b + varphi
         else:
             weight, bias = self.org_weight, self.org_bias
         out = self.fwd_func(input, weight, bias, **self.fwd_kwargs)
-        if quantized and (self.train_output_affine or not self._output_affine_is_identity()):
+        if quantized and not folded and (self.train_output_affine or not self._output_affine_is_identity()):
             out = ops.ChanAffine.apply(out, self.alpha_out, self.beta_out)
         if self.se_module is not None:
             out = self.se_module(out)

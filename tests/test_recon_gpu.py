@@ -431,6 +431,93 @@ def test_bias_cal_matches_reference_autograd():
         assert torch.isfinite(blk(torch.randn(2, 64, 8, 8, device='cuda'))).all()
 
 
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_bias_cal_folded_into_the_weight_launch_matches_reference_autograd(use_graph):
+    """--bias_cal on the 3-launch engine: gamma^z / varphi^z folded into the weight launch (W_eff = gamma W_q,
+    b_eff = gamma b + varphi), their gradients from the folded layer's weight / bias gradients (ssq_affine_grad_mt).
+    Same golden as the exact path: the real reference's forward / autograd / LossFunction / Adam
+    (tests/golden/make_golden_bias_cal.py), its cached features and index stream."""
+    from conftest import golden
+    from shiftedscalequantization_b200.engine import ReconEngine
+    from shiftedscalequantization_b200.quant.adaptive_rounding import AdaRoundQuantizer
+    from shiftedscalequantization_b200 import quant as Q, zoo
+    g = golden("bias_cal")
+    iters, bs = int(g["iters"]), int(g["bs"])
+    torch.manual_seed(1005)
+    cnn = zoo.resnet18(num_classes=10).cuda().eval()
+    qnn = Q.QuantModel(cnn, {'n_bits': 2, 'channel_wise': True, 'scale_method': 'max'}, dict(AQ)).cuda().eval()
+    qnn.set_first_last_layer_to_8bit()
+    cali = torch.from_numpy(g["cali"])
+    qnn.set_quant_state(True, False)
+    with torch.no_grad():
+        qnn(cali.cuda())
+    block = qnn.model.layer2[0]
+    qnn.set_quant_state(False, False); block.set_quant_state(True, False)
+    mods = [(n, m) for n, m in block.named_modules() if isinstance(m, Q.QuantModule)]
+    for _n, m in mods:
+        m.weight_quantizer = AdaRoundQuantizer(uaq=m.weight_quantizer, round_mode='learned_hard_sigmoid',
+                                               weight_tensor=m.org_weight.data)
+        m.weight_quantizer.soft_targets = True
+    inps, outs = torch.from_numpy(g["inps"]).cuda(), torch.from_numpy(g["outs"]).cuda()
+    eng = ReconEngine(block, [m for _n, m in mods], inps, outs, None, act_quant=False, iters=iters, weight=0.01, b_range=(20, 2),
+                      warmup=0.2, p=2.0, batch_size=bs, use_graph=use_graph, idx_table=torch.from_numpy(g["idx"]), verbose=False,
+                      fold_output_affine=True)
+    # first-iteration gradients of gamma / varphi against the reference's autograd (eager step, then roll back)
+    snap = eng._snapshot()
+    eng.keep_grad = True
+    eng._iteration()
+    for n, m in mods:
+        i = [mm for _n, mm in mods].index(m)
+        e = eng.table.keep[i]
+        assert_close(host_(e["ggamma"]), g[f"{n}.g_alpha_out0"].reshape(-1), rtol=1e-4, what=f"{n} d/d alpha_out, iteration 0")
+        assert_close(host_(e["gphi"]), g[f"{n}.g_beta_out0"].reshape(-1), rtol=1e-4, what=f"{n} d/d beta_out, iteration 0")
+    eng._restore(snap)
+    eng.keep_grad = False
+    losses = []
+    if use_graph:
+        eng.capture()
+    for i in range(iters):
+        eng.step()
+        losses.append(float(eng.loss_dev) + float(eng.reg_dev))
+    assert eng.launches_per_iter == 5          # prologue, loss, affine gradients, backward + Adam, Adam of gamma / varphi
+    eng.close()
+    assert_close(np.array(losses), g["losses"], rtol=2e-3, what="total loss per iteration vs reference")
+    for n, m in mods:
+        for name, ours in (("alpha", m.weight_quantizer.alpha), ("alpha_out", m.alpha_out), ("beta_out", m.beta_out)):
+            assert tuple(ours.shape) == tuple(g[f"{n}.{name}"].shape), (n, name)
+            err = np.abs(ours.detach().cpu().numpy() - g[f"{n}.{name}"])
+            assert (err <= 2e-3).mean() >= 0.999 and err.max() <= 2 * 1e-3 * iters, (n, name, err.max())
+        assert (np.sign(m.weight_quantizer.alpha.detach().cpu().numpy()) == np.sign(g[f"{n}.alpha"])).mean() > 0.9995
+        m.weight_quantizer.soft_targets = False
+    with torch.no_grad():
+        out = block(inps[:8]).cpu().numpy()               # module path now: hard weights, out*alpha_out + beta_out on the activation
+    assert np.abs(out - g["hard_out"]).max() <= 5e-3 * np.abs(g["hard_out"]).max()
+
+
+def host_(t):
+    return t.detach().cpu().numpy()
+
+
+def test_bias_cal_exact_and_folded_public_paths_agree():
+    """block_reconstruction(bias_cal=True) (folded, 3-launch engine) and bias_cal='exact' (the reference expression on the
+    activation under autograd) follow the same trajectory up to the fp32 rounding of the fold"""
+    res = {}
+    for mode in (True, 'exact'):
+        Q, qnn, cali = build_qnn()
+        blk = qnn.model.layer1[0]
+        torch.manual_seed(3)
+        Q.block_reconstruction(qnn, blk, cali_data=cali, iters=24, weight=0.01, asym=True, b_range=(20, 2), warmup=0.2,
+                               act_quant=False, opt_mode='mse', batch_size=16, bias_cal=mode)
+        assert not bool((blk.conv1.alpha_out.detach() == 1).all()) and blk.conv1.weight_quantizer.soft_targets is False
+        res[mode] = [t.detach().clone() for t in (blk.conv1.weight_quantizer.alpha, blk.conv1.alpha_out, blk.conv1.beta_out,
+                                                  blk.conv2.weight_quantizer.alpha, blk.conv2.alpha_out, blk.conv2.beta_out)]
+        with torch.no_grad():
+            assert torch.isfinite(blk(torch.randn(2, 64, 8, 8, device='cuda'))).all()
+    for a, b in zip(res[True], res['exact']):
+        err = (a - b).abs()
+        assert float((err <= 2e-3).float().mean()) >= 0.999 and float(err.max()) <= 2 * 24 * 1.05e-3
+
+
 def test_checkpoint_round_trip_through_eval_rebuild():
     """upstream's checkpoint protocol (main_cifar10.py:86,106; myProject.py:43,69-73): torch.save(qnn.state_dict()), later
     rebuild the module structure with `eval=True` reconstruction calls (AdaRound quantisers swapped in, nothing learned,
