@@ -341,14 +341,17 @@ int ssq_adam_step_end_iteration(float* param, const float* grad, float* exp_avg,
  * buffer; then it ends the iteration (*step_dev += 1). n must be a multiple of 4. Every rank must
  * launch it with the same n and world. reduced_shard_out (nullable): the summed gradient shard.
  * *timeouts is incremented if a peer does not arrive within ~2^25 polls (results are then
- * undefined; the caller raises instead of hanging the device). */
+ * undefined; the caller raises instead of hanging the device). epochs: ssq_exchange_pad_bytes()/32
+ * zeroed uint32 in LOCAL device memory (per-CTA launch counters), owned by the caller for the life
+ * of the symmetric buffers. */
 size_t ssq_exchange_pad_bytes(void);
 int64_t ssq_exchange_shard_elems(int64_t n, int world);
 int ssq_grad_exchange_adam(float* const* flat_ptrs, const float* const* grad_ptrs, uint32_t* const* pad_ptrs,
                            int rank, int world, int64_t n,
                            float* exp_avg_shard, float* exp_avg_sq_shard,
                            const float* lr_dev, int64_t* step_dev, double beta1, double beta2, double eps,
-                           float* reduced_shard_out, unsigned int* timeouts, void* ws, size_t ws_bytes, void* stream);
+                           float* reduced_shard_out, unsigned int* timeouts, uint32_t* epochs,
+                           void* ws, size_t ws_bytes, void* stream);
 
 /* ---- calibration loop plumbing -----------------------------------------------------------
  * gather rows of a cached feature tensor: dst[n] = src[index[n]] (quant/block_recon.py:91) */

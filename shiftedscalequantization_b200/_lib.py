@@ -89,7 +89,7 @@ PROTOTYPES = {
     "ssq_affine_grad_mt": (_i32, [C.POINTER(AdaRoundDesc), C.POINTER(AffineDesc), _i32, _p]),
     "ssq_exchange_pad_bytes": (_sz, []),
     "ssq_exchange_shard_elems": (_i64, [_i64, _i32]),
-    "ssq_grad_exchange_adam": (_i32, [_p, _p, _p, _i32, _i32, _i64, _p, _p, _p, _p, _d, _d, _d, _p, _p, _p, _sz, _p]),
+    "ssq_grad_exchange_adam": (_i32, [_p, _p, _p, _i32, _i32, _i64, _p, _p, _p, _p, _d, _d, _d, _p, _p, _p, _p, _sz, _p]),
     "ssq_gather_rows": (_i32, [_p, _p, _p, _i64, _i64, _p]),
     "ssq_packed_row_bytes": (_i64, [_i64, _i32]),
     "ssq_export_codes": (_i32, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _f, _f, _i32, _p]),

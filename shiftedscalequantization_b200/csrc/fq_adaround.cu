@@ -482,24 +482,14 @@ ada_bwd_adam_mt_kernel(const __grid_constant__ MtTable table, const __grid_const
                        int count, int64_t total_tiles,
                        const float* __restrict__ b_dev, float lambda, const __grid_constant__ AdamArgs A) {
     __shared__ int s_which;
-    __shared__ float s_step_size, s_bc2_sqrt;
+    __shared__ AdamConst s_c;
     const float b = b_dev ? __ldg(b_dev) : 0.f;
     const bool reg_on = b_dev && (b > 0.f);
     const float lam_g = reg_on ? lambda : 0.f;
-    if (threadIdx.x == 0) {
-        const double t = (double)(*A.step + 1);
-        s_step_size = (float)((double)__ldg(A.lr) / (1.0 - pow(A.beta1, t)));
-        s_bc2_sqrt = (float)sqrt(1.0 - pow(A.beta2, t));
-    }
-    const float w1 = (float)(1.0 - A.beta1), w2 = (float)(1.0 - A.beta2), beta2 = (float)A.beta2, eps = (float)A.eps;
+    if (threadIdx.x == 0) s_c = adam_const(A.beta1, A.beta2, A.eps, (double)(*A.step + 1), __ldg(A.lr));
     __syncthreads();
-    const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
-    auto adam = [&](float& p, float g, float& mm, float& vv) {
-        mm = mm + w1 * (g - mm);
-        vv = vv * beta2 + w2 * g * g;
-        const float denom = sqrtf(vv) / bc2_sqrt + eps;
-        p = p - step_size * (mm / denom);
-    };
+    const AdamConst c = s_c;
+    auto adam = [&](float& p, float g, float& mm, float& vv) { adam_update(p, g, mm, vv, c); };
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         __syncthreads();
         if (threadIdx.x == 0) s_which = find_desc(table, count, tile);

@@ -12,10 +12,6 @@ __global__ void __launch_bounds__(SSQ_THREADS)
 adam_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,
             int64_t n, const float* __restrict__ lr_dev, double beta1d, double beta2d, double epsd,
             int64_t* step_dev, unsigned int* ticket /* nullable: non-null = end the iteration */, int t_offset) {
-    // Python-double scalars, cast to fp32 by ATen when they meet an fp32 tensor
-    const float w1 = (float)(1.0 - beta1d);   // lerp weight (< 0.5 => m + w*(g-m))
-    const float w2 = (float)(1.0 - beta2d);
-    const float beta2 = (float)beta2d, eps = (float)epsd;
     const bool vec = aligned16(param) && aligned16(grad) && aligned16(m) && aligned16(v);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     // address-ordered tiles of SSQ_THREADS*U float4s, one per CTA (ssq_common.cuh): 8 loads in flight per thread
@@ -35,22 +31,11 @@ adam_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __
     }
     // host-side doubles of torch/optim/adam.py (_single_tensor_adam): bias corrections from the device step count,
     // evaluated by one thread per CTA while the tile's loads are in flight
-    __shared__ float s_step_size, s_bc2_sqrt;
-    if (threadIdx.x == 0) {
-        const double t = (double)(*step_dev + t_offset);
-        const double bc1 = 1.0 - pow(beta1d, t);
-        const double bc2 = 1.0 - pow(beta2d, t);
-        s_step_size = (float)((double)__ldg(lr_dev) / bc1);
-        s_bc2_sqrt = (float)sqrt(bc2);
-    }
+    __shared__ AdamConst s_c;
+    if (threadIdx.x == 0) s_c = adam_const(beta1d, beta2d, epsd, (double)(*step_dev + t_offset), __ldg(lr_dev));
     __syncthreads();
-    const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
-    auto one = [&](float& p, float g, float& mm, float& vv) {
-        mm = mm + w1 * (g - mm);
-        vv = vv * beta2 + w2 * g * g;
-        float denom = sqrtf(vv) / bc2_sqrt + eps;
-        p = p - step_size * (mm / denom);
-    };
+    const AdamConst c = s_c;
+    auto one = [&](float& p, float g, float& mm, float& vv) { adam_update(p, g, mm, vv, c); };
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const int64_t i = i0 + (int64_t)u * SSQ_THREADS;

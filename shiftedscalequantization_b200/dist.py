@@ -140,6 +140,7 @@ class SymmetricUnit:
         self.pad_ptrs = arr(*[b + 8 * self.n for b in bases])
         self.shard = int(lib.ssq_exchange_shard_elems(self.n, self.world))
         self.timeouts = torch.zeros(1, dtype=torch.int32, device=device)
+        self.epochs = torch.zeros(pad_floats // 8 + 8, dtype=torch.int32, device=device)     # per-CTA launch counters (local)
         td.barrier()                                   # every rank has zeroed its pad before anybody polls it
 
     def check(self):

@@ -132,7 +132,7 @@ class ReconEngine:
         self.cached_grads = None if cached_grads is None else cached_grads.contiguous()
         self.act_quant, self.iters, self.weight, self.p, self.opt_mode = act_quant, int(iters), float(weight), float(p), opt_mode
         self.batch = min(int(batch_size), self.cached_inps.shape[0])
-        self.multi_gpu = bool(multi_gpu) and ssq_dist.world_size() > 1
+        self.multi_gpu = bool(multi_gpu) and ssq_dist.world_size() > 1 and ssq_dist.EXCHANGE != 'none'   # 'none': measurement aid
         self.strong = self.multi_gpu and scaling == 'strong'
         self.use_graph = (self.iters >= 8) if use_graph is None else bool(use_graph)
         self.verbose = verbose

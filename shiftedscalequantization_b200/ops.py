@@ -689,7 +689,8 @@ def grad_exchange_adam(sym, exp_avg_shard, exp_avg_sq_shard, lr_dev, step_dev, b
     ws = workspace(dev, _lib.load().ssq_ws_bytes(1), "mt")
     _call("ssq_grad_exchange_adam", sym.flat_ptrs, sym.grad_ptrs, sym.pad_ptrs, sym.rank, sym.world, sym.n,
           exp_avg_shard.data_ptr(), exp_avg_sq_shard.data_ptr(), lr_dev.data_ptr(), step_dev.data_ptr(),
-          float(betas[0]), float(betas[1]), float(eps), _ptr(reduced_out), sym.timeouts.data_ptr(), ws.data_ptr(), ws.numel(),
+          float(betas[0]), float(betas[1]), float(eps), _ptr(reduced_out), sym.timeouts.data_ptr(), sym.epochs.data_ptr(),
+          ws.data_ptr(), ws.numel(),
           torch.cuda.current_stream(dev).cuda_stream)
 
 
