@@ -217,8 +217,9 @@ def test_long_horizon_code_agreement(iters):
     """north_star: codes after the full per-block budget vs the reference. The REAL reference loops ran on the CPU for
     `iters` iterations (block_reconstruction on layer1.0, then layer_reconstruction on fc); here the public API runs the
     same flow on the GPU with the same seeds. Bit-identical trajectories are impossible (cuDNN vs CPU convolutions), so the
-    figure of merit is the fraction of identical hard integer codes; the fraction and the reference's own margin are
-    reported (gpurun_out/parity_report.json, bench.py extra.code_agreement)."""
+    figure of merit is the fraction of identical hard integer codes, judged against the reference's agreement with itself
+    under another CPU convolution backend (stored in the golden); both are reported (gpurun_out/parity_report.json,
+    profiles/r02_parity_report.json, bench.py extra.code_agreement)."""
     from shiftedscalequantization_b200 import quant as Q, zoo
     g = golden("long_horizon")
     torch.manual_seed(1005)
@@ -245,12 +246,15 @@ def test_long_horizon_code_agreement(iters):
         same = codes == ref
         # a reference alpha that finished close to 0 is a decision the reference itself barely made
         rep[name] = {"code_agreement": float(same.mean()), "codes": int(same.size), "differing": int((~same).sum()),
+                     "reference_vs_itself": float(g[f"i{iters}.{name}.self_agreement"]),
                      "differing_where_ref_alpha_abs_gt_1": int(((~same) & (np.abs(a_ref) > 1.0)).sum()),
                      "ref_alpha_abs_lt_1": float((np.abs(a_ref) < 1.0).mean())}
     print(f"long horizon, {iters} iterations:", json.dumps(rep))
     _report(f"long_horizon.{iters}", rep)
+    # the yardstick: the reference's agreement with ITSELF when only its CPU convolution backend changes (oneDNN -> native),
+    # i.e. under the same kind of last-bit differences a cuDNN run has (0.9999 after 2 000 iterations, 0.97-0.985 after 20 000)
     for name, r in rep.items():
-        assert r["code_agreement"] > (0.97 if iters == 2000 else 0.95), (name, r)
+        assert r["code_agreement"] >= r["reference_vs_itself"] - (0.002 if iters == 2000 else 0.01), (name, r)
 
 
 # ------------------------------------------------------------------------------------------------ ChannelQuantAct
