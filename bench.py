@@ -720,7 +720,7 @@ def run_ours(args):
             torch.cuda.synchronize(dev)
             t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
             t0.record()
-            n_unit_iters = max(args.steps, 500)                  # >= 500 timed iterations per unit
+            n_unit_iters = max(args.steps, args.unit_iters)      # >= 500 timed iterations per unit
             for _ in range(n_unit_iters):
                 e.step()
             t1.record(); torch.cuda.synchronize(dev)
@@ -730,7 +730,7 @@ def run_ours(args):
                               "alpha_elems": int(e.flat.numel()), "ssq_launches": e.launches_per_iter}
         hm = len(per_unit) / sum(1.0 / v["iters_per_s"] for v in per_unit.values())
         per_unit["harmonic_mean_iters_per_s"] = round(hm, 1)
-        per_unit["timed_iterations_per_unit"] = max(args.steps, 500)
+        per_unit["timed_iterations_per_unit"] = max(args.steps, args.unit_iters)
         prof, eager_ms = in_step_profile(engines, dev)
     release(engines)
     e2e = None
@@ -896,6 +896,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="multi-GPU partitioning (DESIGN.md §7)")
     ap.add_argument("--tf32", type=int, default=0)
     ap.add_argument("--cudnn-benchmark", type=int, default=1)
+    ap.add_argument("--unit-iters", type=int, default=500, help="timed iterations per unit of the per-unit table (lower it only under a profiler)")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-act", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")

@@ -33,6 +33,8 @@ KERNELS = OrderedDict([
     ("fq_shift_bwd_vec", ("K1c bwd, adaShift soft, S = 3 (ssq_fq_shift_bwd)", 16, W)),
     ("fq_shift_fwd_vec_deq", ("K1c fwd, dequantised mixture, S = 3 (ssq_fq_shift_fwd, -s 16)", 8, W)),
     ("fq_shift_bwd_vec_deq", ("K1c bwd, dequantised mixture, S = 3 (ssq_fq_shift_bwd, -s 16)", 8, W)),
+    ("ada_bwd_adam_mt_kernel", ("launch 3: K1b bwd + regulariser gradient + Adam in one pass (ssq_fq_adaround_bwd_adam_mt)", 32, W)),
+    ("ada_fwd_mt_kernel", ("K1b fwd multi-tensor (ssq_fq_adaround_fwd_mt)", 12, W)),
     ("export_vec_kernel", ("integer export, 2-bit + alpha (ssq_export_codes)", 8.25, W)),
     ("import_vec_kernel", ("integer import, 2-bit (ssq_import_codes)", 4.25, W)),
 ])
@@ -110,7 +112,7 @@ def launch_list(tag, steps=3, units=9):
     # launch order of bench.py: 3 eager warm-up iterations per engine (3*units loop_advance launches), then `steps` untimed + `steps`
     # timed steps (one graph replay per unit each), then the per-unit timing loops and the in-step event pass. The timed region is
     # therefore loop_advance launches [3*units + steps*units, 3*units + 2*steps*units)
-    adv = [i for i, (n, _) in enumerate(recs) if "loop_advance" in n]
+    adv = [i for i, (n, _) in enumerate(recs) if "loop_advance" in n or "iter_prologue" in n]
     first = 3 * units + steps * units
     start, stop = adv[first], adv[first + steps * units]
     region = recs[start:stop]
@@ -138,7 +140,54 @@ def launch_list(tag, steps=3, units=9):
     print(f"launch list: {len(region)} nodes, ssq share {100 * ours / total:.1f} %")
 
 
+def k2_table(tag):
+    """per-launch metric list of the scale-search kernels (ncu --metrics ..., `bench.py --k2-only`) -> profiles/<tag>_k2_ncu.md"""
+    path = os.path.join(GOUT, f"{tag}_k2_ncu.csv")
+    if not os.path.exists(path):
+        return
+    lines = [l for l in open(path) if not l.startswith("==")]
+    rows = list(csv.DictReader(io.StringIO("".join(lines))))
+    by_id = OrderedDict()
+    for r in rows:
+        d = by_id.setdefault(r["ID"], {"name": r["Kernel Name"], "grid": r.get("Grid Size", ""), "block": r.get("Block Size", "")})
+        try:
+            v = float(r["Metric Value"].replace(",", ""))
+        except ValueError:
+            continue
+        d[r["Metric Name"]] = v * SCALE.get(r.get("Metric Unit", ""), 1.0) if r["Metric Name"] in ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum") else v
+    # group identical (kernel, grid) launches: report the LAST one (the warmed microbench launches come last)
+    groups = OrderedDict()
+    for d in by_id.values():
+        key = (d["name"].split("(")[0], d.get("launch__grid_size", d["grid"]))
+        g = groups.setdefault(key, {"n": 0})
+        g["n"] += 1
+        g["last"] = d
+    md = [f"# {tag} — scale-search kernels (K2a / K2b) under ncu\n",
+          "Command (after `python bench.py --k2-only` exited 0 without ncu): `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,"
+          "dram__bytes_write.sum,smsp__issue_active...,smsp__inst_executed.sum,sm__inst_executed_pipe_xu.sum --clock-control none -k regex:mse_search|mse_rank|"
+          "mse_settle|inp_scale_sweep|inp_scale_fit|row_minmax python bench.py --k2-only` (profiles/capture_r02.sh). One row per (kernel, grid) — the last "
+          "launch of that shape; durations are cold-cache single launches (CUDA-event numbers: BENCH extra.scale_search).\n",
+          "| kernel | grid | launches | us | DRAM MB (r+w) | DRAM % of ncu peak | issue-active % | warps-active % | regs | warp-instr (M) | XU-pipe instr (M) |",
+          "|---|---|---|---|---|---|---|---|---|---|---|"]
+    js = []
+    for (name, grid), g in groups.items():
+        d = g["last"]
+        f = lambda m, dflt=float("nan"): d.get(m, dflt)
+        md.append(f"| `{name.replace('ssq::', '')[:60]}` | {int(f('launch__grid_size', 0))} | {g['n']} | {f('gpu__time_duration.sum'):.1f} | "
+                  f"{(f('dram__bytes_read.sum', 0) + f('dram__bytes_write.sum', 0)) / 1e6:.1f} | {f('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'):.1f} | "
+                  f"{f('smsp__issue_active.avg.pct_of_peak_sustained_active'):.1f} | {f('sm__warps_active.avg.pct_of_peak_sustained_active'):.1f} | "
+                  f"{int(f('launch__registers_per_thread', 0))} | {f('smsp__inst_executed.sum', 0) / 1e6:.2f} | {f('sm__inst_executed_pipe_xu.sum', 0) / 1e6:.2f} |")
+        js.append({"kernel": name, "grid": f('launch__grid_size', 0), "launches": g["n"], "us": f('gpu__time_duration.sum'),
+                   "dram_MB": (f('dram__bytes_read.sum', 0) + f('dram__bytes_write.sum', 0)) / 1e6,
+                   "issue_active_pct": f('smsp__issue_active.avg.pct_of_peak_sustained_active'),
+                   "dram_pct": f('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')})
+    open(os.path.join(OUT, f"{tag}_k2_ncu.md"), "w").write("\n".join(md) + "\n")
+    json.dump(js, open(os.path.join(OUT, f"{tag}_k2_ncu.json"), "w"), indent=1)
+    print("k2 table:", len(groups), "rows")
+
+
 if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01c"
     kernels(tag)
     launch_list(tag)
+    k2_table(tag)

@@ -575,6 +575,12 @@ __device__ __forceinline__ int elem_prefix(float w, const RowIv& I, const float*
 }
 
 constexpr int K2B_COLS = 4;                     // columns per thread (one float4 when aligned)
+constexpr int K2B_ROWS = 4;                     // rows of loads in flight per thread
+// One pass over w. A column's answer is the minimum prefix over its rows, so an element only matters when it can LOWER the
+// running minimum `pre`: with jr the estimate above, jr > (pre - 1) + margin implies prefix >= pre whether or not the estimate is
+// decisive (a non-decisive jr rounds to an integer n >= pre and the exact prefix is n or n + 1). That test is one select, one
+// multiply, one FMA and one compare per element; the exact elem_prefix runs only for the few elements per column that fail it
+// (the running minimum of a column drops at most `level` times), which keeps the kernel on the HBM roof instead of the issue roof.
 __global__ void __launch_bounds__(SSQ_THREADS)
 inp_scale_sweep_kernel(const float* __restrict__ w, const RowIv* __restrict__ iv, const float* __restrict__ cand, int level,
                        int64_t oc, int64_t k, int64_t rows_per_cta, const int* __restrict__ need_brute, int* __restrict__ best) {
@@ -587,34 +593,34 @@ inp_scale_sweep_kernel(const float* __restrict__ w, const RowIv* __restrict__ iv
     const float margin = fmaf(flevel, 1e-6f, 1e-6f);                   // >= 2.5x the error bound of jr
     const bool vec = (k % K2B_COLS == 0) && aligned16(w) && col0 + K2B_COLS <= k;
     int pre[K2B_COLS];
+    float thr[K2B_COLS];
 #pragma unroll
-    for (int e = 0; e < K2B_COLS; ++e) pre[e] = level;
-    int64_t r = r0;
-    for (; r + 1 < r1; r += 2) {                                       // two rows of loads in flight
-        float xa[K2B_COLS], xb[K2B_COLS];
-        if (vec) {
-            const float4 a = ld_stream4(w + r * k + col0), b = ld_stream4(w + (r + 1) * k + col0);
-            xa[0] = a.x; xa[1] = a.y; xa[2] = a.z; xa[3] = a.w; xb[0] = b.x; xb[1] = b.y; xb[2] = b.z; xb[3] = b.w;
-        } else {
-#pragma unroll
-            for (int e = 0; e < K2B_COLS; ++e) {
-                const bool in = col0 + e < k;
-                xa[e] = in ? ld_stream1(w + r * k + col0 + e) : 0.f;
-                xb[e] = in ? ld_stream1(w + (r + 1) * k + col0 + e) : 0.f;
-            }
+    for (int e = 0; e < K2B_COLS; ++e) { pre[e] = level; thr[e] = (flevel - 1.0f) + margin; }
+    auto one = [&](int e, float x, const RowIv& I) {
+        const float jr = fmaf(-flevel, x * (x > 0.f ? I.rhi : I.rlo), flevel);
+        if (!(jr > thr[e])) {                                          // may lower the minimum (or NaN / Inf): exact path
+            pre[e] = min(pre[e], elem_prefix(x, I, cand, level, flevel, margin));
+            thr[e] = (float)(pre[e] - 1) + margin;
         }
-        const RowIv Ia = iv[r], Ib = iv[r + 1];
+    };
+    int64_t r = r0;
+    if (vec) {
+        for (; r + K2B_ROWS <= r1; r += K2B_ROWS) {
+            float4 x[K2B_ROWS];
 #pragma unroll
-        for (int e = 0; e < K2B_COLS; ++e) {
-            pre[e] = min(pre[e], elem_prefix(xa[e], Ia, cand, level, flevel, margin));
-            pre[e] = min(pre[e], elem_prefix(xb[e], Ib, cand, level, flevel, margin));
+            for (int u = 0; u < K2B_ROWS; ++u) x[u] = ld_stream4(w + (r + u) * k + col0);
+#pragma unroll
+            for (int u = 0; u < K2B_ROWS; ++u) {
+                const RowIv I = iv[r + u];
+                one(0, x[u].x, I); one(1, x[u].y, I); one(2, x[u].z, I); one(3, x[u].w, I);
+            }
         }
     }
     for (; r < r1; ++r) {
         const RowIv I = iv[r];
 #pragma unroll
         for (int e = 0; e < K2B_COLS; ++e)
-            if (col0 + e < k) pre[e] = min(pre[e], elem_prefix(ld_stream1(w + r * k + col0 + e), I, cand, level, flevel, margin));
+            if (col0 + e < k) one(e, ld_stream1(w + r * k + col0 + e), I);
     }
 #pragma unroll
     for (int e = 0; e < K2B_COLS; ++e)
