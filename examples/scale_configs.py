@@ -1,9 +1,10 @@
 #!/usr/bin/env python
-"""BASELINE.json configs[2] and configs[4] on N GPUs of one box (one rank per GPU, launched by torchrun):
+"""BASELINE.json configs[2], configs[3] and configs[4] on N GPUs of one box (one rank per GPU, launched by torchrun):
 
     configs[4]  RegNetX-3200M W2A4 block reconstruction: every unit (blocks + fc) of the network, the calibration images
                 sharded by rank, the flat AdaRound gradient of the unit summed across ranks every iteration
                 (Brecq/main_imagenet_dist.py:156-221 is the reference's flow; quant/block_recon.py:100-102 its exchange)
+    configs[3]  MobileNetV2 W3A3: whole-model K2a / K2b timings, channelShift_wMSE_flow, block reconstruction of every unit
     configs[2]  ResNet-50 W4A4 shifted-scale LAYER reconstruction (quant/layer_recon_shiftedScale.py:262-338 with the
                 module switch MULTI_GPU, :141), the calibration batch sharded by rank
 
@@ -121,9 +122,85 @@ def resnet50_shift(args, rank, local, world, dev):
         td.barrier()
 
 
+def mobilenetv2_mse(args, rank, local, world, dev):
+    """configs[3]: MobileNetV2 W3A3 (depthwise-heavy) — whole-model MSE weight-scale search (K2a, rows of 9 / 16..960 / 1280),
+    ChannelQuantMSE input-scale search of every layer (K2b, scaled_methods.channelShift_wMSE_flow), then the plain AdaRound block
+    reconstruction of every unit (the most memory-bound fake-quant shapes: depthwise [C,1,3,3])."""
+    from shiftedscalequantization_b200 import scaled_methods as SM
+    from shiftedscalequantization_b200.quant.channelQuantMSE import ChannelQuantMSE
+    torch.manual_seed(1005)
+    cnn = zoo.mobilenetv2().to(dev).eval()
+    qnn = Q.QuantModel(cnn, {'n_bits': 3, 'channel_wise': True, 'scale_method': 'mse'},
+                       {'n_bits': 3, 'channel_wise': False, 'scale_method': 'mse', 'leaf_param': True}).to(dev).eval()
+    qnn.set_first_last_layer_to_8bit()
+    cali = torch.randn(args.images, 3, 224, 224)
+    qnn.set_quant_state(False, False)
+    with torch.no_grad():
+        qnn(cali[:64].to(dev))                                # CUDA / cuDNN warm-up outside the timed scale search
+    mods = [m for m in qnn.modules() if isinstance(m, Q.QuantModule)]
+    rows = [(m.org_weight.reshape(m.org_weight.shape[0], -1).contiguous(), m.weight_quantizer.n_levels) for m in mods]
+
+    def ev(fn, reps=5):
+        fn(); torch.cuda.synchronize(dev)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps
+    k2a_ms = ev(lambda: [ops.mse_scale_search(r, nl, False) for r, nl in rows])
+    qnn.set_quant_state(True, False)
+    torch.cuda.synchronize(dev); t0 = time.perf_counter()
+    with torch.no_grad():
+        qnn(cali[:64].to(dev))
+    torch.cuda.synchronize(dev); first_q_s = time.perf_counter() - t0
+    # K2b on every layer, the kernels only (same arguments ChannelQuantMSE.init_scale builds, level 16, threshold 1.5)
+    level, thr = 16, 1.5
+    jobs = []
+    for m in mods:
+        q = m.weight_quantizer
+        w = m.org_weight.reshape(m.org_weight.shape[0], -1).contiguous()
+        L = q.n_levels
+        cand = torch.tensor([i / level for i in range(level, 0, -1)], dtype=torch.float32, device=dev)
+        lo = float(torch.tensor(0.0 - 0.5 / (L - 1) * thr, dtype=torch.float32)); hi = float(torch.tensor(1.0 + 0.5 / (L - 1) * thr, dtype=torch.float32))
+        jobs.append((w, q.delta.reshape(-1).contiguous(), q.raw_zero_point.reshape(-1).contiguous(), cand, L - 1, lo, hi, torch.ones(w.shape[1], device=dev)))
+    k2b_ms = ev(lambda: [ops.inp_scale_search(*j) for j in jobs])
+    # the public flow (ChannelQuantMSE objects built and initialised for every layer)
+    torch.cuda.synchronize(dev); t0 = time.perf_counter()
+    SM.channelShift_wMSE_flow(qnn, cali[:64], level=level, threshold=thr, layerDisabled=('.model.classifier.1',))
+    torch.cuda.synchronize(dev); flow_s = time.perf_counter() - t0
+    built = sum(isinstance(m.weight_quantizer, ChannelQuantMSE) for m in mods)
+    # AdaRound block reconstruction of every unit on the plain quantisers
+    torch.manual_seed(1005)
+    cnn = zoo.mobilenetv2().to(dev).eval()
+    qnn = Q.QuantModel(cnn, {'n_bits': 3, 'channel_wise': True, 'scale_method': 'mse'},
+                       {'n_bits': 3, 'channel_wise': False, 'scale_method': 'mse', 'leaf_param': True}).to(dev).eval()
+    qnn.set_first_last_layer_to_8bit()
+    lo_, hi_ = D.shard_range(args.images, rank, world)
+    qnn.set_quant_state(True, False)
+    with torch.no_grad():
+        qnn(cali[:64].to(dev))
+    engines, _ = B.make_engines(Q, qnn, cali[lo_:hi_], dev, act_quant=False, multi_gpu=world > 1)
+    ms = B.timed_steps(engines, args.steps, args.warmup, dev, world)
+    n_units = len(engines)
+    B.release(engines)
+    if rank == 0:
+        B.emit(json.dumps({
+            "config": f"configs[3]: MobileNetV2 W3A3, {args.images} randn 224x224 images, {world} rank(s), fp32 convolutions",
+            "n_gpus": world, "quant_modules": len(mods), "weight_rows": int(sum(r.shape[0] for r, _ in rows)), "weight_elems": int(sum(r.numel() for r, _ in rows)),
+            "k2a_weight_scale_search_all_layers_ms": round(k2a_ms, 3), "first_quantised_forward_s": round(first_q_s, 3),
+            "k2b_inp_scale_search_all_layers_ms": round(k2b_ms, 3), "k2b_level": level,
+            "channelShift_wMSE_flow_s": round(flow_s, 3), "channelquantmse_layers_built": built,
+            "block_recon": {"units": n_units, "ms_per_step": ms, "iters_per_s": world * n_units / (ms * 1e-3),
+                            "step": f"one AdaRound iteration on each of the {n_units} units, mini-batch 32"}}))
+    if world > 1:
+        import torch.distributed as td
+        td.barrier()
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", default="regnet", choices=["regnet", "resnet50_shift"])
+    ap.add_argument("--config", default="regnet", choices=["regnet", "resnet50_shift", "mobilenetv2_mse"])
     ap.add_argument("--arch", default="regnetx_3200m")
     ap.add_argument("--images", type=int, default=1024)
     ap.add_argument("--steps", type=int, default=30)
@@ -137,7 +214,7 @@ def main():
     torch.backends.cudnn.benchmark = True
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    (regnet if args.config == "regnet" else resnet50_shift)(args, rank, local, world, dev)
+    {"regnet": regnet, "resnet50_shift": resnet50_shift, "mobilenetv2_mse": mobilenetv2_mse}[args.config](args, rank, local, world, dev)
     if world > 1:
         import torch.distributed as td
         td.destroy_process_group()

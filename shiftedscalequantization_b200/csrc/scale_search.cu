@@ -557,17 +557,12 @@ __device__ __forceinline__ bool elem_fits(float w, const RowIv& I, const float* 
     const float v = div_exact(w, __ldg(cand + j));
     return v >= I.vlo && v <= I.vhi;
 }
-// J+1 for one element: number of leading candidates that fit (0 = none)
-__device__ __forceinline__ int elem_prefix(float w, const RowIv& I, const float* __restrict__ cand, int level, float flevel, float margin) {
-    if (w == 0.f) return level;
-    const float t = w * (w > 0.f ? I.rhi : I.rlo);                     // ~ w / V >= 0
-    const float jr = fmaf(-flevel, t, flevel);                         // level (1 - w/V): candidates 0..floor(jr) fit
-    const float jf = floorf(jr);
-    if (fabsf(jr - rintf(jr)) > margin && t < 1e30f)                   // the estimate is decisive (NaN/Inf w fall through)
-        return jr < 0.f ? 0 : min((int)jf + 1, level);
-    // settle with the exact predicate; the prefix property makes a local walk sufficient
-    int j = jr < 0.f ? 0 : (jr >= flevel ? level - 1 : (int)jf);      // NaN jr -> level-1, walks down to "none"
-    if (!(jr == jr)) j = level - 1;
+// J+1 for one element whose estimate jr is NOT decisive (within `margin` of an integer, or NaN / Inf / huge): settle with the exact
+// predicate; the prefix property makes a local walk sufficient. Rare (a 2*margin fraction of the elements that reach it), out of line.
+__device__ __noinline__ int elem_prefix_settle(float w, float jr, const RowIv& I, const float* __restrict__ cand, int level) {
+    const float flevel = (float)level;
+    int j = jr < 0.f ? 0 : (jr >= flevel ? level - 1 : (int)floorf(jr));
+    if (!(jr == jr)) j = level - 1;                                    // NaN jr -> level-1, walks down to "none"
     j = min(j + 1, level - 1);
     while (j >= 0 && !elem_fits(w, I, cand, j)) --j;
     while (j + 1 < level && elem_fits(w, I, cand, j + 1)) ++j;
@@ -576,12 +571,17 @@ __device__ __forceinline__ int elem_prefix(float w, const RowIv& I, const float*
 
 constexpr int K2B_COLS = 4;                     // columns per thread (one float4 when aligned)
 constexpr int K2B_ROWS = 4;                     // rows of loads in flight per thread
-// One pass over w. A column's answer is the minimum prefix over its rows, so an element only matters when it can LOWER the
-// running minimum `pre`: with jr the estimate above, jr > (pre - 1) + margin implies prefix >= pre whether or not the estimate is
-// decisive (a non-decisive jr rounds to an integer n >= pre and the exact prefix is n or n + 1). That test is one select, one
-// multiply, one FMA and one compare per element; the exact elem_prefix runs only for the few elements per column that fail it
-// (the running minimum of a column drops at most `level` times), which keeps the kernel on the HBM roof instead of the issue roof.
-__global__ void __launch_bounds__(SSQ_THREADS)
+constexpr int K2B_CTAS = 4;                     // resident CTAs per SM the launch bounds allow (64 registers)
+// One pass over w, 4 B/element. A column's answer is the minimum prefix over its rows. Per element, branch-free:
+//   t  = w * (w > 0 ? 1/vhi : 1/vlo)            ~ w / V >= 0
+//   jr = level - level * t                      candidates 0..floor(jr) fit
+//   p  = min(floor(jr) + 1, level)              the prefix when the estimate is decisive (further than `margin` from an integer)
+//   pre = min(pre, p)
+// about 12 instructions per element with no branch taken: a first version that tested "can this element lower the minimum?" and
+// branched to the exact evaluation diverged in nearly every warp (early rows lower the minimum of SOME column) and ran at 0.50 of
+// the HBM peak. Only a non-decisive estimate that could matter (p <= pre) calls the exact settle walk, out of line.
+// w == 0 gives t = 0, jr = level: never lowers (every candidate fits a zero, as the reference predicate says).
+__global__ void __launch_bounds__(SSQ_THREADS, K2B_CTAS)
 inp_scale_sweep_kernel(const float* __restrict__ w, const RowIv* __restrict__ iv, const float* __restrict__ cand, int level,
                        int64_t oc, int64_t k, int64_t rows_per_cta, const int* __restrict__ need_brute, int* __restrict__ best) {
     if (__ldg(need_brute)) return;
@@ -592,16 +592,17 @@ inp_scale_sweep_kernel(const float* __restrict__ w, const RowIv* __restrict__ iv
     const float flevel = (float)level;
     const float margin = fmaf(flevel, 1e-6f, 1e-6f);                   // >= 2.5x the error bound of jr
     const bool vec = (k % K2B_COLS == 0) && aligned16(w) && col0 + K2B_COLS <= k;
-    int pre[K2B_COLS];
-    float thr[K2B_COLS];
+    int pre[K2B_COLS];                                                 // running minimum prefix (may dip below 0: clamped at the end)
 #pragma unroll
-    for (int e = 0; e < K2B_COLS; ++e) { pre[e] = level; thr[e] = (flevel - 1.0f) + margin; }
+    for (int e = 0; e < K2B_COLS; ++e) pre[e] = level;
     auto one = [&](int e, float x, const RowIv& I) {
         const float jr = fmaf(-flevel, x * (x > 0.f ? I.rhi : I.rlo), flevel);
-        if (!(jr > thr[e])) {                                          // may lower the minimum (or NaN / Inf): exact path
-            pre[e] = min(pre[e], elem_prefix(x, I, cand, level, flevel, margin));
-            thr[e] = (float)(pre[e] - 1) + margin;
-        }
+        int p = min(__float2int_rd(jr) + 1, level);                    // the decisive estimate (<= 0: nothing fits; NaN -> 1)
+        // not decisive: within `margin` of an integer n (the exact prefix is n or n + 1 >= p - 1), NaN, Inf, or |jr| >= 2^23.
+        // It can only matter when p <= pre, and not at all when n >= level (the prefix is `level` either way: zeros land here).
+        const float rn = rintf(jr);
+        if (!(fabsf(jr - rn) > margin) && !(rn >= flevel) && p <= pre[e]) p = elem_prefix_settle(x, jr, I, cand, level);
+        pre[e] = min(pre[e], p);
     };
     int64_t r = r0;
     if (vec) {
@@ -624,7 +625,7 @@ inp_scale_sweep_kernel(const float* __restrict__ w, const RowIv* __restrict__ iv
     }
 #pragma unroll
     for (int e = 0; e < K2B_COLS; ++e)
-        if (col0 + e < k && pre[e] < level) atomicMin(best + col0 + e, pre[e]);
+        if (col0 + e < k && pre[e] < level) atomicMin(best + col0 + e, max(pre[e], 0));
 }
 
 // brute force: every (column, candidate) with the reference expression; runs only when need_brute is set (or forced)
@@ -788,10 +789,10 @@ extern "C" int ssq_inp_scale_search_ex(const float* w, const float* delta, const
     inp_scale_row_interval_kernel<<<(unsigned)((oc + 127) / 128), 128, 0, st>>>(delta, raw_zero_point, x_range, lo, hi, oc, level, cand, iv, need_brute);
     e = launch_status();
     if (e) return e;
-    // sweep: column blocks x row slabs, about two waves of CTAs
+    // sweep: column blocks x row slabs = ONE wave of resident CTAs (a second, partial wave costs as much as a full one)
     const int64_t colblocks = (k + (int64_t)SSQ_THREADS * K2B_COLS - 1) / ((int64_t)SSQ_THREADS * K2B_COLS);
-    int64_t slabs = ((int64_t)SSQ_NUM_SMS * SSQ_CTAS_PER_SM * 2 + colblocks - 1) / colblocks;
-    if (slabs > (oc + 7) / 8) slabs = (oc + 7) / 8;
+    int64_t slabs = ((int64_t)SSQ_NUM_SMS * K2B_CTAS) / colblocks;
+    if (slabs > (oc + 2 * K2B_ROWS - 1) / (2 * K2B_ROWS)) slabs = (oc + 2 * K2B_ROWS - 1) / (2 * K2B_ROWS);
     if (slabs > 65535) slabs = 65535;
     if (slabs < 1) slabs = 1;
     const int64_t rows_per_cta = (oc + slabs - 1) / slabs;

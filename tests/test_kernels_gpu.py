@@ -327,12 +327,14 @@ def test_inp_scale_search_one_pass_equals_brute_force(ops, level, thr, bits):
         vmax = d[i] * (hi * (L - 1) - zero[i])
         w[i, j] = np.float32(vmax * c * (1 + (r.integers(-3, 4)) * 6e-8))
     w[3, 5] = np.nan; w[7, 11] = np.inf; w[9, 13] = -np.inf
+    w[11, 17] = 3e38; w[12, 19] = -1e20; w[13, 23] = 1e-40; w[14, 29] = -0.0      # huge finite, denormal, negative zero
     cand = torch.from_numpy(cand_np).cuda()
     fast = torch.ones(k, device="cuda"); brute = torch.ones(k, device="cuda")
     ops.inp_scale_search(dev(w), dev(d), dev(raw), cand, L - 1, float(lo), float(hi), fast)
     ops.inp_scale_search(dev(w), dev(d), dev(raw), cand, L - 1, float(lo), float(hi), brute, force_brute=True)
     assert_exact(host(fast), host(brute), f"inp_scale, level {level}")
     assert host(fast)[5] == 1.0 and host(fast)[11] == 1.0 and host(fast)[13] == 1.0     # NaN / Inf columns never fit: untouched
+    assert host(fast)[17] == 1.0 and host(fast)[19] == 1.0                               # ... nor do huge finite values
     if level <= 16:
         ref = O.inp_scale_search(w, d.reshape(-1, 1), raw.reshape(-1, 1), L, level, thr)
         assert_exact(host(fast), ref.reshape(-1), "inp_scale vs oracle")
