@@ -35,6 +35,7 @@ KERNELS = OrderedDict([
     ("fq_shift_bwd_vec_deq", ("K1c bwd, dequantised mixture, S = 3 (ssq_fq_shift_bwd, -s 16)", 8, W)),
     ("ada_bwd_adam_mt_kernel", ("launch 3: K1b bwd + regulariser gradient + Adam in one pass (ssq_fq_adaround_bwd_adam_mt)", 32, W)),
     ("ada_fwd_mt_kernel", ("K1b fwd multi-tensor (ssq_fq_adaround_fwd_mt)", 12, W)),
+    ("inp_scale_sweep_kernel", ("K2b sweep: max t per column in one pass over the weights (inside ssq_inp_scale_search), level 16", 4, W)),
     ("export_vec_kernel", ("integer export, 2-bit + alpha (ssq_export_codes)", 8.25, W)),
     ("import_vec_kernel", ("integer import, 2-bit (ssq_import_codes)", 4.25, W)),
 ])

@@ -499,10 +499,15 @@ mse_settle_tensor_kernel(const float* __restrict__ x, int64_t k, const float* __
 // [vlo_r, vhi_r] of floats — found ONCE per row by bisection on the float ordering with the exact ops (row_interval).
 // fl(w / c) is weakly monotone in c, so when the interval contains 0 (it does whenever 0 <= zero_r <= x_range, lo < 0 < 1 < hi:
 // every quantiser this repo or the reference builds) an element fits exactly the candidates c >= c*(w, r): the set of fitting
-// indices is a prefix 0..J, J = floor(level (1 - w / V)) up to rounding, V = vhi_r for w > 0, vlo_r for w < 0. The sweep
-// kernel evaluates that estimate, accepts it when it is further than the error bound from an integer, and otherwise settles J with
-// the exact predicate on the neighbouring candidates. Column answer = min over rows. Whenever the preconditions fail (flag
-// set by row_interval) the brute-force kernel below evaluates all `level` candidates instead.
+// indices is a prefix 0..J, J = floor(jr), jr = level (1 - t), t = |w| / |V|, V = vhi_r for w > 0, vlo_r for w < 0, up to
+// rounding. The column answer is the MINIMUM prefix over its rows, and jr is monotone in t, so the sweep over the weights only
+// has to find max_r t per column: one select, one multiply and one integer max per element (t >= 0, so the IEEE bit patterns
+// order like integers and the canonical NaN 0x7fffffff is the largest of all) — 4 B/element and nothing else on the hot path.
+// The finish kernel turns max t into the prefix: decisive when jr is further than `margin` (>= 2.5x its error bound) from an
+// integer — then every other element of the column has a prefix >= that one, see DESIGN.md K2b — and otherwise (a 2*margin
+// fraction of the columns) the warp re-reads that column and settles the elements within 3*margin of the maximum with the exact
+// predicate on the neighbouring candidates. Whenever the preconditions fail (flag set by row_interval) the brute-force kernel
+// below evaluates all `level` candidates instead.
 __device__ __forceinline__ float g_row(float v, float d, float zero, float x_range) {
     return __fdiv_rn(__fadd_rn(__fdiv_rn(v, d), zero), x_range);
 }
@@ -510,16 +515,17 @@ __device__ __forceinline__ float g_row(float v, float d, float zero, float x_ran
 __device__ __forceinline__ uint32_t f2ord(float f) { uint32_t u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
 __device__ __forceinline__ float ord2f(uint32_t o) { return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o); }
 
-struct RowIv { float vlo, vhi, rlo, rhi; };     // interval of v = fl(w/c) that fits, and reciprocals of its ends
+struct RowIv { float vlo, vhi, rlo, rhi; };     // interval of v = fl(w/c) that fits; rlo = 1/|vlo|, rhi = 1/vhi (both > 0)
 __global__ void inp_scale_row_interval_kernel(const float* __restrict__ delta, const float* __restrict__ raw_zp, float x_range,
                                               float lo, float hi, int64_t oc, int level, const float* __restrict__ cand,
                                               RowIv* __restrict__ iv, int* __restrict__ need_brute) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r == 0) {
-        // the estimate assumes the reference's list cand[j] = fp32((level - j) / level) (channelQuantMSE.py:79)
+    {   // the estimate assumes the reference's list cand[j] = fp32((level - j) / level) (channelQuantMSE.py:79)
         bool okc = true;
-        for (int j = 0; j < level; ++j) okc &= cand[j] == (float)((double)(level - j) / (double)level);
-        if (!okc || !(lo < 0.f) || !(hi > 1.0f) || !(x_range >= 1.0f)) atomicExch(need_brute, 1);
+        const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+        for (int64_t j = r; j < level; j += nthr) okc &= cand[j] == (float)((double)(level - j) / (double)level);
+        if (r == 0) okc = okc && (lo < 0.f) && (hi > 1.0f) && (x_range >= 1.0f);
+        if (!okc) atomicExch(need_brute, 1);
     }
     if (r >= oc) return;
     const float d = delta[r];
@@ -546,7 +552,7 @@ __global__ void inp_scale_row_interval_kernel(const float* __restrict__ delta, c
         }
         out.vlo = ord2f(e0);
         ok = mid_exponent(out.vhi) && out.vhi > 0.f && mid_exponent(out.vlo) && out.vlo < 0.f;
-        if (ok) { out.rhi = make_recip(out.vhi).r; out.rlo = -make_recip(-out.vlo).r; }
+        if (ok) { out.rhi = make_recip(out.vhi).r; out.rlo = make_recip(-out.vlo).r; }
     }
     iv[r] = out;
     if (!ok) atomicExch(need_brute, 1);
@@ -570,40 +576,22 @@ __device__ __noinline__ int elem_prefix_settle(float w, float jr, const RowIv& I
 }
 
 constexpr int K2B_COLS = 4;                     // columns per thread (one float4 when aligned)
-constexpr int K2B_ROWS = 4;                     // rows of loads in flight per thread
-constexpr int K2B_CTAS = 4;                     // resident CTAs per SM the launch bounds allow (64 registers)
-// One pass over w, 4 B/element. A column's answer is the minimum prefix over its rows. Per element, branch-free:
-//   t  = w * (w > 0 ? 1/vhi : 1/vlo)            ~ w / V >= 0
-//   jr = level - level * t                      candidates 0..floor(jr) fit
-//   p  = min(floor(jr) + 1, level)              the prefix when the estimate is decisive (further than `margin` from an integer)
-//   pre = min(pre, p)
-// about 12 instructions per element with no branch taken: a first version that tested "can this element lower the minimum?" and
-// branched to the exact evaluation diverged in nearly every warp (early rows lower the minimum of SOME column) and ran at 0.50 of
-// the HBM peak. Only a non-decisive estimate that could matter (p <= pre) calls the exact settle walk, out of line.
-// w == 0 gives t = 0, jr = level: never lowers (every candidate fits a zero, as the reference predicate says).
+constexpr int K2B_ROWS = 8;                     // rows of loads in flight per thread
+constexpr int K2B_CTAS = 6;                     // resident CTAs per SM the launch bounds allow
+__device__ __forceinline__ float k2b_t(float x, float rlo, float rhi) { return fabsf(x) * (x > 0.f ? rhi : rlo); }   // >= +0, or NaN
+// sweep: tmax[col] = max over the slab's rows of t, as int bit patterns (tmax zeroed by the reset kernel)
 __global__ void __launch_bounds__(SSQ_THREADS, K2B_CTAS)
-inp_scale_sweep_kernel(const float* __restrict__ w, const RowIv* __restrict__ iv, const float* __restrict__ cand, int level,
-                       int64_t oc, int64_t k, int64_t rows_per_cta, const int* __restrict__ need_brute, int* __restrict__ best) {
+inp_scale_sweep_kernel(const float* __restrict__ w, const RowIv* __restrict__ iv, int64_t oc, int64_t k, int64_t rows_per_cta,
+                       const int* __restrict__ need_brute, int* __restrict__ tmax) {
     if (__ldg(need_brute)) return;
     const int64_t col0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * K2B_COLS;
     if (col0 >= k) return;
     const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
     const int64_t r1 = r0 + rows_per_cta < oc ? r0 + rows_per_cta : oc;
-    const float flevel = (float)level;
-    const float margin = fmaf(flevel, 1e-6f, 1e-6f);                   // >= 2.5x the error bound of jr (DESIGN.md, K2b)
     const bool vec = (k % K2B_COLS == 0) && aligned16(w) && col0 + K2B_COLS <= k;
-    int pre[K2B_COLS];                                                 // running minimum prefix (may dip below 0: clamped at the end)
+    int tm[K2B_COLS];
 #pragma unroll
-    for (int e = 0; e < K2B_COLS; ++e) pre[e] = level;
-    auto one = [&](int e, float x, const RowIv& I) {
-        const float jr = fmaf(-flevel, x * (x > 0.f ? I.rhi : I.rlo), flevel);
-        int p = min(__float2int_rd(jr) + 1, level);                    // the decisive estimate (<= 0: nothing fits; NaN -> 1)
-        // not decisive: within `margin` of an integer n (the exact prefix is n or n + 1 >= p - 1), NaN, Inf, or |jr| >= 2^23.
-        // It can only matter when p <= pre, and not at all when n >= level (the prefix is `level` either way: zeros land here).
-        const float rn = rintf(jr);
-        if (!(fabsf(jr - rn) > margin) && !(rn >= flevel) && p <= pre[e]) p = elem_prefix_settle(x, jr, I, cand, level);
-        pre[e] = min(pre[e], p);
-    };
+    for (int e = 0; e < K2B_COLS; ++e) tm[e] = 0;
     int64_t r = r0;
     if (vec) {
         for (; r + K2B_ROWS <= r1; r += K2B_ROWS) {
@@ -612,20 +600,77 @@ inp_scale_sweep_kernel(const float* __restrict__ w, const RowIv* __restrict__ iv
             for (int u = 0; u < K2B_ROWS; ++u) x[u] = ld_stream4(w + (r + u) * k + col0);
 #pragma unroll
             for (int u = 0; u < K2B_ROWS; ++u) {
-                const RowIv I = iv[r + u];
-                one(0, x[u].x, I); one(1, x[u].y, I); one(2, x[u].z, I); one(3, x[u].w, I);
+                const float2 s = __ldg(reinterpret_cast<const float2*>(&iv[r + u].rlo));
+                tm[0] = max(tm[0], __float_as_int(k2b_t(x[u].x, s.x, s.y)));
+                tm[1] = max(tm[1], __float_as_int(k2b_t(x[u].y, s.x, s.y)));
+                tm[2] = max(tm[2], __float_as_int(k2b_t(x[u].z, s.x, s.y)));
+                tm[3] = max(tm[3], __float_as_int(k2b_t(x[u].w, s.x, s.y)));
             }
         }
     }
     for (; r < r1; ++r) {
-        const RowIv I = iv[r];
+        const float2 s = __ldg(reinterpret_cast<const float2*>(&iv[r].rlo));
 #pragma unroll
         for (int e = 0; e < K2B_COLS; ++e)
-            if (col0 + e < k) one(e, ld_stream1(w + r * k + col0 + e), I);
+            if (col0 + e < k) tm[e] = max(tm[e], __float_as_int(k2b_t(ld_stream1(w + r * k + col0 + e), s.x, s.y)));
     }
 #pragma unroll
     for (int e = 0; e < K2B_COLS; ++e)
-        if (col0 + e < k && pre[e] < level) atomicMin(best + col0 + e, max(pre[e], 0));
+        if (col0 + e < k && tm[e] != 0) atomicMax(tmax + col0 + e, tm[e]);
+}
+// finish: one CTA per 256 columns. best[col] holds max t on entry and the prefix length (0 = nothing fits) on exit. Columns whose
+// estimate is not decisive are settled by the WHOLE CTA, one after the other: the column is re-read (strided, 4 rows of loads in
+// flight per thread — a lone warp walking 4096 rows one dependent load at a time took longer than the sweep itself).
+__global__ void __launch_bounds__(SSQ_THREADS)
+inp_scale_finish_kernel(const float* __restrict__ w, const RowIv* __restrict__ iv, const float* __restrict__ cand, int level,
+                        int64_t oc, int64_t k, const int* __restrict__ need_brute, int* __restrict__ best) {
+    if (__ldg(need_brute)) return;
+    __shared__ int s_n;
+    __shared__ int s_col[SSQ_THREADS], s_min[SSQ_THREADS];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int64_t col_base = (int64_t)blockIdx.x * SSQ_THREADS, col = col_base + tid;
+    const bool valid = col < k;
+    const float flevel = (float)level;
+    const float margin = fmaf(flevel, 1e-6f, 1e-6f);                   // >= 2.5x the error bound of jr (DESIGN.md, K2b)
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    const float tm = valid ? __int_as_float(best[col]) : 0.f;
+    const float jr = fmaf(-flevel, tm, flevel);                        // candidates 0..floor(jr) fit the column's tightest element
+    const float rn = rintf(jr);
+    const bool none = !(tm < 1e30f);                                   // NaN / Inf / huge weight in the column: nothing fits
+    int p = none ? 0 : max(min(__float2int_rd(jr) + 1, level), 0);
+    // not decisive: jr within `margin` of an integer n in [0, level) — the exact prefix is n or n + 1 (n >= level gives `level`
+    // either way: all-zero columns land there; n < 0 gives 0 either way)
+    const bool settle = valid && !none && !(fabsf(jr - rn) > margin) && rn >= 0.f && rn < flevel;
+    int slot = -1;
+    if (settle) { slot = atomicAdd(&s_n, 1); s_col[slot] = tid; s_min[slot] = level; }
+    __syncthreads();
+    const int n_settle = s_n;
+    for (int i = 0; i < n_settle; ++i) {
+        const int64_t c = col_base + s_col[i];
+        const float near = fmaf(-flevel, __int_as_float(best[c]), flevel) + 3.0f * margin;   // best[] is written after the loop
+        int local = level;
+        for (int64_t r0 = tid; r0 < oc; r0 += 4 * SSQ_THREADS) {
+            float x[4]; RowIv I[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t r = r0 + (int64_t)u * SSQ_THREADS;
+                x[u] = r < oc ? w[r * k + c] : 0.f;
+                I[u] = iv[r < oc ? r : 0];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float je = fmaf(-flevel, k2b_t(x[u], I[u].rlo, I[u].rhi), flevel);
+                if (r0 + (int64_t)u * SSQ_THREADS < oc && !(je > near)) local = min(local, elem_prefix_settle(x[u], je, I[u], cand, level));
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) local = min(local, __shfl_xor_sync(0xffffffffu, local, o));
+        if (lane == 0 && local < level) atomicMin(&s_min[i], local);
+    }
+    __syncthreads();
+    if (settle) p = s_min[slot];
+    if (valid) best[col] = p;
 }
 
 // brute force: every (column, candidate) with the reference expression; runs only when need_brute is set (or forced)
@@ -656,19 +701,19 @@ inp_scale_fit_kernel(const float* __restrict__ w, const float* __restrict__ delt
     for (int e = 0; e < CH; ++e) if (fit[e]) last = j0 + e + 1;
     if (last > 0) atomicMax(last_fit + col, last);
 }
-// best[col]: prefix length from the sweep (level = untouched = every candidate fits); last_fit[col] from the brute force
+// best[col]: prefix length from the finish kernel; last_fit[col] from the brute force
 __global__ void inp_scale_pick_kernel(const float* __restrict__ cand, int level, const int* __restrict__ need_brute,
                                       int* __restrict__ best, int* __restrict__ last_fit, float* __restrict__ inp_scale, int64_t k) {
     int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= k) return;
     const int b = __ldg(need_brute) ? last_fit[col] : best[col];
     if (b > 0) inp_scale[col] = __ldg(cand + b - 1);
-    best[col] = level; last_fit[col] = 0;
+    best[col] = 0; last_fit[col] = 0;
 }
 __global__ void inp_scale_reset_kernel(int* __restrict__ best, int* __restrict__ last_fit, int* need_brute, int level, int force_brute, int64_t k) {
     int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (col == 0) *need_brute = force_brute;
-    if (col < k) { best[col] = level; last_fit[col] = 0; }
+    if (col < k) { best[col] = 0; last_fit[col] = 0; }
 }
 
 constexpr int64_t ROW_SMEM_MAX_ELEMS = 48 * 1024;  // 192 KB of the 227 KB a CTA may use
@@ -797,7 +842,10 @@ extern "C" int ssq_inp_scale_search_ex(const float* w, const float* delta, const
     if (slabs < 1) slabs = 1;
     const int64_t rows_per_cta = (oc + slabs - 1) / slabs;
     slabs = (oc + rows_per_cta - 1) / rows_per_cta;
-    inp_scale_sweep_kernel<<<dim3((unsigned)colblocks, (unsigned)slabs), SSQ_THREADS, 0, st>>>(w, iv, cand, level, oc, k, rows_per_cta, need_brute, best);
+    inp_scale_sweep_kernel<<<dim3((unsigned)colblocks, (unsigned)slabs), SSQ_THREADS, 0, st>>>(w, iv, oc, k, rows_per_cta, need_brute, best);
+    e = launch_status();
+    if (e) return e;
+    inp_scale_finish_kernel<<<(unsigned)((k + SSQ_THREADS - 1) / SSQ_THREADS), SSQ_THREADS, 0, st>>>(w, iv, cand, level, oc, k, need_brute, best);
     e = launch_status();
     if (e) return e;
     dim3 grid(kgrid, (unsigned)((level + CH - 1) / CH));
