@@ -193,7 +193,7 @@ def recon_units(Q, qnn):
 CAPTURE_S = []      # seconds spent in save_inp_oup_data per unit (feature capture, reported beside the loop numbers)
 
 
-def make_engines(Q, qnn, cali, dev, act_quant, multi_gpu, host_resident=False, feats=None, scaling='weak'):
+def make_engines(Q, qnn, cali, dev, act_quant, multi_gpu, host_resident=False, feats=None, scaling='weak', host_stage='pull'):
     """replicates the setup half of block_reconstruction/layer_reconstruction for every unit, keeping the engines"""
     from shiftedscalequantization_b200.engine import ReconEngine
     from shiftedscalequantization_b200.quant.adaptive_rounding import AdaRoundQuantizer
@@ -227,7 +227,7 @@ def make_engines(Q, qnn, cali, dev, act_quant, multi_gpu, host_resident=False, f
             kw.update(p=2.4)
         eng = ReconEngine(unit, mods, inps, outs, None, act_quant=act_quant, iters=SCHED_ITERS, lr=4e-4, opt_mode='mse',
                           batch_size=BATCH, multi_gpu=multi_gpu, act_quantizers=aqs, use_graph=True, verbose=False,
-                          host_resident=host_resident, device=dev, scaling=scaling, **kw)
+                          host_resident=host_resident, device=dev, scaling=scaling, host_stage=host_stage, **kw)
         # time a representative point of the 20k schedule: past warm-up, so the regulariser path is live
         eng.step_dev.fill_(int(SCHED_ITERS * 0.5)); eng.host_step = int(SCHED_ITERS * 0.5)
         eng.capture()
@@ -751,13 +751,14 @@ def run_ours(args):
         bound = D.bind_to_gpu_cpus(local) if world == 1 else 0
         log(f"[rank {rank}] e2e: bound to {bound} GPU-local cores (0 = unchanged) of {len(saved_affinity)}")
         eng_h, _ = make_engines(Q, qnn, cali, dev, act_quant=False, multi_gpu=world > 1, host_resident=True, feats=feats,
-                                scaling=args.scaling)
+                                scaling=args.scaling, host_stage=args.host_stage)
         ms_e2e = timed_steps(eng_h, max(args.steps // 2, 3), max(args.warmup // 2, 3), dev, world, read_loss=True)
         if world == 1:
             os.sched_setaffinity(0, saved_affinity)
         e2e = {"value": work * n_units / (ms_e2e * 1e-3), "unit": "iters/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": sum(e.h2d_bytes_per_step() for e in eng_h), "d2h_bytes_per_step": 4 * n_units,
                "h2d_dense_bytes_per_step": sum(4 * (e.cur_inp.numel() + e.cur_out.numel()) for e in eng_h),
+               "host_stage": args.host_stage,
                "path": "ReconEngine(host_resident=True, host_stage='pull'): pinned host feature cache, post-ReLU tensors kept zero-packed "
                        "(non-zero values on the host; bit mask + chunk offsets, 3 % of the dense size, on the device); inside each captured "
                        "iteration a 16-24-CTA kernel (ssq_pull_rows_host[_packed]) reads the NEXT mini-batch's input and target rows out "
@@ -906,6 +907,7 @@ def main():
     ap.add_argument("--tf32", type=int, default=0)
     ap.add_argument("--cudnn-benchmark", type=int, default=1)
     ap.add_argument("--unit-iters", type=int, default=500, help="timed iterations per unit of the per-unit table (lower it only under a profiler)")
+    ap.add_argument("--host-stage", default="pull", choices=["pull", "dma"], help="e2e: how the mini-batch crosses PCIe (SM pull inside the graph | per-row copy-engine transfers)")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-act", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")

@@ -18,6 +18,7 @@ exchange and adam_step_end_iteration.
 from __future__ import annotations
 
 import math
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -25,6 +26,8 @@ import torch.nn as nn
 
 from . import dist as ssq_dist
 from . import ops
+
+PULL_CTAS = int(os.environ.get("SSQ_PULL_CTAS", "16"))     # CTAs of the host-pull kernels (scratch/pull_probe.py: 16 reach the link's rate)
 
 
 def temperature(t: int, t_max: int, rel_start_decay: float, start_b, end_b):
@@ -326,10 +329,10 @@ class ReconEngine:
         for src, stage, _cur in self._pull_bufs:
             if isinstance(src, ops.PackedRows):
                 ops.pull_rows_host_packed(src, self.idx_table, self.step_dev, lookahead, self.idx_table.shape[0], stage,
-                                          max_ctas=16, stream=self._pull_stream)
+                                          max_ctas=PULL_CTAS, stream=self._pull_stream)
             else:
                 ops.pull_rows_host(src, self.idx_table, self.step_dev, lookahead, self.idx_table.shape[0], stage,
-                                   max_ctas=16, stream=self._pull_stream)
+                                   max_ctas=PULL_CTAS, stream=self._pull_stream)
 
     def _prime_pull(self):
         """first mini-batch of a run: pull row *step_dev (not yet advanced) before the first iteration"""
@@ -565,8 +568,16 @@ class AutogradReconEngine:
                 uniq.append((owner, attr, old))
         uniq.sort(key=lambda e: mult[id(e[2])] > 1)              # singles first (stable), repeated ones behind them
         sizes = [_pad4(old.numel()) for _o, _a, old in uniq]
-        self.flat = torch.zeros(sum(sizes), device=self.dev)
-        self.gflat = torch.zeros_like(self.flat)
+        # several GPUs, no tensor listed twice (the weight phases): parameters and gradients in symmetric memory, SUM over the
+        # ranks + Adam + hand-out of the new parameters as ONE peer-memory kernel, as in ReconEngine; otherwise NCCL all-reduce
+        self.sym = ssq_dist.symmetric_unit_or_none(sum(sizes), self.dev) \
+            if (self.multi_gpu and sum(sizes) > 0 and all(v == 1 for v in mult.values())) else None
+        if self.sym is not None:
+            self.flat, self.gflat = self.sym.flat, self.sym.gflat
+            self.xchg_step = torch.zeros(1, dtype=torch.int64, device=self.dev)      # iterations completed (the kernel steps with t = this + 1)
+        else:
+            self.flat = torch.zeros(sum(sizes), device=self.dev)
+            self.gflat = torch.zeros_like(self.flat)
         self.params, self.gviews, self.repeats, off = [], [], [], 0
         self.n_single = 0
         for (owner, attr, old), sz in zip(uniq, sizes):
@@ -584,8 +595,9 @@ class AutogradReconEngine:
             else:
                 self.n_single = off + sz
             off += sz
-        self.exp_avg = torch.zeros_like(self.flat)
-        self.exp_avg_sq = torch.zeros_like(self.flat)
+        n_state = self.sym.shard if self.sym is not None else self.flat.numel()       # the exchange kernel steps this rank's shard only
+        self.exp_avg = torch.zeros(n_state, device=self.dev)
+        self.exp_avg_sq = torch.zeros(n_state, device=self.dev)
         mine = {id(q) for q in self.params}
         self._frozen = [(q, q.requires_grad) for q in unit.parameters() if id(q) not in mine]
         for q, _ in self._frozen:
@@ -617,6 +629,9 @@ class AutogradReconEngine:
                 view.zero_()
             else:
                 view.copy_(g.view_as(view))
+        if self.sym is not None:
+            ops.grad_exchange_adam(self.sym, self.exp_avg, self.exp_avg_sq, self.lr_live, self.xchg_step, self.betas, self.eps)
+            return
         if self.multi_gpu:
             ssq_dist.all_reduce_sum_(self.gflat)
         n1 = self.n_single
@@ -629,7 +644,8 @@ class AutogradReconEngine:
                               self.exp_avg_sq[off:off + sz], self.lr_live, ctr, self.betas, self.eps)
 
     def _state(self):
-        return [self.flat, self.exp_avg, self.exp_avg_sq, self.step_dev] + self.extra_steps + [r[3] for r in self.repeats]
+        return [self.flat, self.exp_avg, self.exp_avg_sq, self.step_dev] + self.extra_steps + [r[3] for r in self.repeats] + \
+            ([self.xchg_step] if self.sym is not None else [])
 
     def capture(self, warm: int = 3):
         snap = [t.clone() for t in self._state()]
@@ -680,4 +696,6 @@ class AutogradReconEngine:
     def close(self):
         for q, flag in self._frozen:
             q.requires_grad_(flag)
-        self.graph = None
+        had_graph, self.graph = self.graph is not None, None
+        if getattr(self, 'sym', None) is not None and had_graph:
+            self.sym.check()                  # a rendezvous of the exchange kernel that timed out invalidates the run

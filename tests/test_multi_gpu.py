@@ -156,6 +156,10 @@ def run(multi):
 single, _ = run(False)
 a, captured = run(True)
 assert captured, "the sharded loop must run as the captured graph"
+D.EXCHANGE = "nccl"                                                   # same run through NCCL all-reduce + ssq_adam_step
+a_nccl, _ = run(True)
+D.EXCHANGE = "p2p"
+assert torch.equal(a, a_nccl), "peer-memory exchange vs NCCL all-reduce + Adam in the shifted loop (two ranks: identical sums)"
 both = [torch.empty_like(a) for _ in range(world)]
 td.all_gather(both, a)
 assert torch.equal(both[0], both[1]), "replicas diverged"            # summed gradients => identical Adam steps
