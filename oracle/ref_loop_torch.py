@@ -104,8 +104,22 @@ def unit_forward(unit, x, wqs, act_state=None):
     return out
 
 
+def rec_loss(pred, tgt, grad=None, mode="mse", p=2.0):
+    """LossFunction's reconstruction term (quant/block_recon.py:154-162)"""
+    if mode == "mse":
+        return lp_loss(pred, tgt, p=p)
+    if mode == "fisher_diag":
+        return ((pred - tgt).pow(2) * grad.pow(2)).sum(1).mean()
+    if mode == "fisher_full":
+        a = (pred - tgt).abs()
+        g = grad.abs()
+        batch_dotprod = torch.sum(a * g, (1, 2, 3)).view(-1, 1, 1, 1)
+        return (batch_dotprod * a * g).mean() / 100
+    raise ValueError(mode)
+
+
 def recon_weight_loop(unit, cached_inps, cached_outs, idx_table, iters, weight=0.01, b_range=(20, 2), warmup=0.2,
-                      p=2.0, alphas=None, start_count=0, t_max=None, state=None):
+                      p=2.0, alphas=None, start_count=0, t_max=None, state=None, opt_mode="mse", cached_grads=None):
     """the weight-rounding loop: returns (alphas, losses). `idx_table[i]` is the mini-batch of iteration i.
     t_max/start_count let a caller run a slice of a longer schedule (the CPU baseline times iterations from the
     middle of the 20 000-iteration schedule, where the regulariser is live and b is non-integer); `state` (a dict) keeps
@@ -128,7 +142,7 @@ def recon_weight_loop(unit, cached_inps, cached_outs, idx_table, iters, weight=0
         wqs = {n: adaround_forward(s["weight"], alphas[n], s["delta"], s["zero_point"], s["n_levels"], True) for n, s in L.items()}
         out_quant = unit_forward(unit, cur_inp, wqs)
         count += 1
-        rec = lp_loss(out_quant, cur_out, p=p)
+        rec = rec_loss(out_quant, cur_out, None if cached_grads is None else cached_grads[idx], opt_mode, p)
         b = temperature(count, t_max, warmup, b_range[0], b_range[1])
         if count < loss_start:
             b = rnd = 0

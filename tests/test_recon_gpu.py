@@ -325,6 +325,49 @@ def test_engine_vs_oracle_loop_on_identical_features(which):
         assert_close(a, ref, rtol=2e-3, what=f"alpha {n} engine vs oracle loop")
 
 
+@pytest.mark.parametrize("mode", ["fisher_diag", "fisher_full"])
+def test_fisher_engine_vs_oracle_loop(mode):
+    """the Fisher-weighted reconstruction losses (quant/block_recon.py:154-162) through the LOOP: ReconEngine against the oracle's
+    restatement of the reference loop on the same cached features, cached gradients (save_grad_data) and index stream"""
+    from oracle import ref_loop_torch as R
+    from shiftedscalequantization_b200.engine import ReconEngine, index_table
+    from shiftedscalequantization_b200.quant.adaptive_rounding import AdaRoundQuantizer
+    from shiftedscalequantization_b200.quant.data_utils import save_grad_data, save_inp_oup_data
+    Q, qnn, cali = build_qnn(res=32, n_cali=32)
+    unit = qnn.model.layer1[0]
+    iters, bs = 12, 16
+    qnn.set_quant_state(False, False); unit.set_quant_state(True, False)
+    mods = [m for m in unit.modules() if isinstance(m, Q.QuantModule)]
+    for m in mods:
+        m.weight_quantizer = AdaRoundQuantizer(uaq=m.weight_quantizer, round_mode='learned_hard_sigmoid', weight_tensor=m.org_weight.data)
+        m.weight_quantizer.soft_targets = True
+    inps, outs = save_inp_oup_data(qnn, unit, cali, True, False, bs)
+    grads = save_grad_data(qnn, unit, cali, False, batch_size=bs)
+    assert grads.shape == outs.shape and float(grads.abs().max()) > 0
+    qnn.set_quant_state(False, False); unit.set_quant_state(True, False)
+    torch.manual_seed(3)
+    tab = index_table(inps.shape[0], bs, iters)
+    spec = _unit_spec(Q, unit)
+    ref_alphas, ref_losses = R.recon_weight_loop(spec, inps.cpu(), outs.cpu(), tab, iters, weight=0.01, b_range=(20, 2), warmup=0.2,
+                                                 opt_mode=mode, cached_grads=grads.cpu())
+    eng = ReconEngine(unit, mods, inps, outs, grads, act_quant=False, iters=iters, weight=0.01, b_range=(20, 2), warmup=0.2,
+                      p=2.0, opt_mode=mode, batch_size=bs, use_graph=True, idx_table=tab, verbose=False)
+    eng.run()
+    last_loss = float(eng.loss_dev)
+    eng.close()
+    names = [n for n, m in unit.named_modules() if isinstance(m, Q.QuantModule)]
+    for n, m in zip(names, mods):
+        a, ref = m.weight_quantizer.alpha.detach().cpu().numpy(), ref_alphas[n].detach().numpy()
+        init = R.init_alpha(spec["layers"][n]["weight"], spec["layers"][n]["delta"]).numpy()
+        assert np.abs(ref - init).max() > 5e-3, "the loop must have moved alpha"
+        # Adam turns any gradient into a step of ~lr: compare the 12-step displacement, sign included
+        same_dir = np.mean(np.sign(a - init) == np.sign(ref - init))
+        print(mode, n, "max |alpha-ref|", np.abs(a - ref).max(), "same direction", same_dir)
+        assert_close(a, ref, rtol=2e-3, what=f"alpha {n}, {mode} engine vs oracle loop")
+        assert same_dir > 0.98, (mode, n, same_dir)
+    assert np.isfinite(last_loss)
+
+
 def test_act_phase_engine_vs_oracle_loop():
     """Activation step-size learning (LSQ, cosine lr, p=2.4): ReconEngine against the oracle's CPU restatement of the
     reference loop on identical cached features, index stream and initial step sizes."""
