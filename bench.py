@@ -390,6 +390,8 @@ def scale_search_bench(Q, qnn, dev, peak_gbs):
         for r, nl in rows:
             ops.mse_scale_search(r, nl, False)
     w_ms = timeit(run, reps=3, warm=1)
+    # what QuantModel.forward does: every layer's search issued together, round-robin on 4 side streams
+    w_many_ms = timeit(lambda: ops.mse_scale_search_many([(r, nl, False) for r, nl in rows]), reps=3, warm=1)
     act = torch.relu(torch.randn(64, 64, 112, 112, device=dev)).reshape(1, -1)
     a_ms = timeit(lambda: ops.mse_scale_search(act, 16, False), reps=3, warm=1)
     # issue-rate roof: 148 SMs x 4 schedulers x 1 warp-instruction/clk; ncu counts 25 warp-instructions per 32 (element,
@@ -404,7 +406,7 @@ def scale_search_bench(Q, qnn, dev, peak_gbs):
         return {"ms": round(ms, 4), "rows": x2d.shape[0], "k": x2d.shape[1], "elems": n, "gbs": round(4 * n / ms / 1e6, 1),
                 "hbm_frac": round(4 * n / ms / 1e6 / peak_gbs, 4), "cand_evals_per_s": round(80 * n / ms * 1e3, 0),
                 "issue_frac_est": round(80 * n / (ms * 1e-3) / pair_roof, 3)}
-    out = {"weights_all_layers_ms": w_ms, "channels": int(sum(r.shape[0] for r, _ in rows)),
+    out = {"weights_all_layers_ms": w_many_ms, "weights_all_layers_one_stream_ms": w_ms, "channels": int(sum(r.shape[0] for r, _ in rows)),
            "weight_elems": int(sum(r.numel() for r, _ in rows)), "activation_tensor_ms": a_ms, "activation_elems": int(act.numel()),
            "round1_ms": {"weights_all_layers": 4.63, "activation_tensor": 17.07, "source": "BENCH_r01.json extra.scale_search"},
            "k2a": {}, "k2b": {}}

@@ -516,46 +516,67 @@ __device__ __forceinline__ uint32_t f2ord(float f) { uint32_t u = __float_as_uin
 __device__ __forceinline__ float ord2f(uint32_t o) { return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o); }
 
 struct RowIv { float vlo, vhi, rlo, rhi; };     // interval of v = fl(w/c) that fits; rlo = 1/|vlo|, rhi = 1/vhi (both > 0)
-__global__ void inp_scale_row_interval_kernel(const float* __restrict__ delta, const float* __restrict__ raw_zp, float x_range,
-                                              float lo, float hi, int64_t oc, int level, const float* __restrict__ cand,
-                                              RowIv* __restrict__ iv, int* __restrict__ need_brute) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per row: the two interval ends are found by a 33-ary search over the ordered float encoding — every round the 32
+// lanes probe 32 points of the bracket at once and a ballot picks the sub-bracket (7 rounds instead of the 31 dependent steps of
+// a bisection; g_row is two IEEE divisions and an add, ~150 cycles of latency per evaluation).
+__global__ void __launch_bounds__(128)
+inp_scale_row_interval_kernel(const float* __restrict__ delta, const float* __restrict__ raw_zp, float x_range,
+                              float lo, float hi, int64_t oc, int level, const float* __restrict__ cand,
+                              RowIv* __restrict__ iv, int* __restrict__ need_brute) {
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
     {   // the estimate assumes the reference's list cand[j] = fp32((level - j) / level) (channelQuantMSE.py:79)
         bool okc = true;
         const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
-        for (int64_t j = r; j < level; j += nthr) okc &= cand[j] == (float)((double)(level - j) / (double)level);
-        if (r == 0) okc = okc && (lo < 0.f) && (hi > 1.0f) && (x_range >= 1.0f);
+        for (int64_t j = gtid; j < level; j += nthr) okc &= cand[j] == (float)((double)(level - j) / (double)level);
+        if (gtid == 0) okc = okc && (lo < 0.f) && (hi > 1.0f) && (x_range >= 1.0f);
         if (!okc) atomicExch(need_brute, 1);
     }
-    if (r >= oc) return;
+    const int64_t r = gtid >> 5;
+    if (r >= oc) return;                                               // whole warps leave together
     const float d = delta[r];
     const float zero = rintf(__fdiv_rn(raw_zp[r], d));
     bool ok = mid_exponent(d) && d > 0.f && zero >= 0.f && zero <= x_range;
     const float g0 = g_row(0.f, d, zero, x_range);
     ok = ok && g0 > lo && g0 < hi;
     RowIv out = {0.f, 0.f, 0.f, 0.f};
-    if (ok) {
-        // largest v >= 0 with g(v) < hi: bisection over the ordered encoding of [0, FLT_MAX]
-        uint32_t a = f2ord(0.f), b = f2ord(3.402823466e+38f);           // invariant: g(a) < hi
+    if (ok) {                                                          // uniform across the warp
+        // probe point of this lane inside the open bracket (x, y), y - x > 1: strictly between, non-decreasing in the lane
+        auto probe = [&](uint32_t x, uint32_t y) {
+            const uint32_t step = (uint32_t)(((uint64_t)(y - x) * (uint32_t)(lane + 1)) / 33u);
+            return x + (step ? step : 1u);
+        };
+        // largest v >= 0 with g(v) < hi; invariant: g(a) < hi, and g(b) >= hi unless b is the top of the range
+        uint32_t a = f2ord(0.f), b = f2ord(3.402823466e+38f);
         if (g_row(ord2f(b), d, zero, x_range) < hi) a = b;
         while (b - a > 1u && a != b) {
-            const uint32_t m = a + ((b - a) >> 1);
-            if (g_row(ord2f(m), d, zero, x_range) < hi) a = m; else b = m;
+            const uint32_t m = probe(a, b);
+            const unsigned below = __ballot_sync(0xffffffffu, g_row(ord2f(m), d, zero, x_range) < hi);   // a prefix of the lanes (g is monotone)
+            const int t = __popc(below);
+            const uint32_t m_lo = __shfl_sync(0xffffffffu, m, t > 0 ? t - 1 : 0), m_hi = __shfl_sync(0xffffffffu, m, t < 32 ? t : 31);
+            if (t > 0) a = m_lo;
+            if (t < 32) b = m_hi;
         }
         out.vhi = ord2f(a);
-        // smallest v <= 0 with g(v) > lo
-        uint32_t c0 = f2ord(-3.402823466e+38f), e0 = f2ord(-0.f);       // invariant: g(e0) > lo
+        // smallest v <= 0 with g(v) > lo; invariant: g(e0) > lo, and g(c0) <= lo unless c0 is the bottom of the range
+        uint32_t c0 = f2ord(-3.402823466e+38f), e0 = f2ord(-0.f);
         if (g_row(ord2f(c0), d, zero, x_range) > lo) e0 = c0;
         while (e0 - c0 > 1u && e0 != c0) {
-            const uint32_t m = c0 + ((e0 - c0) >> 1);
-            if (g_row(ord2f(m), d, zero, x_range) > lo) e0 = m; else c0 = m;
+            const uint32_t m = probe(c0, e0);
+            const unsigned above = __ballot_sync(0xffffffffu, g_row(ord2f(m), d, zero, x_range) > lo);   // a suffix of the lanes
+            const int t = 32 - __popc(above);                          // lanes 0..t-1 are not above
+            const uint32_t m_lo = __shfl_sync(0xffffffffu, m, t > 0 ? t - 1 : 0), m_hi = __shfl_sync(0xffffffffu, m, t < 32 ? t : 31);
+            if (t > 0) c0 = m_lo;
+            if (t < 32) e0 = m_hi;
         }
         out.vlo = ord2f(e0);
         ok = mid_exponent(out.vhi) && out.vhi > 0.f && mid_exponent(out.vlo) && out.vlo < 0.f;
         if (ok) { out.rhi = make_recip(out.vhi).r; out.rlo = make_recip(-out.vlo).r; }
     }
-    iv[r] = out;
-    if (!ok) atomicExch(need_brute, 1);
+    if (lane == 0) {
+        iv[r] = out;
+        if (!ok) atomicExch(need_brute, 1);
+    }
 }
 
 // exact predicate for one element and candidate index j
@@ -680,26 +701,31 @@ inp_scale_fit_kernel(const float* __restrict__ w, const float* __restrict__ delt
                      const float* __restrict__ cand, int level, float x_range, float lo, float hi,
                      int64_t oc, int64_t k, const int* __restrict__ need_brute, int* __restrict__ last_fit /* [k], 0 = none */) {
     if (!__ldg(need_brute)) return;
-    const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int j0 = blockIdx.y * CH;
-    if (col >= k) return;
-    float c[CH]; bool fit[CH];
+    // grid-stride over (column block, candidate block) pairs: the grid is capped so that the usual, idle launch costs a few
+    // hundred empty CTAs instead of one per pair (18 432 of them at level 1024 took 13.6 us to do nothing)
+    const int64_t colblocks = (k + SSQ_THREADS - 1) / SSQ_THREADS, candblocks = (level + CH - 1) / CH;
+    for (int64_t job = blockIdx.x; job < colblocks * candblocks; job += gridDim.x) {
+        const int64_t col = (job % colblocks) * SSQ_THREADS + threadIdx.x;
+        const int j0 = (int)(job / colblocks) * CH;
+        if (col >= k) continue;
+        float c[CH]; bool fit[CH];
 #pragma unroll
-    for (int e = 0; e < CH; ++e) { c[e] = (j0 + e < level) ? __ldg(cand + j0 + e) : 1.f; fit[e] = (j0 + e < level); }
-    for (int64_t r = 0; r < oc; ++r) {
-        float d = __ldg(delta + r);
-        float zero = rintf(__fdiv_rn(__ldg(raw_zp + r), d));
-        float xv = w[r * k + col];
+        for (int e = 0; e < CH; ++e) { c[e] = (j0 + e < level) ? __ldg(cand + j0 + e) : 1.f; fit[e] = (j0 + e < level); }
+        for (int64_t r = 0; r < oc; ++r) {
+            float d = __ldg(delta + r);
+            float zero = rintf(__fdiv_rn(__ldg(raw_zp + r), d));
+            float xv = w[r * k + col];
 #pragma unroll
-        for (int e = 0; e < CH; ++e) {
-            float u = __fdiv_rn(__fadd_rn(__fdiv_rn(__fdiv_rn(xv, c[e]), d), zero), x_range);
-            fit[e] = fit[e] && (u > lo) && (u < hi);
+            for (int e = 0; e < CH; ++e) {
+                float u = __fdiv_rn(__fadd_rn(__fdiv_rn(__fdiv_rn(xv, c[e]), d), zero), x_range);
+                fit[e] = fit[e] && (u > lo) && (u < hi);
+            }
         }
-    }
-    int last = 0;
+        int last = 0;
 #pragma unroll
-    for (int e = 0; e < CH; ++e) if (fit[e]) last = j0 + e + 1;
-    if (last > 0) atomicMax(last_fit + col, last);
+        for (int e = 0; e < CH; ++e) if (fit[e]) last = j0 + e + 1;
+        if (last > 0) atomicMax(last_fit + col, last);
+    }
 }
 // best[col]: prefix length from the finish kernel; last_fit[col] from the brute force
 __global__ void inp_scale_pick_kernel(const float* __restrict__ cand, int level, const int* __restrict__ need_brute,
@@ -831,7 +857,7 @@ extern "C" int ssq_inp_scale_search_ex(const float* w, const float* delta, const
     inp_scale_reset_kernel<<<kgrid, SSQ_THREADS, 0, st>>>(best, last_fit, need_brute, level, force_brute ? 1 : 0, k);
     int e = launch_status();
     if (e) return e;
-    inp_scale_row_interval_kernel<<<(unsigned)((oc + 127) / 128), 128, 0, st>>>(delta, raw_zero_point, x_range, lo, hi, oc, level, cand, iv, need_brute);
+    inp_scale_row_interval_kernel<<<(unsigned)((oc + 3) / 4), 128, 0, st>>>(delta, raw_zero_point, x_range, lo, hi, oc, level, cand, iv, need_brute);
     e = launch_status();
     if (e) return e;
     // sweep: column blocks x row slabs = ONE wave of resident CTAs (a second, partial wave costs as much as a full one)
@@ -848,8 +874,9 @@ extern "C" int ssq_inp_scale_search_ex(const float* w, const float* delta, const
     inp_scale_finish_kernel<<<(unsigned)((k + SSQ_THREADS - 1) / SSQ_THREADS), SSQ_THREADS, 0, st>>>(w, iv, cand, level, oc, k, need_brute, best);
     e = launch_status();
     if (e) return e;
-    dim3 grid(kgrid, (unsigned)((level + CH - 1) / CH));
-    inp_scale_fit_kernel<<<grid, SSQ_THREADS, 0, st>>>(w, delta, raw_zero_point, cand, level, x_range, lo, hi, oc, k, need_brute, last_fit);
+    int64_t fit_jobs = (int64_t)kgrid * ((level + CH - 1) / CH);
+    if (fit_jobs > (int64_t)SSQ_NUM_SMS * 8) fit_jobs = (int64_t)SSQ_NUM_SMS * 8;
+    inp_scale_fit_kernel<<<(unsigned)fit_jobs, SSQ_THREADS, 0, st>>>(w, delta, raw_zero_point, cand, level, x_range, lo, hi, oc, k, need_brute, last_fit);
     e = launch_status();
     if (e) return e;
     inp_scale_pick_kernel<<<kgrid, SSQ_THREADS, 0, st>>>(cand, level, need_brute, best, last_fit, inp_scale, k);

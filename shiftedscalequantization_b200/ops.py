@@ -476,19 +476,56 @@ class ShiftMix(torch.autograd.Function):
 
 
 # --------------------------------------------------------------------------------------- K2
-def mse_scale_search(x2d, n_levels: int, symmetric: bool, p_norm: float = 2.4):
+def mse_scale_search(x2d, n_levels: int, symmetric: bool, p_norm: float = 2.4, ws_tag: str = "search", out=None):
     """x2d: [rows, k]. Returns delta, zero_point, raw_zero_point, best_score (fp32 [rows]) and index (int32)."""
     x2d = _req(x2d, "x")
     rows, k = x2d.shape
     dev = x2d.device
-    delta = torch.empty(rows, dtype=torch.float32, device=dev)
-    zp = torch.empty_like(delta); raw = torch.empty_like(delta); score = torch.empty_like(delta)
-    idx = torch.empty(rows, dtype=torch.int32, device=dev)
-    ws = workspace(dev, _lib.load().ssq_mse_scale_search_ws_bytes(rows, k), "search")
+    if out is None:
+        delta = torch.empty(rows, dtype=torch.float32, device=dev)
+        zp = torch.empty_like(delta); raw = torch.empty_like(delta); score = torch.empty_like(delta)
+        idx = torch.empty(rows, dtype=torch.int32, device=dev)
+    else:
+        delta, zp, raw, score, idx = out
+    ws = workspace(dev, _lib.load().ssq_mse_scale_search_ws_bytes(rows, k), ws_tag)
     _call("ssq_mse_scale_search", x2d.data_ptr(), rows, k, int(n_levels), int(bool(symmetric)), float(p_norm),
           delta.data_ptr(), zp.data_ptr(), raw.data_ptr(), score.data_ptr(), idx.data_ptr(),
           ws.data_ptr(), ws.numel(), _stream(x2d))
     return delta, zp, raw, score, idx
+
+
+_search_streams = {}
+
+
+def mse_scale_search_many(jobs, n_streams: int = 4):
+    """the searches of several independent tensors (jobs: (x2d, n_levels, symmetric[, p_norm]) each) issued round-robin on
+    `n_streams` side streams forked from the current stream and joined back into it: a model's layers have 64-512 rows each,
+    i.e. one launch fills a fraction of the 148 SMs x 8 resident CTAs, and their searches do not depend on each other
+    (quant_layer.py:100-166 runs them one after the other only because each quantiser initialises itself lazily).
+    Results are bit-identical to calling mse_scale_search per tensor; outputs are allocated on the calling stream."""
+    if not jobs:
+        return []
+    dev = jobs[0][0].device
+    main = torch.cuda.current_stream(dev)
+    key = (dev.index, n_streams)
+    if key not in _search_streams:
+        _search_streams[key] = [torch.cuda.Stream(dev) for _ in range(n_streams)]
+    streams = _search_streams[key]
+    outs = []
+    for x2d, *_rest in jobs:                                   # outputs belong to the calling stream's allocator pool
+        rows = x2d.shape[0]
+        f = lambda dt=torch.float32: torch.empty(rows, dtype=dt, device=dev)
+        outs.append((f(), f(), f(), f(), f(torch.int32)))
+    for s in streams:
+        s.wait_stream(main)
+    for i, (job, out) in enumerate(zip(jobs, outs)):
+        x2d, n_levels, symmetric = job[:3]
+        p_norm = job[3] if len(job) > 3 else 2.4
+        with torch.cuda.stream(streams[i % n_streams]):
+            mse_scale_search(x2d.contiguous(), n_levels, symmetric, p_norm, ws_tag=f"search{i % n_streams}", out=out)
+    for s in streams:
+        main.wait_stream(s)
+    return outs
 
 
 def row_minmax(x2d):

@@ -59,7 +59,39 @@ class QuantModel(nn.Module):
             m.set_quant_init_state()
 
     def forward(self, input):
+        self._init_weight_scales_together()
         return self.model(input)
+
+    def _init_weight_scales_together(self):
+        """The per-channel MSE scale search of a layer depends on its weights only (quant_layer.py:100-166), so the searches of
+        every layer that is about to initialise itself in this forward are issued together, round-robin on side streams: a layer
+        has 64-512 output channels, i.e. one launch fills a fraction of the GPU. Each quantiser ends up exactly as its own lazy
+        initialisation would leave it (same kernel, same inputs: bit-identical delta / zero point). One host check for all
+        layers instead of one per layer; anything unusual (an all-zero channel, several ranks, per-tensor or `max` scales, rows
+        too long for the row kernel) is left to the lazy per-layer path, which raises what upstream raises."""
+        import torch
+        from .. import dist as ssq_dist, ops
+        from .quant_layer import UniformAffineQuantizer
+        todo = []
+        for m in self._quant_modules():
+            q = m.weight_quantizer
+            if (m.use_weight_quant and m.cache_features == 'none' and m._engine_weight is None and type(q) is UniformAffineQuantizer
+                    and q.inited is False and q.scale_method == 'mse' and q.channel_wise and m.weight.is_cuda
+                    and m.weight.dtype == torch.float32 and 0 < m.weight[0].numel() <= 48 * 1024):
+                todo.append(m)
+        if len(todo) < 2 or ssq_dist.world_size() > 1:
+            return
+        outs = ops.mse_scale_search_many([(m.weight.detach().reshape(m.weight.shape[0], -1), m.weight_quantizer.n_levels,
+                                           m.weight_quantizer.sym) for m in todo])
+        if bool(torch.stack([(o[4] < 0).any() for o in outs]).any()):
+            return                                              # an all-NaN-score channel somewhere: the lazy path raises at that layer
+        for m, (delta, zp, raw, _score, _idx) in zip(todo, outs):
+            q = m.weight_quantizer
+            shape = (-1, 1, 1, 1) if m.weight.dim() == 4 else (-1, 1)
+            q.delta = nn.Parameter(delta.view(shape))
+            q.zero_point = nn.Parameter(zp.view(shape))
+            q.raw_zero_point = raw.view(shape)
+            q.inited = True
 
     def set_first_last_layer_to_8bit(self):
         """8-bit stem/head (quant_model.py:59-69): first layer weights+acts, last layer weights, and the

@@ -325,6 +325,34 @@ def test_engine_vs_oracle_loop_on_identical_features(which):
         assert_close(a, ref, rtol=2e-3, what=f"alpha {n} engine vs oracle loop")
 
 
+def test_weight_scales_initialised_together_equal_the_lazy_per_layer_init():
+    """QuantModel.forward issues every layer's MSE scale search together on side streams; each quantiser must end up exactly
+    as its own lazy initialisation (quant_layer.py:77-98 on first use) leaves it"""
+    from shiftedscalequantization_b200 import quant as Q, zoo
+    res = {}
+    for together in (True, False):
+        torch.manual_seed(1005)
+        cnn = zoo.resnet18(num_classes=10).cuda().eval()
+        qnn = Q.QuantModel(cnn, dict(WQ), dict(AQ)).cuda().eval()
+        qnn.set_first_last_layer_to_8bit()
+        qnn.set_quant_state(True, False)
+        mods = [m for m in qnn.modules() if isinstance(m, Q.QuantModule)]
+        if together:
+            with torch.no_grad():
+                qnn(torch.randn(4, 3, 32, 32).cuda())
+        else:
+            for m in mods:                                   # the lazy path, layer by layer
+                m.weight_quantizer(m.weight)
+        assert all(m.weight_quantizer.inited for m in mods)
+        res[together] = [(m.weight_quantizer.delta.detach().cpu().numpy(), m.weight_quantizer.zero_point.detach().cpu().numpy(),
+                          m.weight_quantizer.raw_zero_point.detach().cpu().numpy()) for m in mods]
+    assert len(res[True]) == 21
+    for a, b in zip(res[True], res[False]):
+        for x, y, what in zip(a, b, ("delta", "zero_point", "raw_zero_point")):
+            assert x.shape == y.shape
+            assert_exact(x, y, f"{what}: searched together vs lazily")
+
+
 @pytest.mark.parametrize("mode", ["fisher_diag", "fisher_full"])
 def test_fisher_engine_vs_oracle_loop(mode):
     """the Fisher-weighted reconstruction losses (quant/block_recon.py:154-162) through the LOOP: ReconEngine against the oracle's
