@@ -148,7 +148,7 @@ def mobilenetv2_mse(args, rank, local, world, dev):
             fn()
         e1.record(); torch.cuda.synchronize(dev)
         return e0.elapsed_time(e1) / reps
-    k2a_ms = ev(lambda: [ops.mse_scale_search(r, nl, False) for r, nl in rows])
+    k2a_ms = ev(lambda: ops.mse_scale_search_many([(r, nl, False) for r, nl in rows]))        # as QuantModel.forward issues them
     qnn.set_quant_state(True, False)
     torch.cuda.synchronize(dev); t0 = time.perf_counter()
     with torch.no_grad():
