@@ -256,10 +256,14 @@ int ssq_row_minmax(const float* x, int64_t rows, int64_t k, float* row_min, floa
  * inp_scale[col] = the LAST fitting candidate, else it keeps its incoming value.
  * zero = rint(raw_zp/delta) per row is computed by the kernel.
  * One pass over w (4 B/element, independent of `level`): the predicate is monotone in the
- * candidate, so each element's fitting prefix is estimated in closed form and settled with
- * the exact predicate near boundaries; inputs outside the proof's preconditions (a foreign
- * candidate list, zero outside [0, L-1], lo >= 0, hi <= 1) run the brute-force sweep of all
- * `level` candidates instead. _ex(force_brute=1) selects the brute force explicitly. */
+ * candidate and a column's answer is set by its tightest element, so the pass keeps
+ * max_r |w| / |V_r| per column (one select, one multiply, one integer max per element) and a
+ * finish kernel turns it into the fitting prefix, settling with the exact predicate the
+ * columns whose estimate lies within the error margin of a candidate boundary; inputs outside
+ * the proof's preconditions (a foreign candidate list, zero outside [0, L-1], lo >= 0,
+ * hi <= 1) run the brute-force sweep of all `level` candidates instead (device-side switch, no
+ * host round trip). Four launches: row intervals, sweep, finish, brute force (idle).
+ * _ex(force_brute=1) selects the brute force explicitly. ws: zero-filled once by the caller. */
 int ssq_inp_scale_search(const float* w, const float* delta, const float* raw_zero_point,
                          const float* cand, int level, float x_range, float lo, float hi,
                          float* inp_scale, int64_t oc, int64_t k,

@@ -16,6 +16,7 @@
 //       the reference predicate is monotone in the candidate, which turns the `level`-candidate sweep into one
 //       estimate per element, verified with the exact predicate wherever the estimate is near a boundary.
 #include "ssq_common.cuh"
+#include <atomic>
 
 namespace ssq {
 
@@ -522,15 +523,17 @@ struct RowIv { float vlo, vhi, rlo, rhi; };     // interval of v = fl(w/c) that 
 __global__ void __launch_bounds__(128)
 inp_scale_row_interval_kernel(const float* __restrict__ delta, const float* __restrict__ raw_zp, float x_range,
                               float lo, float hi, int64_t oc, int level, const float* __restrict__ cand,
-                              RowIv* __restrict__ iv, int* __restrict__ need_brute) {
+                              RowIv* __restrict__ iv, int* __restrict__ need_brute, int epoch,
+                              int* __restrict__ best, int* __restrict__ last_fit, int64_t k) {
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
+    if (gtid < k) { best[gtid] = 0; last_fit[gtid] = 0; }           // the per-column slots of this call (the grid covers k threads)
     {   // the estimate assumes the reference's list cand[j] = fp32((level - j) / level) (channelQuantMSE.py:79)
         bool okc = true;
         const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
         for (int64_t j = gtid; j < level; j += nthr) okc &= cand[j] == (float)((double)(level - j) / (double)level);
         if (gtid == 0) okc = okc && (lo < 0.f) && (hi > 1.0f) && (x_range >= 1.0f);
-        if (!okc) atomicExch(need_brute, 1);
+        if (!okc) atomicExch(need_brute, epoch);
     }
     const int64_t r = gtid >> 5;
     if (r >= oc) return;                                               // whole warps leave together
@@ -575,7 +578,7 @@ inp_scale_row_interval_kernel(const float* __restrict__ delta, const float* __re
     }
     if (lane == 0) {
         iv[r] = out;
-        if (!ok) atomicExch(need_brute, 1);
+        if (!ok) atomicExch(need_brute, epoch);
     }
 }
 
@@ -603,8 +606,8 @@ __device__ __forceinline__ float k2b_t(float x, float rlo, float rhi) { return f
 // sweep: tmax[col] = max over the slab's rows of t, as int bit patterns (tmax zeroed by the reset kernel)
 __global__ void __launch_bounds__(SSQ_THREADS, K2B_CTAS)
 inp_scale_sweep_kernel(const float* __restrict__ w, const RowIv* __restrict__ iv, int64_t oc, int64_t k, int64_t rows_per_cta,
-                       const int* __restrict__ need_brute, int* __restrict__ tmax) {
-    if (__ldg(need_brute)) return;
+                       const int* __restrict__ need_brute, int epoch, int force_brute, int* __restrict__ tmax) {
+    if (force_brute || __ldg(need_brute) == epoch) return;
     const int64_t col0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * K2B_COLS;
     if (col0 >= k) return;
     const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
@@ -639,13 +642,14 @@ inp_scale_sweep_kernel(const float* __restrict__ w, const RowIv* __restrict__ iv
     for (int e = 0; e < K2B_COLS; ++e)
         if (col0 + e < k && tm[e] != 0) atomicMax(tmax + col0 + e, tm[e]);
 }
-// finish: one CTA per 256 columns. best[col] holds max t on entry and the prefix length (0 = nothing fits) on exit. Columns whose
+// finish: one CTA per 256 columns. best[col] holds max t; the prefix length p picks inp_scale[col] = cand[p - 1]. Columns whose
 // estimate is not decisive are settled by the WHOLE CTA, one after the other: the column is re-read (strided, 4 rows of loads in
 // flight per thread — a lone warp walking 4096 rows one dependent load at a time took longer than the sweep itself).
 __global__ void __launch_bounds__(SSQ_THREADS)
 inp_scale_finish_kernel(const float* __restrict__ w, const RowIv* __restrict__ iv, const float* __restrict__ cand, int level,
-                        int64_t oc, int64_t k, const int* __restrict__ need_brute, int* __restrict__ best) {
-    if (__ldg(need_brute)) return;
+                        int64_t oc, int64_t k, const int* __restrict__ need_brute, int epoch, int force_brute,
+                        const int* __restrict__ best, float* __restrict__ inp_scale) {
+    if (force_brute || __ldg(need_brute) == epoch) return;
     __shared__ int s_n;
     __shared__ int s_col[SSQ_THREADS], s_min[SSQ_THREADS];
     const int tid = threadIdx.x, lane = tid & 31;
@@ -669,7 +673,7 @@ inp_scale_finish_kernel(const float* __restrict__ w, const RowIv* __restrict__ i
     const int n_settle = s_n;
     for (int i = 0; i < n_settle; ++i) {
         const int64_t c = col_base + s_col[i];
-        const float near = fmaf(-flevel, __int_as_float(best[c]), flevel) + 3.0f * margin;   // best[] is written after the loop
+        const float near = fmaf(-flevel, __int_as_float(best[c]), flevel) + 3.0f * margin;
         int local = level;
         for (int64_t r0 = tid; r0 < oc; r0 += 4 * SSQ_THREADS) {
             float x[4]; RowIv I[4];
@@ -691,7 +695,7 @@ inp_scale_finish_kernel(const float* __restrict__ w, const RowIv* __restrict__ i
     }
     __syncthreads();
     if (settle) p = s_min[slot];
-    if (valid) best[col] = p;
+    if (valid && p > 0) inp_scale[col] = __ldg(cand + p - 1);          // the LAST fitting candidate; none fits: left as it is
 }
 
 // brute force: every (column, candidate) with the reference expression; runs only when need_brute is set (or forced)
@@ -699,8 +703,10 @@ constexpr int CH = 8;   // candidates per thread
 __global__ void __launch_bounds__(SSQ_THREADS)
 inp_scale_fit_kernel(const float* __restrict__ w, const float* __restrict__ delta, const float* __restrict__ raw_zp,
                      const float* __restrict__ cand, int level, float x_range, float lo, float hi,
-                     int64_t oc, int64_t k, const int* __restrict__ need_brute, int* __restrict__ last_fit /* [k], 0 = none */) {
-    if (!__ldg(need_brute)) return;
+                     int64_t oc, int64_t k, int* __restrict__ need_brute, int epoch, int force_brute, unsigned int* __restrict__ ticket,
+                     int* __restrict__ last_fit /* [k], 0 = none */, float* __restrict__ inp_scale) {
+    if (!(force_brute || __ldg(need_brute) == epoch)) return;
+    __shared__ bool s_last;
     // grid-stride over (column block, candidate block) pairs: the grid is capped so that the usual, idle launch costs a few
     // hundred empty CTAs instead of one per pair (18 432 of them at level 1024 took 13.6 us to do nothing)
     const int64_t colblocks = (k + SSQ_THREADS - 1) / SSQ_THREADS, candblocks = (level + CH - 1) / CH;
@@ -726,22 +732,21 @@ inp_scale_fit_kernel(const float* __restrict__ w, const float* __restrict__ delt
         for (int e = 0; e < CH; ++e) if (fit[e]) last = j0 + e + 1;
         if (last > 0) atomicMax(last_fit + col, last);
     }
+    // the last CTA to finish turns last_fit into inp_scale and leaves the flag clean for the next call on this workspace
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int64_t col = threadIdx.x; col < k; col += blockDim.x) {
+        const int b = __ldcg(last_fit + col);
+        if (b > 0) inp_scale[col] = __ldg(cand + b - 1);
+    }
+    if (threadIdx.x == 0) { *ticket = 0u; *need_brute = 0; }
 }
-// best[col]: prefix length from the finish kernel; last_fit[col] from the brute force
-__global__ void inp_scale_pick_kernel(const float* __restrict__ cand, int level, const int* __restrict__ need_brute,
-                                      int* __restrict__ best, int* __restrict__ last_fit, float* __restrict__ inp_scale, int64_t k) {
-    int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= k) return;
-    const int b = __ldg(need_brute) ? last_fit[col] : best[col];
-    if (b > 0) inp_scale[col] = __ldg(cand + b - 1);
-    best[col] = 0; last_fit[col] = 0;
-}
-__global__ void inp_scale_reset_kernel(int* __restrict__ best, int* __restrict__ last_fit, int* need_brute, int level, int force_brute, int64_t k) {
-    int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (col == 0) *need_brute = force_brute;
-    if (col < k) { best[col] = 0; last_fit[col] = 0; }
-}
-
 constexpr int64_t ROW_SMEM_MAX_ELEMS = 48 * 1024;  // 192 KB of the 227 KB a CTA may use
 constexpr int TENSOR_GRID = SSQ_NUM_SMS * 4;
 
@@ -831,7 +836,7 @@ extern "C" int ssq_mse_scale_search(const float* x, int64_t rows, int64_t k, int
     return SSQ_OK;
 }
 
-// workspace: [need_brute : 64 B][best : k ints][last_fit : k ints][RowIv : oc]
+// workspace: [header 64 B: brute-force epoch flag, ticket][best (max t) : k ints][last_fit : k ints][RowIv : oc]
 extern "C" size_t ssq_inp_scale_search_ws_bytes2(int64_t oc, int64_t k) {
     const size_t kk = (size_t)(k > 0 ? k : 1), rr = (size_t)(oc > 0 ? oc : 1);
     return 64 + 2 * ((kk * sizeof(int) + 15) / 16 * 16) + rr * sizeof(RowIv);
@@ -853,14 +858,21 @@ extern "C" int ssq_inp_scale_search_ex(const float* w, const float* delta, const
     int* best = reinterpret_cast<int*>(base + 64);
     int* last_fit = reinterpret_cast<int*>(base + 64 + karr);
     RowIv* iv = reinterpret_cast<RowIv*>(base + 64 + 2 * karr);
-    const unsigned kgrid = (unsigned)((k + SSQ_THREADS - 1) / SSQ_THREADS);
-    inp_scale_reset_kernel<<<kgrid, SSQ_THREADS, 0, st>>>(best, last_fit, need_brute, level, force_brute ? 1 : 0, k);
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(base + 4);
+    // "this call needs the brute force" is the flag holding THIS call's epoch: nothing has to be cleared before use, and a stale
+    // value left by anything else never matches (0 is never an epoch; the brute-force kernel writes 0 back when it is done)
+    static std::atomic<int> s_epoch{0};
+    int epoch = ++s_epoch;
+    if (epoch <= 0) { s_epoch = 1; epoch = 1; }
+    const int force = force_brute ? 1 : 0;
+    // launch 1: per-row intervals (one warp per row) + this call's per-column slots zeroed
+    int64_t prep = (oc + 3) / 4;
+    if (prep < (k + 127) / 128) prep = (k + 127) / 128;
+    inp_scale_row_interval_kernel<<<(unsigned)prep, 128, 0, st>>>(delta, raw_zero_point, x_range, lo, hi, oc, level, cand, iv, need_brute, epoch,
+                                                                   best, last_fit, k);
     int e = launch_status();
     if (e) return e;
-    inp_scale_row_interval_kernel<<<(unsigned)((oc + 3) / 4), 128, 0, st>>>(delta, raw_zero_point, x_range, lo, hi, oc, level, cand, iv, need_brute);
-    e = launch_status();
-    if (e) return e;
-    // sweep: column blocks x row slabs = ONE wave of resident CTAs (a second, partial wave costs as much as a full one)
+    // launch 2, sweep: column blocks x row slabs = ONE wave of resident CTAs (a second, partial wave costs as much as a full one)
     const int64_t colblocks = (k + (int64_t)SSQ_THREADS * K2B_COLS - 1) / ((int64_t)SSQ_THREADS * K2B_COLS);
     int64_t slabs = ((int64_t)SSQ_NUM_SMS * K2B_CTAS) / colblocks;
     if (slabs > (oc + 2 * K2B_ROWS - 1) / (2 * K2B_ROWS)) slabs = (oc + 2 * K2B_ROWS - 1) / (2 * K2B_ROWS);
@@ -868,18 +880,19 @@ extern "C" int ssq_inp_scale_search_ex(const float* w, const float* delta, const
     if (slabs < 1) slabs = 1;
     const int64_t rows_per_cta = (oc + slabs - 1) / slabs;
     slabs = (oc + rows_per_cta - 1) / rows_per_cta;
-    inp_scale_sweep_kernel<<<dim3((unsigned)colblocks, (unsigned)slabs), SSQ_THREADS, 0, st>>>(w, iv, oc, k, rows_per_cta, need_brute, best);
+    inp_scale_sweep_kernel<<<dim3((unsigned)colblocks, (unsigned)slabs), SSQ_THREADS, 0, st>>>(w, iv, oc, k, rows_per_cta, need_brute, epoch, force, best);
     e = launch_status();
     if (e) return e;
-    inp_scale_finish_kernel<<<(unsigned)((k + SSQ_THREADS - 1) / SSQ_THREADS), SSQ_THREADS, 0, st>>>(w, iv, cand, level, oc, k, need_brute, best);
+    // launch 3: prefix per column -> inp_scale
+    const unsigned kgrid = (unsigned)((k + SSQ_THREADS - 1) / SSQ_THREADS);
+    inp_scale_finish_kernel<<<kgrid, SSQ_THREADS, 0, st>>>(w, iv, cand, level, oc, k, need_brute, epoch, force, best, inp_scale);
     e = launch_status();
     if (e) return e;
+    // launch 4: the brute force, idle (a few hundred empty CTAs) unless the flag carries this epoch or the caller forces it
     int64_t fit_jobs = (int64_t)kgrid * ((level + CH - 1) / CH);
     if (fit_jobs > (int64_t)SSQ_NUM_SMS * 8) fit_jobs = (int64_t)SSQ_NUM_SMS * 8;
-    inp_scale_fit_kernel<<<(unsigned)fit_jobs, SSQ_THREADS, 0, st>>>(w, delta, raw_zero_point, cand, level, x_range, lo, hi, oc, k, need_brute, last_fit);
-    e = launch_status();
-    if (e) return e;
-    inp_scale_pick_kernel<<<kgrid, SSQ_THREADS, 0, st>>>(cand, level, need_brute, best, last_fit, inp_scale, k);
+    inp_scale_fit_kernel<<<(unsigned)fit_jobs, SSQ_THREADS, 0, st>>>(w, delta, raw_zero_point, cand, level, x_range, lo, hi, oc, k, need_brute, epoch, force,
+                                                                     ticket, last_fit, inp_scale);
     return launch_status();
 }
 
