@@ -340,6 +340,40 @@ def test_inp_scale_search_one_pass_equals_brute_force(ops, level, thr, bits):
         assert_exact(host(fast), ref.reshape(-1), "inp_scale vs oracle")
 
 
+@pytest.mark.parametrize("seed,oc,k,level,bits,thr", [(1, 300, 2052, 16, 2, 1.5), (2, 1100, 516, 100, 3, 1.0), (3, 64, 4100, 1024, 4, 2.0),
+                                                         (4, 513, 1030, 3, 2, 1.5), (5, 2048, 260, 64, 2, 0.7)])
+def test_inp_scale_search_many_columns_on_candidate_boundaries(ops, seed, oc, k, level, bits, thr):
+    """the column-wise decision of the one-pass search under stress: in most columns the tightest element sits within a few ulps
+    of a candidate boundary (w = V c_j (1 +- n ulp)), so most columns take the finish kernel's exact settle path — many per CTA —
+    and several near-maximal elements compete in one column. Must equal the brute force bit for bit."""
+    r = rng(7000 + seed)
+    L = 2 ** bits
+    w = (r.standard_normal((oc, k)) * 0.01).astype(np.float32)
+    d, z, raw = zip(*[O.max_init(row, bits) for row in w])
+    d = np.array(d, np.float32); raw = np.array(raw, np.float32)
+    lo = np.float32(0.0 - 0.5 / (L - 1) * thr); hi = np.float32(1.0 + 0.5 / (L - 1) * thr)
+    cand_np = np.array([i / level for i in range(level, 0, -1)], dtype=np.float32)
+    zero = np.rint(raw / d)
+    vmax = (d * (hi * (L - 1) - zero)).astype(np.float32)            # ~ the positive end of each row's fitting interval
+    vmin = (d * (lo * (L - 1) - zero)).astype(np.float32)            # ~ the negative end
+    cols = r.permutation(k)[: (3 * k) // 4]                          # three quarters of the columns get boundary elements
+    for j in cols:
+        c = cand_np[r.integers(0, level)]
+        for i in r.integers(0, oc, size=r.integers(1, 4)):           # one to three competing rows
+            end = vmax[i] if r.random() < 0.5 else vmin[i]
+            w[i, j] = np.float32(end * c) * np.float32(1 + r.integers(-4, 5) * 6e-8)
+    cand = torch.from_numpy(cand_np).cuda()
+    fast = torch.ones(k, device="cuda"); brute = torch.ones(k, device="cuda")
+    ops.inp_scale_search(dev(w), dev(d), dev(raw), cand, L - 1, float(lo), float(hi), fast)
+    ops.inp_scale_search(dev(w), dev(d), dev(raw), cand, L - 1, float(lo), float(hi), brute, force_brute=True)
+    assert_exact(host(fast), host(brute), f"inp_scale, {oc}x{k}, level {level}")
+    assert len(np.unique(host(fast))) > 1                            # the columns really end up on different candidates
+    # the same workspace serves the next call: a forced brute force must not leave the switch on
+    again = torch.ones(k, device="cuda")
+    ops.inp_scale_search(dev(w), dev(d), dev(raw), cand, L - 1, float(lo), float(hi), again)
+    assert_exact(host(again), host(fast), "second call on the same workspace")
+
+
 def test_inp_scale_search_falls_back_outside_its_preconditions(ops):
     """a zero point outside [0, L-1], a foreign candidate list and lo >= 0 take the brute-force path: same answers as the
     forced brute force, and as the oracle"""
