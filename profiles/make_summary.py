@@ -166,7 +166,8 @@ def k2_table(tag):
     md = [f"# {tag} — scale-search kernels (K2a / K2b) under ncu\n",
           "Command (after `python bench.py --k2-only` exited 0 without ncu): `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,"
           "dram__bytes_write.sum,smsp__issue_active...,smsp__inst_executed.sum,sm__inst_executed_pipe_xu.sum --clock-control none -k regex:mse_search|mse_rank|"
-          "mse_settle|inp_scale_sweep|inp_scale_fit|row_minmax python bench.py --k2-only` (profiles/capture_r02.sh). One row per (kernel, grid) — the last "
+          "mse_settle|inp_scale|row_minmax python bench.py --k2-only` (profiles/capture_r02_final.sh; the inp_scale rows were re-captured by profiles/capture_r02h.sh after "
+          "the K2b call became four launches). One row per (kernel, grid) — the last "
           "launch of that shape; durations are cold-cache single launches (CUDA-event numbers: BENCH extra.scale_search).\n",
           "| kernel | grid | launches | us | DRAM MB (r+w) | DRAM % of ncu peak | issue-active % | warps-active % | regs | warp-instr (M) | XU-pipe instr (M) |",
           "|---|---|---|---|---|---|---|---|---|---|---|"]
