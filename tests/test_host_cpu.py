@@ -51,6 +51,43 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert lib.ssq_recon_loss(p, p, None, None, p, None, 2, 8, 4.0, 7, 2.0, None, None, 0, None) == -4     # mode
 
 
+def test_host_side_sizing_functions_of_the_abi():
+    """the ABI's pure host functions (no CUDA call inside): the exchange kernel's shard plan covers the flat buffer exactly once,
+    workspaces grow with the problem, packed rows are byte-aligned, argument errors of the round-2 entry points"""
+    from shiftedscalequantization_b200 import _lib
+    lib = _lib.load()
+    pad = lib.ssq_exchange_pad_bytes()
+    assert pad > 0 and pad % 4 == 0
+    for n in (0, 4, 8, 1000, 4096, 73728, 4718592, 15232128):
+        for world in (1, 2, 3, 4, 8, 16):
+            shard = lib.ssq_exchange_shard_elems(n, world)
+            assert shard % 4 == 0 and shard * world >= n                   # every vector has an owner
+            if n:
+                assert shard * (world - 1) < n + 4 * world                 # ... and the last rank's shard starts inside (or at the end of) the buffer
+            # ranks' ranges [r*shard, min((r+1)*shard, n)) are disjoint and cover [0, n)
+            covered = sum(max(0, min((r + 1) * shard, n) - min(r * shard, n)) for r in range(world))
+            assert covered == n
+    assert lib.ssq_exchange_shard_elems(-4, 2) == 0 and lib.ssq_exchange_shard_elems(16, 0) == 0
+    assert lib.ssq_inp_scale_search_ws_bytes2(512, 2304) > 2 * 2304 * 4 + 512 * 16
+    assert lib.ssq_inp_scale_search_ws_bytes2(4096, 36864) > lib.ssq_inp_scale_search_ws_bytes2(512, 2304)
+    assert lib.ssq_inp_scale_search_ws_bytes(2304) >= lib.ssq_inp_scale_search_ws_bytes2(65536, 2304)
+    assert lib.ssq_mse_scale_search_ws_bytes(1, 51380224) > 0
+    for bits, per in ((1, 8), (2, 4), (4, 2), (8, 1)):
+        for k in (1, 9, 147, 576, 4608):
+            assert lib.ssq_packed_row_bytes(k, bits) == (k + per - 1) // per
+    buf = (ctypes.c_float * 64)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    # K2b: NULL pointers, a workspace that is too small, empty problems
+    assert lib.ssq_inp_scale_search(None, p, p, p, 16, 3.0, -0.25, 1.25, p, 4, 4, p, 1 << 20, None) == -1
+    assert lib.ssq_inp_scale_search(p, p, p, p, 16, 3.0, -0.25, 1.25, p, 4, 4, p, 8, None) != 0
+    assert lib.ssq_inp_scale_search(p, p, p, p, 16, 3.0, -0.25, 1.25, p, 0, 4, None, 0, None) == 0
+    # exchange: world out of range, a buffer length that is not a multiple of four floats
+    arr = (ctypes.c_void_p * 2)(p, p)
+    assert lib.ssq_grad_exchange_adam(arr, arr, arr, 0, 17, 16, p, p, p, p, 0.9, 0.999, 1e-8, None, p, p, p, 1 << 20, None) == -2
+    assert lib.ssq_grad_exchange_adam(arr, arr, arr, 0, 2, 6, p, p, p, p, 0.9, 0.999, 1e-8, None, p, p, p, 1 << 20, None) == -2
+    assert lib.ssq_grad_exchange_adam(None, arr, arr, 0, 2, 8, p, p, p, p, 0.9, 0.999, 1e-8, None, p, p, p, 1 << 20, None) == -1
+
+
 def test_quantiser_refuses_cpu_tensors():
     from shiftedscalequantization_b200 import ops
     from shiftedscalequantization_b200._lib import SsqError
