@@ -245,6 +245,13 @@ rows = torch.arange(9.).reshape(9, 1)
 lo, hi = D.shard_range(9)
 full = D.all_gather_rows(rows[lo:hi] * 2, 9)
 assert torch.equal(full, rows * 2)
+# the peer-memory exchange needs symmetric (P2P) device memory: where it cannot be set up — here: CPU tensors under gloo —
+# EVERY rank must agree to fall back to the NCCL/gloo all-reduce path (a MIN all-reduce of the per-rank outcome), never hang
+assert D.EXCHANGE == "p2p"
+unit = D.symmetric_unit_or_none(64, torch.device("cpu"))
+assert unit is None
+D.EXCHANGE = "nccl"
+assert D.symmetric_unit_or_none(64, torch.device("cpu")) is None      # switched off: no collective, no allocation
 sys.stdout.write(f"rank {rk} ok\n"); sys.stdout.flush()      # one write per rank: the two ranks share the pipe
 '''
 
