@@ -4,6 +4,12 @@
 weight-scale init -> block/layer reconstruction of every unit -> activation-scale init -> activation reconstruction.
 
     python examples/run_ptq.py --arch resnet18 --n_bits_w 2 --n_bits_a 4 --res 224 --num_samples 1024 --iters_w 20000
+
+Several GPUs of one box (the flow of Brecq/main_imagenet_dist.py:156-221): one rank per GPU under torchrun; every rank builds
+the same seeded model, keeps its shard of the calibration set (num_samples / N images), and the reconstruction calls run with
+multi_gpu=True — the unit's gradients are summed over the ranks every iteration, so all replicas learn the same parameters:
+
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 examples/run_ptq.py --arch regnetx_3200m
 """
 import argparse
 import os
@@ -54,8 +60,14 @@ def main(argv=None):
                     help='learn the input-channel group R: shifted-scale ChannelQuant + fused shift/rounding loop on BasicBlock units')
     args = ap.parse_args(argv)
 
-    dev = torch.device(args.device_gpu)
+    from shiftedscalequantization_b200 import dist as ssq_dist
+    rank, local, world = ssq_dist.init_from_env()
+    multi = world > 1
+    dev = torch.device('cuda', local) if multi else torch.device(args.device_gpu)
     torch.cuda.set_device(dev)
+    if rank != 0:                                              # one voice: the other ranks compute silently
+        import builtins
+        builtins.print = lambda *a, **k: None
     torch.backends.cudnn.allow_tf32 = bool(args.tf32)
     torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
     torch.backends.cudnn.benchmark = bool(args.cudnn_benchmark)
@@ -67,6 +79,10 @@ def main(argv=None):
     qnn = QuantModel(model=cnn, weight_quant_params=wq, act_quant_params=aq).to(dev).eval()
     qnn.set_first_last_layer_to_8bit()
     cali = torch.randn(args.num_samples, 3, args.res, args.res)
+    if multi:
+        cali = ssq_dist.shard_calibration(cali)                # main_imagenet_dist.py:165: num_samples / ngpus images per rank
+        from shiftedscalequantization_b200.quant import layer_recon_shiftedScale as LS
+        LS.MULTI_GPU = True                                    # the shifted-scale loops' own switch
 
     t0 = time.time()
     qnn.set_quant_state(True, False)
@@ -122,7 +138,7 @@ def main(argv=None):
     t0 = time.time()
     recon_model(qnn, cali_data=cali, iters=args.iters_w, weight=args.weight, asym=True, b_range=(args.b_start, args.b_end),
                 warmup=args.warmup, act_quant=False, opt_mode='mse', batch_size=args.batch_size, bias_cal=args.bias_cal,
-                host_resident=args.host_resident)
+                host_resident=args.host_resident, multi_gpu=multi)
     torch.cuda.synchronize()
     print(f'weight reconstruction: {time.time() - t0:.2f}s for {done[0]} units x {args.iters_w} iterations')
     qnn.set_quant_state(weight_quant=True, act_quant=False)
@@ -135,10 +151,12 @@ def main(argv=None):
         with torch.no_grad():
             qnn(cali[:64].to(dev))
         qnn.disable_network_output_quantization()
+        if multi:
+            qnn.synchorize_activation_statistics()             # main_imagenet_dist.py:211: the ranks saw different images
         done[0] = 0
         t0 = time.time()
         recon_model(qnn, cali_data=cali, iters=args.iters_a, act_quant=True, opt_mode='mse', lr=args.lr, p=args.p,
-                    batch_size=args.batch_size)
+                    batch_size=args.batch_size, multi_gpu=multi)
         torch.cuda.synchronize()
         print(f'activation reconstruction: {time.time() - t0:.2f}s for {done[0]} units x {args.iters_a} iterations')
         qnn.set_quant_state(weight_quant=True, act_quant=True)
@@ -146,7 +164,19 @@ def main(argv=None):
             out_wa = qnn(cali[:32].to(dev))
         assert torch.isfinite(out_wa).all()
     sd = qnn.state_dict()
+    if multi:
+        # replicas must have learned the same parameters bit for bit (summed gradients, identical Adam steps)
+        import torch.distributed as td
+        digest = torch.stack([v.detach().double().sum() for k, v in sorted(sd.items()) if v.is_floating_point() and v.is_cuda])
+        both = [torch.empty_like(digest) for _ in range(world)]
+        td.all_gather(both, digest)
+        assert all(torch.equal(both[0], b) for b in both), 'replicas diverged'
+        print(f'{world} replicas identical ({digest.numel()} tensors compared)')
     print(f'done: state_dict with {len(sd)} tensors; W{args.n_bits_w}A{args.n_bits_a if args.act_quant else 32}')
+    if multi:
+        import torch.distributed as td
+        td.barrier()
+        td.destroy_process_group()
     return qnn
 
 

@@ -107,12 +107,23 @@ class QuantModel(nn.Module):
         self._quant_modules()[-1].disable_act_quant = True
 
     def synchorize_activation_statistics(self):
-        """all-average of the activation step sizes across ranks (upstream intent, commented out at
-        quant_model.py:78-83 but still called by Brecq/main_imagenet_dist.py:211)."""
+        """all-average of the activation step sizes across ranks (upstream intent, commented out at quant_model.py:78-83 but
+        still called by Brecq/main_imagenet_dist.py:211). Upstream's text walks the QuantModules only; a block's own output
+        quantiser (quant_block.py:32) is initialised from the rank's images in exactly the same way, and replicas that are to
+        stay identical through the activation phase need it averaged too — so every initialised activation quantiser of the
+        model is covered, and its zero point (an integer per rank: post-ReLU tensors give 0 everywhere) is averaged and
+        rounded."""
         from ..dist import all_average_
-        for m in self._quant_modules():
-            if m.act_quantizer.delta is not None:
-                all_average_(m.act_quantizer.delta.data)
+        from .quant_layer import UniformAffineQuantizer
+        seen = set()
+        for m in self._units():
+            q = getattr(m, 'act_quantizer', None)
+            if isinstance(q, UniformAffineQuantizer) and q.delta is not None and q.inited and id(q) not in seen:
+                seen.add(id(q))
+                all_average_(q.delta.data)
+                if q.zero_point is not None:
+                    all_average_(q.zero_point.data)
+                    q.zero_point.data.round_()
 
     def disable_cache_features(self):
         for m in self._units():

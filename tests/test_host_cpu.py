@@ -252,6 +252,22 @@ unit = D.symmetric_unit_or_none(64, torch.device("cpu"))
 assert unit is None
 D.EXCHANGE = "nccl"
 assert D.symmetric_unit_or_none(64, torch.device("cpu")) is None      # switched off: no collective, no allocation
+# activation statistics: every initialised activation quantiser — the QuantModules' AND the blocks' own — ends up identical on
+# all ranks (Brecq/main_imagenet_dist.py:211; a block quantiser left out keeps the replicas apart for the whole act phase)
+from shiftedscalequantization_b200 import quant as Q, zoo
+torch.manual_seed(1005)
+qnn = Q.QuantModel(zoo.resnet18(num_classes=10), {'n_bits': 2, 'channel_wise': True, 'scale_method': 'mse'},
+                   {'n_bits': 4, 'channel_wise': False, 'scale_method': 'mse', 'leaf_param': True})
+qs = [m.act_quantizer for m in qnn.modules() if isinstance(m, (Q.QuantModule, Q.BaseQuantBlock))]
+assert any(isinstance(m, Q.BaseQuantBlock) for m in qnn.modules()) and len(qs) > 21
+for i, q in enumerate(qs):
+    q.delta = torch.nn.Parameter(torch.tensor(0.1 * (i + 1) * (1 + rk)))
+    q.zero_point = torch.nn.Parameter(torch.tensor(float(rk * (i % 2))))
+    q.inited = True
+qnn.synchorize_activation_statistics()
+for i, q in enumerate(qs):
+    assert abs(float(q.delta) - 0.15 * (i + 1)) < 1e-6, (i, float(q.delta))
+    assert float(q.zero_point) in (0.0, 1.0) and float(q.zero_point) == round(0.5 * (i % 2))    # averaged, then rounded (half to even)
 sys.stdout.write(f"rank {rk} ok\n"); sys.stdout.flush()      # one write per rank: the two ranks share the pipe
 '''
 
