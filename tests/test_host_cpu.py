@@ -369,3 +369,55 @@ def test_k1c_backward_slab_plan_is_one_wave(tmp_path):
     from shiftedscalequantization_b200 import _lib
     # [4096,4096,3,3], S = 3: 36 column blocks -> 16 slabs at 4 CTAs/SM (576 of 592 slots), 8 at 2; the workspace holds the larger plan
     assert _lib.load().ssq_shift_bwd_ws_bytes(4096, 4096, 9, 3, 0) == 16 * 36864 * 3 * 4 + 16
+
+
+_SURFACE_CHECK = r'''
+import os, sys
+root = os.environ["SSQ_ROOT"]
+sys.path[:0] = [os.path.join(root, "compat"), root]          # what run_driver.py arranges
+# main_cifar10.py:4-7, Brecq/main_imagenet.py:8-10, ShiftedScaleQuant.py:4-10 (the import lines of the upstream drivers)
+ns = {}
+exec("from quant import *", ns)
+exec("from common import *", ns)
+exec("from myScaledMethods import *", ns)
+exec("from quant.layer_recon_shiftedScale import *", ns)
+exec("from quant.layer_recon_fused_shiftedScale import *", ns)
+import hubconf
+from data.cifar10 import build_cifar10_data
+from data.imagenet import build_imagenet_data
+from pretrained.PyTorch_CIFAR10.cifar10_models.resnet import resnet18
+from quant.quant_layer import QuantModule, UniformAffineQuantizer
+from quant.quant_block import BaseQuantBlock, QuantBasicBlock
+from quant.channelQuant import ChannelQuant
+from quant.channelQuantMSE import ChannelQuantMSE
+from quant.channelQuantAct import ChannelQuantAct
+from quant.adaptive_rounding import AdaRoundQuantizer
+from quant.data_utils import save_inp_oup_data, save_grad_data
+need = ["QuantModel", "QuantModule", "BaseQuantBlock", "block_reconstruction", "layer_reconstruction",      # quant/__init__.py
+        "loadArgments", "seed_all", "validate_model", "get_train_samples",                                    # common.py
+        "block_recon_shiftedScale", "layer_recon_shiftedScale", "block_recon_fused_shiftedScale"]            # the shifted loops
+missing = [n for n in need if n not in ns]
+assert not missing, missing
+import inspect
+sig = inspect.signature(ns["block_reconstruction"])
+# upstream's positional order (quant/block_recon.py:10-14); the extra keywords come after it
+up = ["model", "block", "cali_data", "batch_size", "iters", "weight", "opt_mode", "asym", "include_act_func", "b_range", "warmup",
+      "act_quant", "lr", "p", "multi_gpu"]
+assert list(sig.parameters)[:len(up)] == up, list(sig.parameters)
+d = {k: v.default for k, v in sig.parameters.items()}
+assert (d["batch_size"], d["iters"], d["weight"], d["opt_mode"], d["asym"], d["b_range"], d["warmup"], d["lr"], d["p"]) == \
+       (32, 20000, 0.01, "mse", False, (20, 2), 0.0, 4e-5, 2.0)
+sig = inspect.signature(ns["layer_reconstruction"])
+assert list(sig.parameters)[:3] == ["model", "layer", "cali_data"] and sig.parameters["weight"].default == 0.001
+print("surface ok")
+'''
+
+
+def test_upstream_import_surface_resolves_through_compat(tmp_path):
+    """the import lines of the reference's drivers (main_cifar10.py:4-7, Brecq/main_imagenet.py:8-10, ShiftedScaleQuant.py:4-10)
+    resolve against compat/ the way run_driver.py arranges sys.path, and the reconstruction entry points keep upstream's
+    positional order and defaults (quant/block_recon.py:10-14, quant/layer_recon.py:10-13)"""
+    script = tmp_path / "surface.py"
+    script.write_text(_SURFACE_CHECK)
+    out = subprocess.run([sys.executable, str(script)], env=dict(os.environ, SSQ_ROOT=ROOT), capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0 and "surface ok" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
