@@ -177,3 +177,20 @@ def test_sparse_row_packing_round_trip():
     rows = [4, 1, 3, 3, 0, 2]
     y = O.sparse_unpack_rows(mask, vals, off, rows, 3072)
     assert np.array_equal(y.view(np.uint32), x[rows].view(np.uint32))
+
+
+def test_oracle_loop_rec_loss_matches_reference_lossfunction():
+    """oracle/ref_loop_torch.rec_loss — the reconstruction term the oracle LOOP uses (mse / fisher_diag / fisher_full,
+    quant/block_recon.py:154-162) — against the values and gradients the real LossFunction produced (tests/golden/loss.npz);
+    the GPU test test_fisher_engine_vs_oracle_loop leans on it"""
+    import torch
+    from oracle import ref_loop_torch as R
+    g = golden("loss").case("conv")
+    tgt, fisher = torch.from_numpy(g["tgt"]), torch.from_numpy(g["fisher"])
+    for mode, val, grad, p in (("mse", "lp2.0", "dlp2.0", 2.0), ("mse", "lp2.4", "dlp2.4", 2.4),
+                               ("fisher_diag", "fdiag", "dfdiag", 2.0), ("fisher_full", "ffull", "dffull", 2.0)):
+        pred = torch.from_numpy(g["pred"]).clone().requires_grad_(True)
+        loss = R.rec_loss(pred, tgt, fisher if mode != "mse" else None, mode, p)
+        loss.backward()
+        assert_close(loss.detach().numpy(), g[val], what=f"{mode} p={p}")
+        assert_close(pred.grad.numpy(), g[grad], rtol=2e-5, what=f"d {mode} p={p}")
