@@ -98,6 +98,19 @@ def test_channelquantmse_module_matches_reference(case):
         ChannelQuantMSE(1.0, uaq, w, opt_mode='mse').init_scale(w)
 
 
+@pytest.mark.parametrize("case", golden("shift_candidates").cases())
+def test_init_shift_candidates_matches_reference(case):
+    """ChannelQuant.init_shift_candidates (quant/channelQuant.py:240-277: rank-vote of the 14 scales i/8 by per-group L2.4 error;
+    upstream's only call is commented out at :281, the method itself runs) against the real reference class
+    (tests/golden/make_golden_shift_candidates.py)"""
+    from shiftedscalequantization_b200.quant.channelQuant import ChannelQuant
+    g = golden("shift_candidates").case(case)
+    w = dev(g["w"])
+    q = ChannelQuant(1.0, make_uaq(int(g["bits"]), g["delta"], g["zp"]), w, shiftTarget=[0.96875, 1.03125, 1.0])
+    q.init_shift_candidates(w.clone())
+    assert [float(s) for s in q.shiftTarget] == [float(s) for s in g["shiftTarget"]], (q.shiftTarget, g["shiftTarget"])
+
+
 def test_channelquantact_modes():
     from shiftedscalequantization_b200.quant.channelQuantAct import ChannelQuantAct
     from shiftedscalequantization_b200.quant.quant_layer import UniformAffineQuantizer
