@@ -369,6 +369,31 @@ def shift_backward(gy, w, delta, zero_point, shifts, p, qmin, qmax, mode, beta=N
 
 
 # ------------------------------------------------------------------------------------------------ K2b
+def init_shift_candidates(w, delta, zero_point, n_levels, sym=False, channel_wise_groups=True):
+    """ChannelQuant.init_shift_candidates, quant/channelQuant.py:240-277 (RUN_CHANNEL_WISE = True): every scale i/8, i = 1..15
+    without 8, is scored per input-channel group by sum |x_q(delta * st) - x|^2.4 over output channels and kernel positions; each
+    group votes 3 / 2 / 1 for its three best scales; the two scales with the most votes (first-come on ties: Python's stable sort)
+    plus 1.0 are returned."""
+    w = _f(w)
+    cands = [i / 8 for i in range(1, 16) if i != 8]
+    qmin, qmax = bounds(n_levels, sym)
+    is_fc = w.ndim == 2
+    table = []
+    for st in cands:
+        d = (_f(delta) * F(st)).astype(F)
+        y, _ = uaq_forward(w, d, zero_point, qmin, qmax)
+        err = pow_scalar(np.abs(y - w), 2.4)
+        table.append(err.sum(axis=0, dtype=F) if is_fc else err.sum(axis=(0, 2, 3), dtype=F))
+    table = np.stack(table, 0)                                       # [14, groups]
+    order = np.argsort(table, axis=0, kind="stable")[:3]
+    scores = {i: 0 for i in range(len(cands))}
+    for col in range(table.shape[1]):
+        for j in range(3):
+            scores[int(order[j, col])] += 3 - j
+    top = [k for k, _v in sorted(scores.items(), key=lambda kv: kv[1], reverse=True)][:2]
+    return [cands[i] for i in top] + [1.0]
+
+
 def inp_scale_search(w, delta, raw_zero_point, n_levels, level, threshold, inp_scale=None):
     """quant/channelQuantMSE.py:70-110 ('max' mode). w [OC,IC,kh,kw] or [OC,IC]; returns inp_scale [1,IC,kh,kw]."""
     w = _f(w); d = _bcast(delta, w)

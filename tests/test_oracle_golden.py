@@ -194,3 +194,11 @@ def test_oracle_loop_rec_loss_matches_reference_lossfunction():
         loss.backward()
         assert_close(loss.detach().numpy(), g[val], what=f"{mode} p={p}")
         assert_close(pred.grad.numpy(), g[grad], rtol=2e-5, what=f"d {mode} p={p}")
+
+
+@pytest.mark.parametrize("case", golden("shift_candidates").cases())
+def test_oracle_init_shift_candidates_matches_reference(case):
+    """oracle restatement of ChannelQuant.init_shift_candidates (quant/channelQuant.py:240-277) against the real class"""
+    g = golden("shift_candidates").case(case)
+    got = O.init_shift_candidates(g["w"], g["delta"], g["zp"], 2 ** int(g["bits"]))
+    assert [float(s) for s in got] == [float(s) for s in g["shiftTarget"]], (got, g["shiftTarget"])
