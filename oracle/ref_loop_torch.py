@@ -153,7 +153,7 @@ def recon_weight_loop(unit, cached_inps, cached_outs, idx_table, iters, weight=0
         total = rec + rnd
         total.backward()
         opt.step()
-        losses.append(float(total))
+        losses.append(float(total.detach()) if torch.is_tensor(total) else float(total))
     return alphas, losses
 
 

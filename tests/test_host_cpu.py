@@ -421,3 +421,73 @@ def test_upstream_import_surface_resolves_through_compat(tmp_path):
     script.write_text(_SURFACE_CHECK)
     out = subprocess.run([sys.executable, str(script)], env=dict(os.environ, SSQ_ROOT=ROOT), capture_output=True, text=True, timeout=240)
     assert out.returncode == 0 and "surface ok" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
+
+
+# ------------------------------------------------------------------------------------------- oracle loop, other families
+@pytest.mark.parametrize("tag,arch,bits,pick", [("r50", "resnet50", 4, lambda q: q.model.layer1[0]),
+                                                ("rx32", "regnetx_3200m", 2, lambda q: q.model.s2.b1)])
+def test_oracle_loop_reproduces_reference_bottleneck_blocks(tag, arch, bits, pick):
+    """the oracle's loop restatement (bottleneck kind, grouped 3x3 convolutions, downsample branch) against the REAL reference's
+    block_reconstruction on a ResNet-50 bottleneck and a RegNetX-3200M block (tests/golden/families.npz; 16 iterations, asym=True).
+    Everything runs on the CPU: the FP block outputs come from the seeded zoo model, the block inputs from the same model with every
+    weight replaced by the oracle's nearest-rounding fake-quant ('max' init, 8-bit stem) — what the reference's quantised prefix
+    computes — and the index stream is regenerated from the seed."""
+    from oracle import ref_loop_torch as R
+    from oracle import ssq_oracle as O
+    from shiftedscalequantization_b200 import quant as Q, zoo
+    from shiftedscalequantization_b200.engine import index_table
+    g = golden("families")
+    cali = torch.from_numpy(g[f"{tag}.cali"])
+    torch.manual_seed(1005)
+    cnn = zoo.build(arch, **({"num_classes": 10} if arch.startswith("resnet") else {})).eval()
+    qnn = Q.QuantModel(cnn, {'n_bits': bits, 'channel_wise': True, 'scale_method': 'max'}, dict(AQ)).eval()
+    qnn.set_first_last_layer_to_8bit()
+    block = pick(qnn)
+    named = [(n, m) for n, m in block.named_modules() if isinstance(m, Q.QuantModule)]
+    for n, m in named:
+        assert_exact(m.org_weight.reshape(-1)[:16].numpy(), g[f"{tag}.{n}.probe_w"], f"{n}: seeded weights")
+
+    def capture(model_input):
+        seen = {}
+        h = block.register_forward_hook(lambda m, i, o: seen.update(inp=i[0].detach().clone(), out=o.detach().clone()))
+        qnn.set_quant_state(False, False)                    # QuantModule.forward then uses org_weight: plain torch on the CPU
+        with torch.no_grad():
+            qnn(model_input)
+        h.remove()
+        return seen["inp"], seen["out"]
+
+    _, outs = capture(cali)                                  # FP targets
+    # quantised prefix: nearest-rounding fake-quant of every layer's weights, by the oracle ('max' init in Python doubles)
+    mods = [m for m in qnn.modules() if isinstance(m, Q.QuantModule)]
+    saved = [m.org_weight for m in mods]
+    for m in mods:
+        nb = m.weight_quantizer.n_bits
+        w = m.weight.detach().numpy()
+        rows = w.reshape(w.shape[0], -1)
+        d, z, _raw = zip(*[O.max_init(r, nb) for r in rows])
+        shape = (-1,) + (1,) * (w.ndim - 1)
+        d = np.array(d, np.float32).reshape(shape); z = np.array(z, np.float32).reshape(shape)
+        if m in [mm for _n, mm in named]:
+            n = [nn for nn, mm in named if mm is m][0]
+            assert_exact(d, g[f"{tag}.{n}.delta"], f"{n}: delta of the oracle's max init"); assert_exact(z, g[f"{tag}.{n}.zp"], f"{n}: zero point")
+        y, _codes = O.uaq_forward(w, d, z, 0, 2 ** nb - 1)
+        m.org_weight = torch.from_numpy(y)
+    inps, _ = capture(cali)
+    for m, w in zip(mods, saved):
+        m.org_weight = w
+    layers = {}
+    for n, m in named:
+        act = {"ReLU": "relu", "ReLU6": "relu6"}.get(type(m.activation_function).__name__)
+        layers[n] = dict(weight=m.org_weight.detach(), bias=None if m.org_bias is None else m.org_bias.detach(), conv=dict(m.fwd_kwargs),
+                         act=act, delta=torch.from_numpy(g[f"{tag}.{n}.delta"]), zero_point=torch.from_numpy(g[f"{tag}.{n}.zp"]),
+                         n_levels=2 ** bits)
+    unit = {"kind": "bottleneck", "layers": layers, "tail_act": "relu"}
+    torch.manual_seed(277)
+    tab = index_table(32, 16, 16)
+    alphas, losses = R.recon_weight_loop(unit, inps, outs, tab, 16, weight=0.01, b_range=(20, 2), warmup=0.2)
+    assert np.isfinite(losses).all()
+    for n, _m in named:
+        a, ref = alphas[n].detach().numpy(), g[f"{tag}.{n}.alpha"]
+        moved = np.abs(ref - R.init_alpha(layers[n]["weight"], layers[n]["delta"]).numpy()).max()
+        assert moved > 5e-3
+        assert_close(a, ref, rtol=1e-5, what=f"{tag} alpha {n}: oracle loop vs the reference's block_reconstruction")
