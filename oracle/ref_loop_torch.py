@@ -119,7 +119,8 @@ def rec_loss(pred, tgt, grad=None, mode="mse", p=2.0):
 
 
 def recon_weight_loop(unit, cached_inps, cached_outs, idx_table, iters, weight=0.01, b_range=(20, 2), warmup=0.2,
-                      p=2.0, alphas=None, start_count=0, t_max=None, state=None, opt_mode="mse", cached_grads=None):
+                      p=2.0, alphas=None, start_count=0, t_max=None, state=None, opt_mode="mse", cached_grads=None,
+                      train_affine=False):
     """the weight-rounding loop: returns (alphas, losses). `idx_table[i]` is the mini-batch of iteration i.
     t_max/start_count let a caller run a slice of a longer schedule (the CPU baseline times iterations from the
     middle of the 20 000-iteration schedule, where the regulariser is live and b is non-integer); `state` (a dict) keeps
@@ -129,7 +130,14 @@ def recon_weight_loop(unit, cached_inps, cached_outs, idx_table, iters, weight=0
         alphas = {n: init_alpha(s["weight"].detach(), s["delta"].detach()).requires_grad_(True) for n, s in L.items()}
     opt = state.get("opt") if state is not None else None
     if opt is None:
-        opt = torch.optim.Adam(list(alphas.values()))
+        params = list(alphas.values())
+        if train_affine:
+            # README --bias_cal: the output-channel affine of every layer (alpha_out / beta_out, quant/quant_layer.py:231-238, applied
+            # at :258-259 by _layer above) joins the same optimiser (upstream's commented lines, layer_recon_fused_shiftedScale.py:67-68)
+            for s_ in L.values():
+                s_["alpha_out"].requires_grad_(True); s_["beta_out"].requires_grad_(True)
+                params += [s_["alpha_out"], s_["beta_out"]]
+        opt = torch.optim.Adam(params)
         if state is not None:
             state["opt"] = opt
     t_max = iters if t_max is None else t_max

@@ -491,3 +491,37 @@ def test_oracle_loop_reproduces_reference_bottleneck_blocks(tag, arch, bits, pic
         moved = np.abs(ref - R.init_alpha(layers[n]["weight"], layers[n]["delta"]).numpy()).max()
         assert moved > 5e-3
         assert_close(a, ref, rtol=1e-5, what=f"{tag} alpha {n}: oracle loop vs the reference's block_reconstruction")
+
+
+def test_oracle_loop_reproduces_reference_bias_cal_trajectory():
+    """README --bias_cal on the CPU: the oracle loop with every layer's output affine (gamma^z, varphi^z = alpha_out, beta_out) in the
+    optimiser against the real reference's forward / autograd / LossFunction / Adam (tests/golden/bias_cal.npz: ResNet-18 layer2.0 with
+    its downsample branch, 16 iterations, the reference's own cached features and index stream)"""
+    from oracle import ref_loop_torch as R
+    from oracle import ssq_oracle as O
+    from shiftedscalequantization_b200 import quant as Q, zoo
+    g = golden("bias_cal")
+    torch.manual_seed(1005)
+    qnn = Q.QuantModel(zoo.resnet18(num_classes=10).eval(), {'n_bits': 2, 'channel_wise': True, 'scale_method': 'max'}, dict(AQ)).eval()
+    qnn.set_first_last_layer_to_8bit()
+    assert_exact(torch.randn(32, 3, 16, 16).numpy(), g["cali"], "seeded calibration tensor (same RNG position as the golden run)")
+    block = qnn.model.layer2[0]
+    layers = {}
+    for n, m in [(n, m) for n, m in block.named_modules() if isinstance(m, Q.QuantModule)]:
+        w = m.org_weight.detach().numpy()
+        d, z, _raw = zip(*[O.max_init(r, 2) for r in w.reshape(w.shape[0], -1)])
+        mk = lambda v: torch.from_numpy(np.array(v, np.float32).reshape(-1, 1, 1, 1))
+        act = {"ReLU": "relu"}.get(type(m.activation_function).__name__)
+        layers[n] = dict(weight=m.org_weight.detach(), bias=None if m.org_bias is None else m.org_bias.detach(), conv=dict(m.fwd_kwargs), act=act,
+                         delta=mk(d), zero_point=mk(z), n_levels=4, alpha_out=torch.ones(1, w.shape[0], 1, 1), beta_out=torch.zeros(1, w.shape[0], 1, 1))
+    assert sorted(layers) == ["conv1", "conv2", "downsample"]
+    unit = {"kind": "basic", "layers": layers, "tail_act": "relu"}
+    iters = int(g["iters"])
+    alphas, losses = R.recon_weight_loop(unit, torch.from_numpy(g["inps"]), torch.from_numpy(g["outs"]), torch.from_numpy(g["idx"]), iters,
+                                         weight=0.01, b_range=(20, 2), warmup=0.2, train_affine=True)
+    assert_close(np.array(losses), g["losses"], rtol=1e-5, what="loss trace with the affine in the optimiser")
+    for n in layers:
+        assert_close(alphas[n].detach().numpy(), g[f"{n}.alpha"], rtol=1e-5, what=f"alpha {n}")
+        assert_close(layers[n]["alpha_out"].detach().numpy(), g[f"{n}.alpha_out"], rtol=1e-5, what=f"gamma {n}")
+        assert_close(layers[n]["beta_out"].detach().numpy(), g[f"{n}.beta_out"], rtol=1e-5, what=f"varphi {n}")
+        assert float((layers[n]["alpha_out"].detach() - 1).abs().max()) > 5e-3                     # the affine really moved
