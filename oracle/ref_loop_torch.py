@@ -182,7 +182,7 @@ def recon_act_loop(unit, cached_inps, cached_outs, idx_table, iters, act_state, 
         err.backward()
         opt.step()
         sch.step()
-        losses.append(float(err))
+        losses.append(float(err.detach()))
     return losses
 
 

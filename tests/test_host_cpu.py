@@ -525,3 +525,27 @@ def test_oracle_loop_reproduces_reference_bias_cal_trajectory():
         assert_close(layers[n]["alpha_out"].detach().numpy(), g[f"{n}.alpha_out"], rtol=1e-5, what=f"gamma {n}")
         assert_close(layers[n]["beta_out"].detach().numpy(), g[f"{n}.beta_out"], rtol=1e-5, what=f"varphi {n}")
         assert float((layers[n]["alpha_out"].detach() - 1).abs().max()) > 5e-3                     # the affine really moved
+
+
+def test_oracle_act_loop_reproduces_reference_activation_phase():
+    """the oracle's activation-phase loop (LSQ step sizes, Adam lr 4e-4 + cosine annealing, lp p = 2.4; hard-rounded weights) against
+    the REAL reference's block_reconstruction(act_quant=True) on the CPU (tests/golden/act_phase.npz, make_golden_act_phase.py):
+    same cached features, same index stream, same initial step sizes -> same learned step sizes"""
+    from oracle import ref_loop_torch as R
+    g = golden("act_phase")
+    layers, alphas = {}, {}
+    for n, act in (("conv1", "relu"), ("conv2", None)):
+        layers[n] = dict(weight=torch.from_numpy(g[f"{n}.weight"]), bias=torch.from_numpy(g[f"{n}.bias"]),
+                         conv=dict(stride=1, padding=1, dilation=1, groups=1), act=act, delta=torch.from_numpy(g[f"{n}.delta"]),
+                         zero_point=torch.from_numpy(g[f"{n}.zp"]), n_levels=4)
+        alphas[n] = torch.from_numpy(g[f"{n}.alpha"])
+    unit = {"kind": "basic", "layers": layers, "tail_act": "relu"}
+    act_state = {k: (torch.from_numpy(g[f"{k}.act_delta0"]).clone().requires_grad_(True), torch.from_numpy(g[f"{k}.act_zp"]),
+                     int(g[f"{k}.act_levels"])) for k in ("conv1", "__block__")}
+    losses = R.recon_act_loop(unit, torch.from_numpy(g["inps"]), torch.from_numpy(g["outs"]), torch.from_numpy(g["idx"]), int(g["iters"]),
+                              act_state, alphas, lr=4e-4, p=2.4)
+    assert np.isfinite(losses).all()
+    for k in act_state:
+        d0, d1, got = float(g[f"{k}.act_delta0"]), float(g[f"{k}.act_delta1"]), float(act_state[k][0])
+        assert abs(d1 - d0) > 1e-3                                   # the reference's step size moved ...
+        assert abs(got - d1) <= 1e-5 * abs(d1), (k, d0, d1, got)     # ... and the oracle's ends up in the same place
