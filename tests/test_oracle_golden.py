@@ -202,3 +202,14 @@ def test_oracle_init_shift_candidates_matches_reference(case):
     g = golden("shift_candidates").case(case)
     got = O.init_shift_candidates(g["w"], g["delta"], g["zp"], 2 ** int(g["bits"]))
     assert [float(s) for s in got] == [float(s) for s in g["shiftTarget"]], (got, g["shiftTarget"])
+
+
+def test_oracle_channelquantact_modes_match_reference():
+    """ChannelQuantAct (quant/channelQuantAct.py:45-54): 'none' = the plain UAQ forward, 'adaround' with hard rounding = the AdaRound
+    hard forward on the activation with the caller's beta; the oracle's two functions against the real class (channelquantact.npz)"""
+    g = golden("channelquantact")
+    assert bool(g["soft_raises"])                                    # upstream's soft branch calls an undefined get_soft_round
+    y_none, _ = O.uaq_forward(g["x"], g["delta"], g["zp"], 0, 15)
+    assert_exact(y_none, g["y_none"], "'none' mode")
+    y_hard, _ = O.adaround_forward(g["x"], g["beta"], g["delta"], g["zp"], 0, 15, soft=False)
+    assert_exact(y_hard, g["y_hard"], "'adaround' mode, hard rounding")
