@@ -14,7 +14,14 @@ description of a unit (so it carries no product code):
   LossFunction                       quant/block_recon.py:142-182
   LinearTempDecay                    quant/block_recon.py:185-202
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
-Pinned against the real reference's layer_reconstruction / block loop by tests/golden/recon_loop.npz.
+Pinned against the real reference run on the CPU (tests/test_host_cpu.py, tests/test_oracle_golden.py):
+  recon_loop.npz   block loop body + the real layer_reconstruction (12 iterations): losses and alphas to 1e-6
+  families.npz     the real block_reconstruction on a ResNet-50 bottleneck and a RegNetX-3200M block (16 iterations): alphas to 1e-5
+  bias_cal.npz     alpha_out / beta_out in the optimiser (train_affine=True): loss trace, alphas, gamma, varphi to 1e-5
+  act_phase.npz    the real block_reconstruction(act_quant=True): learned activation step sizes to 1e-5
+  loss.npz         rec_loss (mse / fisher_diag / fisher_full): values and gradients
+  long_horizon.npz 2 000 iterations of the real block_reconstruction: hard codes 100 % identical
+                   (tests/golden/check_oracle_long_horizon.py; 5 minutes, run by hand)
 """
 from __future__ import annotations
 
