@@ -430,6 +430,52 @@ def test_act_phase_engine_vs_oracle_loop():
         assert abs(got - ref) <= 2e-3 * abs(ref - d0[k]) + 1e-5 * abs(ref), (k, d0[k], ref, got)
 
 
+def test_act_phase_engine_matches_reference_activation_phase():
+    """the engine's activation phase against the REAL reference's block_reconstruction(act_quant=True) (tests/golden/act_phase.npz:
+    ResNet-18 layer1.0, the reference's own cached features, index stream, AdaRound alphas and initial step sizes; 16 iterations of
+    Adam lr 4e-4 + cosine annealing on lp p = 2.4): the learned step sizes of conv1's output and of the block's output"""
+    from conftest import golden
+    from shiftedscalequantization_b200.engine import ReconEngine
+    from shiftedscalequantization_b200.quant.adaptive_rounding import AdaRoundQuantizer
+    g = golden("act_phase")
+    torch.manual_seed(1005)
+    from shiftedscalequantization_b200 import quant as Q, zoo
+    cnn = zoo.resnet18(num_classes=10).cuda().eval()
+    qnn = Q.QuantModel(cnn, dict(WQ, scale_method='max'), dict(AQ)).cuda().eval()
+    qnn.set_first_last_layer_to_8bit()
+    cali = torch.from_numpy(g["cali"])
+    qnn.set_quant_state(True, False)
+    with torch.no_grad():
+        qnn(cali.cuda())
+    block = qnn.model.layer1[0]
+    named = [(n, m) for n, m in block.named_modules() if isinstance(m, Q.QuantModule)]
+    for n, m in named:                                   # the reference's weight-phase result, as it stood when its act phase began
+        assert_exact(m.org_weight.detach().cpu().numpy(), g[f"{n}.weight"], f"{n}: seeded, BN-folded weights")
+        assert_exact(m.weight_quantizer.delta.detach().cpu().numpy(), g[f"{n}.delta"], f"{n}: delta")
+        m.weight_quantizer = AdaRoundQuantizer(uaq=m.weight_quantizer, round_mode='learned_hard_sigmoid', weight_tensor=m.org_weight.data)
+        with torch.no_grad():
+            m.weight_quantizer.alpha.copy_(torch.from_numpy(g[f"{n}.alpha"]).cuda())
+        m.weight_quantizer.soft_targets = False
+    aq = {"conv1": block.conv1.act_quantizer, "__block__": block.act_quantizer}
+    for k, q in aq.items():
+        q.delta = torch.nn.Parameter(torch.from_numpy(g[f"{k}.act_delta0"]).cuda())
+        q.zero_point = torch.nn.Parameter(torch.from_numpy(g[f"{k}.act_zp"]).cuda())
+        q.inited = True
+        assert q.n_levels == int(g[f"{k}.act_levels"])
+    qnn.set_quant_state(False, False); block.set_quant_state(True, True)
+    mods = [m for _n, m in named]
+    iters, bs = int(g["iters"]), int(g["bs"])
+    eng = ReconEngine(block, mods, torch.from_numpy(g["inps"]).cuda(), torch.from_numpy(g["outs"]).cuda(), None, act_quant=True, iters=iters,
+                      weight=0.0, p=2.4, lr=4e-4, batch_size=bs,
+                      act_quantizers=[block.act_quantizer] + [m.act_quantizer for m in mods if m.act_quantizer.delta is not None],
+                      use_graph=True, idx_table=torch.from_numpy(g["idx"]), verbose=False)
+    eng.run(); eng.close()
+    for k, q in aq.items():
+        d0, ref, got = float(g[f"{k}.act_delta0"]), float(g[f"{k}.act_delta1"]), float(q.delta.detach())
+        assert abs(ref - d0) > 1e-3
+        assert abs(got - ref) <= 2e-3 * abs(ref - d0) + 1e-5 * abs(ref), (k, d0, ref, got)
+
+
 def test_bias_cal_matches_reference_autograd():
     """README --bias_cal: gamma^z / varphi^z (alpha_out / beta_out) learned with the AdaRound alphas. Golden = the real
     reference's forward/autograd/LossFunction/Adam with those parameters added to the optimiser
